@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s of the ExaMiniMD LJ hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one MD timestep (initial_integrate -> halo update or, every 20th step, exchange + sort +
+halo + binning + neighbor build -> LJ force -> final_integrate) over the configuration BASELINE.json
+quotes the metric on: LJ fcc 2 048 000 atoms (in.lj with `region 0 80 0 80 0 80`), cutoff 2.5, skin
+0.3, half CSR list, one B200.  K should be a multiple of 20 so the timed region holds its share of
+re-neighborings (it starts right after one).
+
+  value     atom-steps/s, state resident in HBM, timed with CUDA events on the module stream
+  e2e       same metric through the host-buffer session API: every step copies x,v,f from pinned
+            host memory to the device, advances one step and copies x,v,f (+ id,type after a
+            re-sort) back
+  roofline  dominant kernel (LJ force incl. its fused zero-f): algorithmic bytes of SURVEY.md 8(d)
+            / CUDA-event duration of that kernel, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference: the CPU oracle restatement of the reference (OpenMP, all host
+            cores) on a bounded sample of the same workload (in.lj 256 000 atoms)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+DECK = REPO / "input" / "in.lj"
+METRIC = "atom_steps_per_s_lj_2M_half_csr"
+UNIT = "atom-steps/s"
+WORKLOAD = "LJ fcc 2048000 atoms (in.lj, region 80^3), rc 2.5 + skin 0.3, half CSR list, re-neighbor every 20 steps, newton off"
+
+
+def peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text())["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def run_oracle(region, nsteps, threads=None):
+    exe = REPO / "oracle" / "oracle_md_omp"
+    if not exe.exists():
+        subprocess.run(["make", "-C", str(REPO / "oracle"), "oracle_md_omp"], check=True, capture_output=True)
+    cores = threads or os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close", OMP_PLACES="cores")
+    cmd = [str(exe), "-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--region", *map(str, region),
+           "--nsteps", str(nsteps)]
+    t0 = time.time()
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True).stdout
+    m = re.search(r"^(\d+) (\d+) \| (\S+) (\S+) (\S+) (\S+) (\S+) \| (\S+) (\S+) (\S+) PERFORMANCE", out, re.M)
+    return {"value": float(m.group(9)), "atoms": int(m.group(2)), "loop_s": float(m.group(3)), "cores": cores,
+            "wall_s": time.time() - t0}
+
+
+def cpu_baseline(nsteps):
+    r = run_oracle((40, 40, 40), nsteps)
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"oracle_md_omp (OpenMP restatement of the reference), in.lj 256000 atoms x {nsteps} steps, half CSR, "
+                      f"loop {r['loop_s']:.2f} s"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    r = run_oracle((40, 40, 40), total)
+    ms = 1e3 * r["loop_s"] / total
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "256000-atom in.lj sample of the workload per step (CPU-bounded)"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                             "sample": f"in.lj 256000 atoms x {total} steps, half CSR, OpenMP oracle"},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device = device
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.splitlines():
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--region", type=int, nargs=3, default=None, help="override the lattice (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import examinimd_b200 as emd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+
+    W = max(args.warmup, 3)
+    K = args.steps
+    region = tuple(args.region) if args.region else (80, 80, 80)
+    # TODO(round 1): N>1 = 3-D brick decomposition through CommNCCL; until it lands every rank runs
+    # its own replica of the single-GPU workload ("replicas only") and the aggregate is the sum.
+    argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--comm-type", "SERIAL",
+            "--region", *map(str, region)]
+    app = emd.App(argv, device=local_rank)
+    L = emd.lib()
+    ctx = app.ctx
+    n_atoms = app.get("N")
+
+    def barrier():
+        app.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    # ---- resident throughput ------------------------------------------------------------
+    app.advance(W)
+    # land on a step just after a re-neighboring so K steps hold K/20 rebuilds
+    rate = app.get("exchange_rate")
+    app.advance((-app.get("step")) % rate)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = app.launches()
+    ms = C.c_float()
+    emd.check(L.emd_ctx_tic(ctx))
+    app.advance(K)
+    emd.check(L.emd_ctx_toc(ctx, C.byref(ms)))
+    launches = app.launches() - launches0
+    barrier()
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    step_ms = float(t_ms.item()) / K
+    value = world * n_atoms * K / (float(t_ms.item()) * 1e-3)
+
+    # ---- dominant kernel: LJ force (with its fused zero-f), timed alone on the live state ----
+    n_local, n_ghost = app.get("N_local"), app.get("N_ghost")
+    total_neighs = app.get("total_neighs")
+    nbar = total_neighs / n_local
+    g = (n_local + n_ghost) / n_local
+    lst = emd.NeighList(app.device_ptr("row_map"), None, app.device_ptr("neighs"), 1)
+    P = C.c_void_p
+    reps = 20
+    # inputs (x 49 MB + list 336 MB + f) exceed L2 (126 MB): no flush needed between launches
+    fk_ms = []
+    for _ in range(3):
+        emd.check(L.emd_force_lj_compute(ctx, P(app.device_ptr("x")), P(app.device_ptr("type")), P(app.device_ptr("f")), n_local,
+                                         n_local + n_ghost, C.byref(lst), 1, 1))
+    for _ in range(reps):
+        emd.check(L.emd_ctx_tic(ctx))
+        emd.check(L.emd_force_lj_compute(ctx, P(app.device_ptr("x")), P(app.device_ptr("type")), P(app.device_ptr("f")), n_local,
+                                         n_local + n_ghost, C.byref(lst), 1, 1))
+        emd.check(L.emd_ctx_toc(ctx, C.byref(ms)))
+        fk_ms.append(ms.value)
+    force_ms = statistics.mean(fk_ms)
+    force_bytes = n_local * (8 + 4 * nbar + 28 * g + 48 * g + 24 * g)  # row_map + list + x,type + f RMW + zero-f
+    peak, peak_kind = peaks()
+    achieved = force_bytes / (force_ms * 1e-3) / 1e9
+    b_lj = 208 + 100 * g + 52 * (g - 1) + 4 * nbar
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "lj_force_kernel<half> + zero_rows_kernel", "kernel_ms": force_ms, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_atom": force_bytes / n_local, "nbar": nbar, "g": g,
+                "whole_step": {"B_LJ_bytes_per_atom_step": b_lj, "achieved_gbs": b_lj * value / world / 1e9,
+                               "frac": b_lj * value / world / 1e9 / peak}}
+
+    # ---- e2e: host buffers in and out every step ---------------------------------------------
+    st = app.download()
+    hx = torch.from_numpy(st["x"]).pin_memory(); hv = torch.from_numpy(st["v"]).pin_memory(); hf = torch.from_numpy(st["f"]).pin_memory()
+    hid = torch.from_numpy(st["id"]).pin_memory(); htype = torch.from_numpy(st["type"]).pin_memory()
+    Ke = min(K, 40)
+    h2d = 72 * n_local
+    d2h = 72 * n_local
+    d2h_rebuild = 8 * n_local
+
+    def e2e_step():
+        emd.check(L.emd_app_upload(app.handle, P(hx.data_ptr()), P(hv.data_ptr()), P(hf.data_ptr())))
+        app.advance(1)
+        resort = app.get("step") % rate == 0
+        emd.check(L.emd_app_download(app.handle, P(hid.data_ptr()) if resort else None, P(htype.data_ptr()) if resort else None, None,
+                                     P(hx.data_ptr()), P(hv.data_ptr()), P(hf.data_ptr())))
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    emd.check(L.emd_ctx_tic(ctx))
+    for _ in range(Ke):
+        e2e_step()
+    emd.check(L.emd_ctx_toc(ctx, C.byref(ms)))
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    t_e = torch.tensor([max(ms.value * 1e-3, e2e_wall)], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_atoms * Ke / float(t_e.item())
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + d2h_rebuild / rate,
+           "steps": Ke, "api": "emd_app_upload -> emd_app_advance(1) -> emd_app_download (pinned host x,v,f)"}
+
+    T, PE, KE = app.thermo()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD if not args.region else f"LJ fcc region {region} (debug override)",
+                       "atoms_per_gpu": n_atoms, "ghosts": n_ghost, "neigh_entries": total_neighs,
+                       "l2": "state + list (>400 MB) exceed the 126 MB L2; no flush between steps",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} replicas (CommNCCL pending)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "thermo_after": {"T": T, "PE": PE, "E": PE + KE}}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(40)
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    app.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,51 @@
+#include "force_lj_neigh.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+static void fail(const char *what) {
+  fprintf(stderr, "ForceLJNeigh: %s: %s\n", what, emd_last_error());
+  exit(1);
+}
+
+ForceLJNeigh::ForceLJNeigh(char **args, System *system, bool half_neigh_) : Force(args, system, half_neigh_), sys(system) {
+  ntypes = system->ntypes;
+  use_stackparams = (ntypes <= MAX_TYPES_STACKPARAMS);
+  lj1.assign((size_t)ntypes * ntypes, 0.0);
+  lj2.assign((size_t)ntypes * ntypes, 0.0);
+  cutsq.assign((size_t)ntypes * ntypes, 0.0);
+}
+
+// src/force_types/force_lj_neigh_impl.h:57-98.  With <= 12 types every pair_coeff line fills
+// the WHOLE table (reference quirk :66-74), otherwise the (t1,t2)/(t2,t1) entries.
+void ForceLJNeigh::init_coeff(int nargs, char **args) {
+  const int t1 = atoi(args[1]) - 1, t2 = atoi(args[2]) - 1;
+  const double eps = atof(args[3]), sigma = atof(args[4]), cut = atof(args[5]);
+  const double a = 48.0 * eps * pow(sigma, 12.0), b = 24.0 * eps * pow(sigma, 6.0), c = cut * cut;
+  if (use_stackparams) {
+    for (size_t k = 0; k < lj1.size(); k++) { lj1[k] = a; lj2[k] = b; cutsq[k] = c; }
+  } else {
+    lj1[t1 * ntypes + t2] = lj1[t2 * ntypes + t1] = a;
+    lj2[t1 * ntypes + t2] = lj2[t2 * ntypes + t1] = b;
+    cutsq[t1 * ntypes + t2] = cutsq[t2 * ntypes + t1] = c;
+  }
+  if (emd_force_lj_set_params(sys->ctx, ntypes, lj1.data(), lj2.data(), cutsq.data())) fail("set_params");
+}
+
+// src/force_types/force_lj_neigh_impl.h:100-126
+void ForceLJNeigh::compute(System *system, Binning *, Neighbor *neighbor) {
+  const emd_neigh_list l = neighbor->list_view();
+  if (emd_force_lj_compute(system->ctx, system->x, system->type, system->f, system->N_local,
+                           system->N_local + system->N_ghost, &l, half_neigh, /*zero_f=*/1))
+    fail("compute");
+}
+
+// src/force_types/force_lj_neigh_impl.h:128-156
+T_F_FLOAT ForceLJNeigh::compute_energy(System *system, Binning *, Neighbor *neighbor) {
+  const emd_neigh_list l = neighbor->list_view();
+  double pe = 0.0;
+  if (emd_force_lj_energy(system->ctx, system->x, system->type, system->N_local, &l, half_neigh, &pe)) fail("energy");
+  return pe;
+}
+
+const char *ForceLJNeigh::name() { return half_neigh ? "ForceLJNeighHalf" : "ForceLJNeighFull"; }

@@ -1,0 +1,17 @@
+// integrator.h -- abstract time integrator (plugin surface of src/integrator.h:45-55).
+#pragma once
+#include "types.h"
+#include "system.h"
+
+class Integrator {
+public:
+  System *system;
+  T_V_FLOAT timestep_size;
+  Integrator(System *s) : system(s), timestep_size(0.0) {}
+  virtual ~Integrator() {}
+  virtual void initial_integrate() {}
+  virtual void final_integrate() {}
+  virtual const char *name() { return "IntegratorNone"; }
+};
+
+#include "modules_integrator.h"

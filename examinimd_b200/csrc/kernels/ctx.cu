@@ -1,0 +1,200 @@
+// ctx.cu -- context lifetime, error string, memory helpers, exclusive scan.
+#include "common.cuh"
+#include <cstdarg>
+
+namespace emd {
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------ exclusive scan (int)
+// Tile = 2048 ints per CTA (256 threads x 8).  Pass 1 reduces each tile, pass 2 scans the tile
+// sums inside one CTA (serial carry over 2048-wide chunks), pass 3 rescans each tile with its
+// offset.  2*n*4 B read + n*4 B written; used only on rebuild steps (bins, rows, halo flags).
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *smem /*>=kScanThreads/32+1*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < (kScanThreads / 32) ? smem[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < (kScanThreads / 32)) smem[lane] = winc - w; // exclusive warp offsets
+    if (lane == (kScanThreads / 32) - 1) smem[kScanThreads / 32] = winc;
+  }
+  __syncthreads();
+  int excl = inc - v + smem[warp];
+  *total = smem[kScanThreads / 32];
+  __syncthreads();
+  return excl;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_reduce(const int *__restrict__ in, int n, int *__restrict__ tile_sums) {
+  __shared__ int sm[kScanThreads / 32 + 1];
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++)
+    if (base + k < n) s += in[base + k];
+  int total;
+  block_exclusive_scan(s, &total, sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(int *tile_sums, int ntiles, int *d_total) {
+  __shared__ int sm[kScanThreads / 32 + 1];
+  int carry = 0;
+  for (int base = 0; base < ntiles; base += kScanThreads) {
+    int idx = base + threadIdx.x;
+    int v = idx < ntiles ? tile_sums[idx] : 0;
+    int total;
+    int ex = block_exclusive_scan(v, &total, sm);
+    if (idx < ntiles) tile_sums[idx] = ex + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && d_total) *d_total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_final(const int *in, int *out, int n, const int *__restrict__ tile_sums) {
+  __shared__ int sm[kScanThreads / 32 + 1];
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  int total;
+  int ex = block_exclusive_scan(s, &total, sm) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+}
+
+int exclusive_scan_int(emd_ctx *ctx, const int *d_in, int *d_out, int n, int *d_total) {
+  if (n <= 0) {
+    if (d_total) EMD_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int), ctx->stream));
+    return 0;
+  }
+  const int ntiles = (n + kScanTile - 1) / kScanTile;
+  if (ctx->s_scan.ensure(sizeof(int) * (size_t)ntiles)) return 1;
+  int *sums = ctx->s_scan.as<int>();
+  EMD_LAUNCH(ctx, scan_tile_reduce, ntiles, kScanThreads, 0, d_in, n, sums);
+  EMD_LAUNCH(ctx, scan_tile_sums, 1, kScanThreads, 0, sums, ntiles, d_total);
+  EMD_LAUNCH(ctx, scan_tile_final, ntiles, kScanThreads, 0, d_in, d_out, n, sums);
+  return 0;
+}
+} // namespace emd
+
+using namespace emd;
+
+extern "C" {
+
+const char *emd_last_error(void) { return emd::g_err; }
+int emd_abi_version(void) { return EMD_ABI_VERSION; }
+
+int emd_ctx_create(emd_ctx **out, int device, void *stream) {
+  if (!out) { set_error("emd_ctx_create: out == NULL"); return 1; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("emd_ctx_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    return 1;
+  }
+  if (device < 0 || device >= ndev) { set_error("emd_ctx_create: device %d out of range (%d devices)", device, ndev); return 1; }
+  EMD_CUDA(cudaSetDevice(device));
+  emd_ctx *c = new emd_ctx();
+  c->device = device;
+  if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+  else { EMD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  EMD_CUDA(cudaEventCreate(&c->ev0));
+  EMD_CUDA(cudaEventCreate(&c->ev1));
+  EMD_CUDA(cudaMallocHost((void **)&c->h_pinned, 64 * sizeof(double)));
+  cudaDeviceProp prop;
+  EMD_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  return 0;
+}
+
+void emd_ctx_destroy(emd_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->s_a.release(); c->s_b.release(); c->s_c.release(); c->s_scan.release();
+  if (c->d_lj_tables) cudaFree(c->d_lj_tables);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void *emd_ctx_stream(emd_ctx *c) { return (void *)c->stream; }
+int emd_ctx_sync(emd_ctx *c) { EMD_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+unsigned long long emd_ctx_launch_count(emd_ctx *c) { return c->launches; }
+int emd_ctx_tic(emd_ctx *c) { EMD_CUDA(cudaEventRecord(c->ev0, c->stream)); return 0; }
+int emd_ctx_toc(emd_ctx *c, float *h_ms) {
+  EMD_CUDA(cudaEventRecord(c->ev1, c->stream));
+  EMD_CUDA(cudaEventSynchronize(c->ev1));
+  EMD_CUDA(cudaEventElapsedTime(h_ms, c->ev0, c->ev1));
+  return 0;
+}
+
+int emd_event_create(void **ev) {
+  cudaEvent_t e;
+  EMD_CUDA(cudaEventCreate(&e));
+  *ev = (void *)e;
+  return 0;
+}
+int emd_event_destroy(void *ev) { if (ev) EMD_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return 0; }
+int emd_event_record(emd_ctx *c, void *ev) { EMD_CUDA(cudaEventRecord((cudaEvent_t)ev, c->stream)); return 0; }
+int emd_event_elapsed_ms(void *a, void *b, float *h_ms) {
+  EMD_CUDA(cudaEventSynchronize((cudaEvent_t)b));
+  EMD_CUDA(cudaEventElapsedTime(h_ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return 0;
+}
+
+int emd_malloc(void **d_ptr, unsigned long long bytes) { EMD_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1)); return 0; }
+int emd_free(void *d_ptr) { if (d_ptr) EMD_CUDA(cudaFree(d_ptr)); return 0; }
+int emd_memcpy_h2d(emd_ctx *c, void *d, const void *h, unsigned long long bytes) {
+  EMD_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+int emd_memcpy_d2h(emd_ctx *c, void *h, const void *d, unsigned long long bytes) {
+  EMD_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  EMD_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int emd_memcpy_d2d(emd_ctx *c, void *d, const void *s, unsigned long long bytes) {
+  EMD_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+int emd_memset_zero(emd_ctx *c, void *d, unsigned long long bytes) {
+  EMD_CUDA(cudaMemsetAsync(d, 0, bytes, c->stream));
+  return 0;
+}
+
+} // extern "C"

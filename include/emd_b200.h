@@ -1,0 +1,174 @@
+/*
+ * emd_b200.h -- C ABI of the B200-native ExaMiniMD hot path (libemd_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the ExaMiniMD checkout).
+ * All `d_` pointers are DEVICE pointers on the context's GPU; `h_` pointers are host pointers.
+ * Calls are stream-ordered on the context's stream; a call that returns a value through an
+ * `h_` pointer synchronises that stream first (as the reference does with deep_copy-to-host).
+ * Every function returns 0 on success, non-zero on error (message: emd_last_error()).
+ * There is no CPU fallback: without a CUDA device emd_ctx_create fails.
+ *
+ * Per-atom arrays use the reference layout (src/types.h:88-113, src/system.h:59-93):
+ * x,v,f = double[N][3] row-major, type,id = int[N], q = double[N], mass = double[ntypes].
+ */
+#ifndef EMD_B200_H
+#define EMD_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMD_ABI_VERSION 1
+
+typedef struct emd_ctx emd_ctx;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to launch on, or NULL to create a private non-blocking stream. */
+int emd_ctx_create(emd_ctx **out, int device, void *stream);
+void emd_ctx_destroy(emd_ctx *ctx);
+void *emd_ctx_stream(emd_ctx *ctx);
+int emd_ctx_sync(emd_ctx *ctx);                 /* replaces Kokkos::fence() */
+const char *emd_last_error(void);
+int emd_abi_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+unsigned long long emd_ctx_launch_count(emd_ctx *ctx);
+/* device event timers on the context's stream: ms between tic and toc (synchronises) */
+int emd_ctx_tic(emd_ctx *ctx);
+int emd_ctx_toc(emd_ctx *ctx, float *h_ms);
+/* opaque device events on the context's stream, for per-phase device timers
+ * (the reference's Kokkos::Timer pairs, src/examinimd.cpp:183-189) without host syncs */
+int emd_event_create(void **ev);
+int emd_event_destroy(void *ev);
+int emd_event_record(emd_ctx *ctx, void *ev);
+int emd_event_elapsed_ms(void *ev_begin, void *ev_end, float *h_ms); /* synchronises on ev_end */
+/* plain device memory helpers for hosts without a CUDA runtime binding of their own */
+int emd_malloc(void **d_ptr, unsigned long long bytes);
+int emd_free(void *d_ptr);
+int emd_memcpy_h2d(emd_ctx *ctx, void *d_dst, const void *h_src, unsigned long long bytes);
+int emd_memcpy_d2h(emd_ctx *ctx, void *h_dst, const void *d_src, unsigned long long bytes);
+int emd_memcpy_d2d(emd_ctx *ctx, void *d_dst, const void *d_src, unsigned long long bytes);
+int emd_memset_zero(emd_ctx *ctx, void *d_dst, unsigned long long bytes); /* Kokkos::deep_copy(view,0) */
+
+/* ---- binning: BinningKKSort::create_binning, src/binning_types/binning_kksort.cpp:71-140 */
+typedef struct {
+  int nbinx, nbiny, nbinz, nhalo;          /* src/binning.h:52 (nbin* INCLUDE the 2*nhalo halo bins) */
+  double minx, maxx, miny, maxy, minz, maxz; /* src/binning.h:53 */
+} emd_bin_geom;
+
+/* host arithmetic of binning_kksort.cpp:77-99, same expressions in the same order */
+int emd_binning_geometry(const double sub_domain[3], const double sub_lo[3], const double sub_hi[3],
+                         double dx_in, double dy_in, double dz_in, int halo_depth, emd_bin_geom *out);
+
+/* Kokkos::BinSort<...,BinOp3D>::create_permute_vector (binning_kksort.cpp:103-111) +
+ * AssignOffsets (:118-125).  d_x points at the first atom of the binned range and n is the
+ * range length, so permute indices are relative to the range start like the reference's.
+ * Outputs: d_bincount/d_binoffsets int[nbinx*nbiny*nbinz] flattened (x slowest, z fastest =
+ * the reference's 3-D views), d_permute int[n].  Within a bin atoms are in ascending index
+ * order (the reference's 1-thread arrival order).  Atoms whose bin falls outside the grid are
+ * an error (reference: undefined behaviour). */
+int emd_binning_build(emd_ctx *ctx, const double *d_x, int n, const emd_bin_geom *geom,
+                      int *d_bincount, int *d_binoffsets, int *d_permute);
+
+/* BinSort::sort(x), (v), (f), (type), (id), (q) (binning_kksort.cpp:126-138) as ONE gather
+ * kernel: out[i] = in[permute[i]].  in/out must not alias (the host classes swap buffers). */
+int emd_binning_permute(emd_ctx *ctx, const int *d_permute, int n,
+                        const double *d_x_in, const double *d_v_in, const double *d_f_in,
+                        const int *d_type_in, const int *d_id_in, const double *d_q_in,
+                        double *d_x_out, double *d_v_out, double *d_f_out,
+                        int *d_type_out, int *d_id_out, double *d_q_out);
+
+/* ---- neighbor lists -------------------------------------------------------------------- */
+/* NeighborCSR<>::create_neigh_list, src/neighbor_types/neighbor_csr.h:370-435.
+ * Step 1 (count_neighbors_{full,half} :176-216/:258-309 + create_offsets :359-368):
+ * fills d_row_map[0..n_local] and returns the total entry count in *h_total (host sync,
+ * as neighbor_csr.h:413-414).  Step 2 (fill_neigh_list_{full,half} :219-255/:312-358) writes
+ * d_entries[0..total).  Rows are in the reference's serial traversal order (27 stencil bins
+ * bx-1..bx+1/by/bz, permute order inside each bin), so they compare equal entry by entry with
+ * the 1-thread reference, not just as sets.
+ * d_type may be NULL (the reference loads type_j but never uses it). */
+int emd_neigh_csr_count(emd_ctx *ctx, const double *d_x, int n_local, const emd_bin_geom *geom,
+                        const int *d_bincount, const int *d_binoffsets, const int *d_permute,
+                        double neigh_cut, int half_neigh, int comm_newton,
+                        int *d_row_map, int *h_total);
+int emd_neigh_csr_fill(emd_ctx *ctx, const double *d_x, int n_local, const emd_bin_geom *geom,
+                       const int *d_bincount, const int *d_binoffsets, const int *d_permute,
+                       double neigh_cut, int half_neigh, int comm_newton,
+                       const int *d_row_map, int *d_entries);
+
+/* Neighbor2D<>::create_neigh_list fill pass, src/neighbor_types/neighbor_2d.h:175-278,304-318.
+ * One pass into d_neighs[(n_local+1)][maxneighs] (row-major, stride maxneighs); entries beyond
+ * maxneighs are dropped but still counted in d_num_neighs, and *h_max_count returns the largest
+ * row count so the caller can apply the reference's resize rule (maxneighs = max*1.2, :322-326)
+ * and call again. */
+int emd_neigh_2d_fill(emd_ctx *ctx, const double *d_x, int n_local, const emd_bin_geom *geom,
+                      const int *d_bincount, const int *d_binoffsets, const int *d_permute,
+                      double neigh_cut, int half_neigh, int comm_newton,
+                      int maxneighs, int *d_num_neighs, int *d_neighs, int *h_max_count);
+
+/* A neighbor list as the force kernels consume it (the duck-typed list concept of
+ * neighbor_csr.h:81-124 / neighbor_2d.h:80-120): row i starts at d_neighs + row_start(i).
+ * CSR: d_row_map != NULL, row i = [row_map[i], row_map[i+1]).
+ * 2D : d_row_map == NULL, row i = [i*stride, i*stride + d_num_neighs[i]). */
+typedef struct {
+  const int *d_row_map;
+  const int *d_num_neighs;
+  const int *d_neighs;
+  int stride;
+} emd_neigh_list;
+
+/* ---- LJ force: ForceLJNeigh<>, src/force_types/force_lj_neigh_impl.h -------------------- */
+/* init_coeff (:57-98) result, host arrays [ntypes][ntypes]: lj1 = 48 eps sigma^12,
+ * lj2 = 24 eps sigma^6, cutsq = rc^2.  Copied into the context. */
+int emd_force_lj_set_params(emd_ctx *ctx, int ntypes, const double *h_lj1, const double *h_lj2,
+                            const double *h_cutsq);
+/* compute (:100-126; functors :161-206 full, :208-254 half).  Accumulates onto d_f (+=), which
+ * the caller has zeroed like examinimd.cpp:232; with zero_f != 0 the kernel itself overwrites
+ * rows [0,n_local) and zeroes rows [n_local,n_all) first, replacing that deep_copy.
+ * half: f_j -= for every listed j including ghosts (:245-247). */
+int emd_force_lj_compute(emd_ctx *ctx, const double *d_x, const int *d_type, double *d_f,
+                         int n_local, int n_all, const emd_neigh_list *list, int half_neigh,
+                         int zero_f);
+/* compute_energy (:128-156; functors :256-296 full, :298-343 half): shifted PE, host result */
+int emd_force_lj_energy(emd_ctx *ctx, const double *d_x, const int *d_type, int n_local,
+                        const emd_neigh_list *list, int half_neigh, double *h_pe);
+
+/* ---- integrator: IntegratorNVE, src/integrator_nve.cpp:41-121 --------------------------- */
+/* dtf = 0.5*dt/mvv2e, dtv = dt (:41-44).  Bit-exact with the reference's CPU arithmetic
+ * (separate multiply and add, no FMA contraction). */
+int emd_nve_initial_integrate(emd_ctx *ctx, double *d_x, double *d_v, const double *d_f,
+                              const int *d_type, const double *d_mass, int n_local,
+                              double dtf, double dtv);
+int emd_nve_final_integrate(emd_ctx *ctx, double *d_v, const double *d_f, const int *d_type,
+                            const double *d_mass, int n_local, double dtf);
+
+/* ---- single-process periodic comm: CommSerial, src/comm_types/comm_serial.{h,cpp} ------- */
+/* exchange (comm_serial.cpp:47-54, TagExchangeSelf comm_serial.h:94-107) */
+int emd_comm_wrap(emd_ctx *ctx, double *d_x, int n_local, const double domain[3]);
+/* one phase of exchange_halo (comm_serial.cpp:62-94, TagHaloSelf comm_serial.h:110-181).
+ * Scans atoms [0,n_scan) for x_dim >= hi-depth (even phase) / <= lo+depth (odd phase), appends
+ * a shifted copy (x,v,q,id,type) of each hit at ghost_begin+slot and records the source index
+ * in d_pack_indicies[slot]; slots are in ascending source index (the 1-thread arrival order).
+ * *h_count returns the hit count (host sync, as comm_serial.cpp:73).  Nothing is written beyond
+ * `capacity` atoms / `pack_capacity` indices: the caller grows and redoes, as the reference. */
+int emd_comm_halo_phase(emd_ctx *ctx, int phase, double *d_x, double *d_v, double *d_q, int *d_id,
+                        int *d_type, int n_scan, int ghost_begin, int capacity,
+                        int *d_pack_indicies, int pack_capacity, const double domain[3],
+                        const double sub_lo[3], const double sub_hi[3], double comm_depth,
+                        int *h_count);
+/* one phase of update_halo (comm_serial.cpp:99-110, TagHaloUpdateSelf comm_serial.h:183-197) */
+int emd_comm_halo_update_phase(emd_ctx *ctx, int phase, double *d_x, double *d_v, double *d_q,
+                               int *d_id, int *d_type, const int *d_pack_indicies, int count,
+                               int ghost_begin, const double domain[3]);
+/* one phase of update_force (comm_serial.cpp:112-127, TagHaloForceSelf comm_serial.h:199-213) */
+int emd_comm_force_fold_phase(emd_ctx *ctx, double *d_f, const int *d_pack_indicies, int count,
+                              int ghost_begin);
+
+/* ---- thermo: Temperature/KinE functor, src/property_temperature.h:55-57 ------------------ */
+/* sum_i m[type_i] * |v_i|^2 over [0,n_local) (deterministic two-stage reduction), host result */
+int emd_reduce_mv2(emd_ctx *ctx, const double *d_v, const int *d_type, const double *d_mass,
+                   int n_local, double *h_sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

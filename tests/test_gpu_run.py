@@ -1,0 +1,113 @@
+"""GPU whole-run parity (-m gpu): the application (C++ host classes + CUDA kernels, driven through
+the session C ABI and through the ExaMiniMD binary with --dumpbinary) free-running against the
+CPU oracle: per-atom x, v, f within 1e-10 of the global RMS after 100 steps, thermo to print
+precision, and size-independent invariants at BASELINE.json's full 2 M-atom size."""
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle_py import OracleMD, REPO
+
+DECK = REPO / "input" / "in.lj"
+TOL = 1e-10
+
+
+def by_id(d, n=None):
+    o = np.argsort(d["id"][:n])
+    return {k: np.asarray(v)[:n][o] for k, v in d.items()}
+
+
+def compare(app_state, md, tol=TOL):
+    n = md.geti("N_local")
+    ref = by_id({k: md.arr(k) for k in ("id", "x", "v", "f")}, n)
+    cur = by_id(app_state)
+    np.testing.assert_array_equal(cur["id"], ref["id"])
+    L = md.getd("domain_x")
+    dx = cur["x"] - ref["x"]
+    dx -= np.round(dx / L) * L  # an atom may be wrapped on one side and not yet on the other
+    assert np.abs(dx).max() / np.sqrt((ref["x"] ** 2).mean()) < tol
+    assert np.abs(cur["v"] - ref["v"]).max() / np.sqrt((ref["v"] ** 2).mean()) < tol
+    assert np.abs(cur["f"] - ref["f"]).max() / np.sqrt((ref["f"] ** 2).mean()) < tol
+
+
+@pytest.mark.parametrize("neigh,iteration", [("CSR", "NEIGH_HALF"), ("CSR", "NEIGH_FULL"), ("2D", "NEIGH_FULL"), ("2D", "NEIGH_HALF")])
+def test_100_steps_vs_oracle(emd, neigh, iteration):
+    region = (20, 20, 20)  # 32 000 atoms, rebuilds at steps 20..100
+    md = OracleMD.from_deck(DECK, neigh, iteration, region=region)
+    app = emd.App(["-il", str(DECK), "--neigh-type", neigh, "--force-iteration", iteration, "--comm-type", "SERIAL",
+                   "--region", *map(str, region)])
+    assert app.get("N") == md.geti("N") and app.get("N_ghost") == md.geti("N_ghost")
+    compare(app.download(), md)  # step 0: bit-identical lattice, forces ~ 0
+    T0, PE0, KE0 = app.thermo()
+    assert (f"{T0:.6f}", f"{PE0:.6f}", f"{PE0 + KE0:.6f}") == ("1.400000", "-6.332812", "-4.232820")
+    for _ in range(5):
+        app.advance(20)
+        md.step(20)
+        compare(app.download(), md)
+        Ta, PEa, KEa = app.thermo()
+        To, PEo, KEo = md.thermo()
+        assert abs(Ta - To) < 1e-9 and abs(PEa - PEo) < 1e-9 and abs(KEa - KEo) < 1e-9
+    assert app.get("N_ghost") == md.geti("N_ghost")
+    if neigh == "CSR":
+        assert app.get("total_neighs") == md.geti("total_neighs")
+    assert abs((PEa + KEa) - (PE0 + KE0)) < 2e-3  # NVE energy drift envelope of the oracle itself
+    app.close(); md.close()
+
+
+def test_binary_dump_and_correctness_flags(emd, tmp_path):
+    """the ExaMiniMD executable with the reference's own record/replay flags (README.md:99-107)."""
+    region = ["--region", "10", "10", "10", "--nsteps", "40"]
+    refdir = tmp_path / "ref"; refdir.mkdir()
+    md = OracleMD.from_deck(DECK, "CSR", "NEIGH_HALF", region=(10, 10, 10))
+    md.L.orcf_dump(md.h, str(refdir).encode(), 0)
+    for s in range(1, 41):
+        md.step(1)
+        if s % 20 == 0:
+            md.L.orcf_dump(md.h, str(refdir).encode(), s)
+    out = tmp_path / "correctness.dat"
+    mine = tmp_path / "mine"; mine.mkdir()
+    r = subprocess.run([str(emd.EXE_PATH), "-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF",
+                        "--comm-type", "SERIAL", *region, "--dumpbinary", "20", str(mine), "--correctness", "20", str(refdir), str(out)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "Using: ForceLJNeighHalf NeighborCSR CommSerial BinningKKSort" in r.stdout
+    assert "\n0 1.400000 -6.332812 -4.232820 " in r.stdout
+    assert "PERFORMANCE" in r.stdout
+    rows = [l.split() for l in out.read_text().splitlines() if not l.startswith("#")]
+    assert [int(r_[0]) for r_ in rows] == [0, 20, 40]
+    for r_ in rows:  # absolute norms / max deltas of r, v, f against the oracle's dumps
+        assert max(float(t) for t in r_[1:]) < 1e-8
+    # dump format: int n; id; type; q; x; v; f (examinimd.cpp:337-343)
+    raw = (mine / "output.0000000040.000").read_bytes()
+    n = struct.unpack("i", raw[:4])[0]
+    assert n == 4000 and len(raw) == 4 + n * 88
+    md.close()
+
+
+def test_full_size_invariants(emd):
+    """BASELINE configs[1]: LJ fcc 2 048 000 atoms, half CSR list.  Too big for the oracle in seconds,
+    so check size-independent properties: known step-0 answers, 39+ neighbors per atom, momentum and
+    energy conservation across two rebuilds, sorted/consistent CSR."""
+    import torch
+    app = emd.App(["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--comm-type", "SERIAL",
+                   "--region", "80", "80", "80"])
+    n = app.get("N")
+    assert n == 2048000 and (app.get("nbinx"), app.get("nbiny"), app.get("nbinz")) == (49, 49, 49)
+    T0, PE0, KE0 = app.thermo()
+    assert (f"{T0:.6f}", f"{PE0:.6f}") == ("1.400000", "-6.332812")
+    st = app.download()
+    assert np.abs(st["f"]).max() < 1e-10
+    app.advance(45)
+    T, PE, KE = app.thermo()
+    assert abs((PE + KE) - (PE0 + KE0)) < 2e-3
+    st = app.download()
+    assert np.array_equal(np.sort(st["id"]), np.arange(1, n + 1, dtype=np.int32))  # a permutation of all atoms
+    p = st["v"].sum(0) * 2.0
+    assert np.abs(p).max() / n < 1e-12  # momentum stays zero (Newton's third law in the half list)
+    total = app.get("total_neighs")
+    assert total >= 39 * n * 0.9
+    app.close()
