@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--region", type=int, nargs=3, default=None, help="override the lattice (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--iteration", default="NEIGH_HALF", help="force iteration (debug; the headline config is NEIGH_HALF)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -161,7 +162,8 @@ def main():
     region = tuple(args.region) if args.region else (80, 80, 80)
     # TODO(round 1): N>1 = 3-D brick decomposition through CommNCCL; until it lands every rank runs
     # its own replica of the single-GPU workload ("replicas only") and the aggregate is the sum.
-    argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--comm-type", "SERIAL",
+    half = 1 if args.iteration == "NEIGH_HALF" else 0
+    argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", args.iteration, "--comm-type", "SERIAL",
             "--region", *map(str, region)]
     app = emd.App(argv, device=local_rank)
     L = emd.lib()
@@ -208,11 +210,11 @@ def main():
     fk_ms = []
     for _ in range(3):
         emd.check(L.emd_force_lj_compute(ctx, P(app.device_ptr("x")), P(app.device_ptr("type")), P(app.device_ptr("f")), n_local,
-                                         n_local + n_ghost, C.byref(lst), 1, 1))
+                                         n_local + n_ghost, C.byref(lst), half, 1))
     for _ in range(reps):
         emd.check(L.emd_ctx_tic(ctx))
         emd.check(L.emd_force_lj_compute(ctx, P(app.device_ptr("x")), P(app.device_ptr("type")), P(app.device_ptr("f")), n_local,
-                                         n_local + n_ghost, C.byref(lst), 1, 1))
+                                         n_local + n_ghost, C.byref(lst), half, 1))
         emd.check(L.emd_ctx_toc(ctx, C.byref(ms)))
         fk_ms.append(ms.value)
     force_ms = statistics.mean(fk_ms)

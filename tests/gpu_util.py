@@ -24,7 +24,10 @@ def ptr(t):
 
 
 def new_ctx():
-    return emd.Context(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    # torch's default stream has handle 0, which the C ABI reads as "create a private stream"; pass
+    # cudaStreamLegacy (0x1) instead so the kernels are ordered with torch's own copies/allocations
+    s = torch.cuda.current_stream().cuda_stream
+    return emd.Context(torch.cuda.current_device(), s if s else 1)
 
 
 def geom_from(d):

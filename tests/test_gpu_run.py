@@ -31,7 +31,9 @@ def compare(app_state, md, tol=TOL):
     dx -= np.round(dx / L) * L  # an atom may be wrapped on one side and not yet on the other
     assert np.abs(dx).max() / np.sqrt((ref["x"] ** 2).mean()) < tol
     assert np.abs(cur["v"] - ref["v"]).max() / np.sqrt((ref["v"] ** 2).mean()) < tol
-    assert np.abs(cur["f"] - ref["f"]).max() / np.sqrt((ref["f"] ** 2).mean()) < tol
+    # on the perfect lattice (step 0) every force is zero to roundoff (~1e-13), so the scale is floored at 1
+    # (LJ units; the liquid's RMS force is ~10) -- SURVEY.md section 7, hard part 6
+    assert np.abs(cur["f"] - ref["f"]).max() / max(np.sqrt((ref["f"] ** 2).mean()), 1.0) < tol
 
 
 @pytest.mark.parametrize("neigh,iteration", [("CSR", "NEIGH_HALF"), ("CSR", "NEIGH_FULL"), ("2D", "NEIGH_FULL"), ("2D", "NEIGH_HALF")])
