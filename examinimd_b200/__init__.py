@@ -77,6 +77,17 @@ _SIGS = {
     "emd_force_lj_set_params": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "emd_force_lj_compute": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NeighList), C.c_int, C.c_int]),
     "emd_force_lj_energy": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(NeighList), C.c_int, C.POINTER(C.c_double)]),
+    "emd_tiles_create": (C.c_int, [C.POINTER(_P)]),
+    "emd_tiles_destroy": (None, [_P]),
+    "emd_tiles_valid": (C.c_int, [_P]),
+    "emd_tiles_invalidate": (None, [_P]),
+    "emd_tiles_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int)]),
+    "emd_neigh_tiles_build": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(BinGeom), _P, _P, _P, C.c_double]),
+    "emd_neigh_tiles_count": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
+    "emd_neigh_tiles_fill_csr": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "emd_neigh_tiles_fill_2d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)]),
+    "emd_force_lj_compute_tiles": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
     "emd_nve_initial_integrate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double]),
     "emd_nve_final_integrate": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double]),
     "emd_comm_wrap": (C.c_int, [_P, _P, C.c_int, _D3]),
@@ -90,6 +101,7 @@ _SIGS = {
     "emd_app_destroy": (None, [_P]),
     "emd_app_ctx": (_P, [_P]),
     "emd_app_advance": (C.c_int, [_P, C.c_int]),
+    "emd_app_advance_timed": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "emd_app_thermo": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emd_app_get": (C.c_longlong, [_P, C.c_char_p]),
     "emd_app_download": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
@@ -175,6 +187,12 @@ class App:
 
     def advance(self, nsteps: int) -> None:
         check(lib().emd_app_advance(self._h, nsteps), "emd_app_advance")
+
+    def advance_timed(self, nsteps: int) -> dict:
+        """advance with the reference's phase timers; seconds per phase over the nsteps"""
+        out = (C.c_double * 4)()
+        check(lib().emd_app_advance_timed(self._h, nsteps, out), "emd_app_advance_timed")
+        return {"force": out[0], "neigh": out[1], "comm": out[2], "other": out[3]}
 
     def sync(self) -> None:
         check(lib().emd_ctx_sync(self.ctx), "emd_ctx_sync")

@@ -39,6 +39,15 @@ int emd_app_advance(emd_app *a, int nsteps) {
   return 0;
 }
 
+int emd_app_advance_timed(emd_app *a, int nsteps, double *h_seconds4) {
+  PhaseTimers tm(a->md->system->ctx);
+  for (int k = 0; k < nsteps; k++) a->md->step_once(++a->md->current_step, &tm);
+  tm.flush();
+  h_seconds4[0] = tm.seconds[PhaseTimers::FORCE]; h_seconds4[1] = tm.seconds[PhaseTimers::NEIGH];
+  h_seconds4[2] = tm.seconds[PhaseTimers::COMM]; h_seconds4[3] = tm.seconds[PhaseTimers::OTHER];
+  return 0;
+}
+
 int emd_app_thermo(emd_app *a, double *T, double *PE, double *KE) {
   a->md->thermo(T, PE, KE);
   return 0;
@@ -97,6 +106,7 @@ void *emd_app_device_ptr(emd_app *a, const char *what) {
   if (!strcmp(what, "bincount")) return a->md->binning->bincount;
   if (!strcmp(what, "binoffsets")) return a->md->binning->binoffsets;
   if (!strcmp(what, "permute")) return a->md->binning->permute_vector;
+  if (!strcmp(what, "tiles")) return a->md->neighbor->tiles();
   const emd_neigh_list l = a->md->neighbor->list_view();
   if (!strcmp(what, "row_map")) return const_cast<int *>(l.d_row_map);
   if (!strcmp(what, "num_neighs")) return const_cast<int *>(l.d_num_neighs);

@@ -34,6 +34,15 @@ void ForceLJNeigh::init_coeff(int nargs, char **args) {
 
 // src/force_types/force_lj_neigh_impl.h:100-126
 void ForceLJNeigh::compute(System *system, Binning *, Neighbor *neighbor) {
+  // fast path (kernels/tiles.cu): same forces on the owned atoms, every pair evaluated from both
+  // sides out of shared memory.  A half list with newton on needs the ghost forces: generic kernel.
+  emd_tiles *t = neighbor->tiles();
+  if (t && !(half_neigh && comm_newton)) {
+    if (comm_newton && system->N_ghost > 0) // ghost rows stay zero, as after the reference's deep_copy(f,0)
+      emd_memset_zero(system->ctx, system->f + 3 * (size_t)system->N_local, sizeof(T_F_FLOAT) * 3 * (size_t)system->N_ghost);
+    if (emd_force_lj_compute_tiles(system->ctx, t, system->x, system->type, system->f, nullptr)) fail("compute (tiles)");
+    return;
+  }
   const emd_neigh_list l = neighbor->list_view();
   if (emd_force_lj_compute(system->ctx, system->x, system->type, system->f, system->N_local,
                            system->N_local + system->N_ghost, &l, half_neigh, /*zero_f=*/1))
@@ -42,8 +51,13 @@ void ForceLJNeigh::compute(System *system, Binning *, Neighbor *neighbor) {
 
 // src/force_types/force_lj_neigh_impl.h:128-156
 T_F_FLOAT ForceLJNeigh::compute_energy(System *system, Binning *, Neighbor *neighbor) {
-  const emd_neigh_list l = neighbor->list_view();
   double pe = 0.0;
+  emd_tiles *t = neighbor->tiles();
+  if (t && !(half_neigh && comm_newton)) {
+    if (emd_force_lj_compute_tiles(system->ctx, t, system->x, system->type, system->f, &pe)) fail("energy (tiles)");
+    return pe;
+  }
+  const emd_neigh_list l = neighbor->list_view();
   if (emd_force_lj_energy(system->ctx, system->x, system->type, system->N_local, &l, half_neigh, &pe)) fail("energy");
   return pe;
 }

@@ -9,6 +9,17 @@ static void fail(const char *who, const char *what) {
   exit(1);
 }
 
+bool Neighbor::build_tiles(System *system, Binning *binning, T_X_FLOAT neigh_cut) {
+  static const bool disabled = getenv("EMD_NO_TILES") && atoi(getenv("EMD_NO_TILES")) != 0;
+  if (disabled) { if (tile_lists) emd_tiles_invalidate(tile_lists); return false; }
+  if (!tile_lists && emd_tiles_create(&tile_lists)) fail("Neighbor", "tiles create");
+  const emd_bin_geom g = binning->geom();
+  const int rc = emd_neigh_tiles_build(system->ctx, tile_lists, system->x, system->N_local, system->N_local + system->N_ghost, &g,
+                                       binning->bincount, binning->binoffsets, binning->permute_vector, neigh_cut);
+  if (rc != 0 && rc != 3) fail("Neighbor", "tiles build");
+  return rc == 0;
+}
+
 // src/neighbor_types/neighbor_csr.h:370-435
 void NeighborCSR::create_neigh_list(System *system, Binning *binning, bool half_neigh_, bool) {
   const T_INT N_local = system->N_local;
@@ -17,6 +28,21 @@ void NeighborCSR::create_neigh_list(System *system, Binning *binning, bool half_
   }
   const emd_bin_geom g = binning->geom();
   int total = 0;
+  if (build_tiles(system, binning, neigh_cut)) {
+    // fast path: exact CSR rows emitted from the tile lists (same rows, same order)
+    if (emd_neigh_tiles_count(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_offsets.ptr, &total))
+      fail("NeighborCSR", "tiles count");
+    if (neighs.extent() < (size_t)total) {
+      if (!neighs.alloc((size_t)total + total / 16)) fail("NeighborCSR", "alloc entries");
+    }
+    if (emd_neigh_tiles_fill_csr(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_offsets.ptr, neighs.ptr))
+      fail("NeighborCSR", "tiles fill");
+    neigh_list.row_map = neigh_offsets.ptr;
+    neigh_list.entries = neighs.ptr;
+    neigh_list.N_local = N_local;
+    neigh_list.total = total;
+    return;
+  }
   if (emd_neigh_csr_count(system->ctx, system->x, N_local, &g, binning->bincount, binning->binoffsets,
                           binning->permute_vector, neigh_cut, half_neigh_, comm_newton, neigh_offsets.ptr, &total))
     fail("NeighborCSR", "count");
@@ -41,6 +67,7 @@ void Neighbor2D::create_neigh_list(System *system, Binning *binning, bool half_n
   const emd_bin_geom g = binning->geom();
   fill_passes = 0;
   bool resize;
+  const bool fast = build_tiles(system, binning, neigh_cut);
   do {
     if (rows_cap < (size_t)N_local + 1 || cols_cap != (size_t)neigh_list.maxneighs) {
       rows_cap = (size_t)N_local + 1;
@@ -48,7 +75,11 @@ void Neighbor2D::create_neigh_list(System *system, Binning *binning, bool half_n
       if (!neighs_buf.alloc(rows_cap * cols_cap)) fail("Neighbor2D", "alloc neighs");
     }
     int max_count = 0;
-    if (emd_neigh_2d_fill(system->ctx, system->x, N_local, &g, binning->bincount, binning->binoffsets,
+    if (fast) {
+      if (emd_neigh_tiles_fill_2d(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_list.maxneighs, num_neighs_buf.ptr,
+                                  neighs_buf.ptr, &max_count))
+        fail("Neighbor2D", "tiles fill");
+    } else if (emd_neigh_2d_fill(system->ctx, system->x, N_local, &g, binning->bincount, binning->binoffsets,
                           binning->permute_vector, neigh_cut, half_neigh_, comm_newton, neigh_list.maxneighs,
                           num_neighs_buf.ptr, neighs_buf.ptr, &max_count))
       fail("Neighbor2D", "fill");

@@ -1,0 +1,612 @@
+// tiles.cu -- the B200 fast path of the neighbor build and the LJ force: cell TILES staged in
+// shared memory.
+//
+// Why (measured on B200, profiles/r01_microbench_b200.json): a thread-per-atom walk over a CSR
+// list is bound by the L1/L2 gather of x[j] (184 G rows/s) and, for Newton-3 half lists, by
+// REDG.F64 (224 Gop/s; shared-memory FP64 atomics are CAS loops) -- 14 % FP64-pipe use at
+// 0.96 ms for 2 M atoms.  FP64 FMA issue (36.8 TFLOP/s) is the cheap resource on this part, so
+// the fast path recomputes each pair from both sides instead of scattering -f to j, and serves
+// every x[j] from shared memory:
+//
+//   * the interior bins of BinningKKSort's grid are grouped into tiles of tx*ty*tz cells; one
+//     CTA owns one tile and stages the coordinates of the (tx+2)(ty+2)(tz+2) cells around it
+//     ONCE (coalesced: atoms are cell-sorted), ~6x re-read instead of 78 gathers per atom;
+//   * the neighbor build emits, next to the reference's CSR/2D list, a tile-local FULL adjacency
+//     in ELL layout (uint16 slot numbers into the staged array, 4 entries packed per 8-byte
+//     word, atom-major so a warp reads 256 contiguous bytes per 4 neighbors).  It is filled by
+//     an FP32 pre-filter with a conservative radius (warp = one cell, broadcast LDS of the
+//     candidate, 7 FP32 ops per pair instead of 8 FP64); the exact FP64 inclusion test of the
+//     reference (rsq <= cut*cut, no FMA contraction; half-list owner rule) is applied when the
+//     CSR/2D list is emitted from it, so the API-visible list is bit-identical to the reference
+//     and the ELL list is a superset that differs only by pairs within 1e-4 of the list radius
+//     (which the force kernel's own cutoff test rejects);
+//   * the force kernel walks the ELL rows with x[j] from shared memory, f_i in registers, one
+//     coalesced store per atom, no atomics, no zero-f pass; the summation order is the
+//     reference's serial row order.
+//
+// Replaces, when applicable (list radius <= bin width, tile fits in shared memory):
+//   NeighborCSR/2D::create_neigh_list  src/neighbor_types/neighbor_csr.h:370-435, neighbor_2d.h:280-331
+//   ForceLJNeigh::compute/_energy      src/force_types/force_lj_neigh_impl.h:100-156
+// The generic kernels (neighbor.cu, force_lj.cu) remain the path for half lists with newton on
+// (ghost forces are needed there) and for tiles that do not fit.
+#include "common.cuh"
+#include <cstdint>
+#include <cmath>
+#include <algorithm>
+
+using namespace emd;
+
+namespace {
+
+constexpr int kMaxStagedCells = 400;
+constexpr int kMaxInteriorCells = 128;
+constexpr int kFilterThreads = 256;
+
+struct TileArgs {
+  int nbx, nby, nbz, nhalo; // bin grid incl. halo bins
+  int tx, ty, tz;           // interior cells per tile
+  int ntx, nty, ntz;        // tiles per dimension
+  int stride;               // atom slots (= threads of the per-atom kernels) per tile, multiple of 32
+  int maxrow;               // ELL row capacity, multiple of 4
+  int cap;                  // staged-atom capacity of the shared-memory arrays
+  int n_local;
+  const int *bincount, *binoffsets, *permute;
+  const double *x;
+  const int *type;
+  double ox, oy, oz; // bin grid origin
+  double wx, wy, wz; // bin widths
+  unsigned short *ell; // [ntiles][maxrow/4][stride][4]
+  int *nell;           // [ntiles][stride]
+  int *flags;          // [0] overflow bits (1 staged, 2 interior, 4 row)  [1] max row  [2] max staged  [3] max interior
+};
+
+struct TileCtx {
+  int tile;
+  int bx0, by0, bz0;  // first interior cell of the tile (grid coordinates)
+  int sxn, syn, szn;  // staged cells per dimension
+  int ncs, nci;       // staged / interior cell counts
+  int total, n_int;   // staged atoms / atoms in interior cells
+};
+
+// in-place exclusive scan of arr[0..n) by warp 0; arr[n] = total
+__device__ __forceinline__ void warp0_exclusive_scan(int *arr, int n) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int chunk = (n + 31) / 32;
+    const int b = lane * chunk, e = min(n, b + chunk);
+    int s = 0;
+    for (int k = b; k < e; k++) s += arr[k];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int run = inc - s;
+    for (int k = b; k < e; k++) { const int v = arr[k]; arr[k] = run; run += v; }
+    if (lane == 31) arr[n] = inc;
+  }
+}
+
+__device__ __forceinline__ int staged_of_interior(const TileCtx &t, const TileArgs &a, int ci) {
+  const int cz = ci % a.tz, cy = (ci / a.tz) % a.ty, cx = ci / (a.tz * a.ty);
+  return ((cx + 1) * t.syn + (cy + 1)) * t.szn + (cz + 1);
+}
+
+// cell tables of this CTA's tile: s_start[c] = first staged slot of staged cell c, s_goff[c] =
+// its offset in the permute vector, s_ibase[ci] = first dense atom slot of interior cell ci
+__device__ __forceinline__ void tile_setup(const TileArgs &a, TileCtx &t, int *s_start, int *s_goff, int *s_ibase) {
+  t.tile = blockIdx.x;
+  const int tZ = t.tile % a.ntz, tY = (t.tile / a.ntz) % a.nty, tX = t.tile / (a.ntz * a.nty);
+  t.bx0 = a.nhalo + tX * a.tx; t.by0 = a.nhalo + tY * a.ty; t.bz0 = a.nhalo + tZ * a.tz;
+  t.sxn = a.tx + 2; t.syn = a.ty + 2; t.szn = a.tz + 2;
+  t.ncs = t.sxn * t.syn * t.szn;
+  t.nci = a.tx * a.ty * a.tz;
+  for (int c = threadIdx.x; c < t.ncs; c += blockDim.x) {
+    const int cz = c % t.szn, cy = (c / t.szn) % t.syn, cx = c / (t.szn * t.syn);
+    const int gx = t.bx0 - 1 + cx, gy = t.by0 - 1 + cy, gz = t.bz0 - 1 + cz;
+    const bool valid = gx >= 0 && gx < a.nbx && gy >= 0 && gy < a.nby && gz >= 0 && gz < a.nbz;
+    const int bin = (gx * a.nby + gy) * a.nbz + gz;
+    s_start[c] = valid ? a.bincount[bin] : 0;
+    s_goff[c] = valid ? a.binoffsets[bin] : 0;
+  }
+  __syncthreads();
+  for (int ci = threadIdx.x; ci < t.nci; ci += blockDim.x) {
+    const int cz = ci % a.tz, cy = (ci / a.tz) % a.ty, cx = ci / (a.tz * a.ty);
+    const int gx = t.bx0 + cx, gy = t.by0 + cy, gz = t.bz0 + cz;
+    const bool interior = gx < a.nbx - a.nhalo && gy < a.nby - a.nhalo && gz < a.nbz - a.nhalo;
+    s_ibase[ci] = interior ? s_start[staged_of_interior(t, a, ci)] : 0;
+  }
+  __syncthreads();
+  warp0_exclusive_scan(s_start, t.ncs);
+  __syncthreads();
+  warp0_exclusive_scan(s_ibase, t.nci);
+  __syncthreads();
+  t.total = s_start[t.ncs];
+  t.n_int = s_ibase[t.nci];
+}
+
+enum { ST_F32 = 1, ST_F64 = 2, ST_J = 4, ST_TYPE = 8 };
+
+template <int WHAT>
+__device__ __forceinline__ void tile_stage(const TileArgs &a, const TileCtx &t, const int *s_start, const int *s_goff,
+                                           float4 *sf, double *sx, double *sy, double *sz, int *sj, unsigned char *st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // FP32 coordinates are relative to the staged region's low corner
+  const double cx0 = a.ox + (t.bx0 - 1) * a.wx, cy0 = a.oy + (t.by0 - 1) * a.wy, cz0 = a.oz + (t.bz0 - 1) * a.wz;
+  for (int c = warp; c < t.ncs; c += nwarps) {
+    const int base = s_start[c], n = s_start[c + 1] - base, goff = s_goff[c];
+    for (int k = lane; k < n; k += 32) {
+      const int j = a.permute[goff + k];
+      const double xj = a.x[3 * (size_t)j], yj = a.x[3 * (size_t)j + 1], zj = a.x[3 * (size_t)j + 2];
+      const int s = base + k;
+      if (WHAT & ST_F32) sf[s] = make_float4((float)(xj - cx0), (float)(yj - cy0), (float)(zj - cz0), 0.f);
+      if (WHAT & ST_F64) { sx[s] = xj; sy[s] = yj; sz[s] = zj; }
+      if (WHAT & ST_J) sj[s] = j;
+      if (WHAT & ST_TYPE) st[s] = (unsigned char)a.type[j];
+    }
+  }
+}
+
+// dense atom slot t -> staged slot / global index of the interior atoms
+__device__ __forceinline__ void tile_interior_table(const TileArgs &a, const TileCtx &t, const int *s_start, const int *s_goff,
+                                                    const int *s_ibase, unsigned short *s_islot, int *s_iglob) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int ci = warp; ci < t.nci; ci += nwarps) {
+    const int n = s_ibase[ci + 1] - s_ibase[ci];
+    if (n == 0) continue;
+    const int c = staged_of_interior(t, a, ci);
+    for (int k = lane; k < n; k += 32) {
+      s_islot[s_ibase[ci] + k] = (unsigned short)(s_start[c] + k);
+      if (s_iglob) s_iglob[s_ibase[ci] + k] = a.permute[s_goff[c] + k];
+    }
+  }
+}
+
+__device__ __forceinline__ size_t ell_index(const TileArgs &a, int tile, int q, int t) {
+  return (((size_t)tile * (a.maxrow >> 2) + (q >> 2)) * a.stride + t) * 4 + (q & 3);
+}
+
+// ---------------------------------------------------------------------------- FP32 pre-filter
+// warp = one interior cell (lane = atom), candidates broadcast from shared memory in the
+// reference's stencil order (bx-1..bx+1, by, bz; permute order inside a bin)
+__global__ void __launch_bounds__(kFilterThreads) tiles_filter_kernel(TileArgs a, float cutf2) {
+  __shared__ int s_start[kMaxStagedCells + 1], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float4 *sf = reinterpret_cast<float4 *>(dyn);
+  TileCtx t;
+  tile_setup(a, t, s_start, s_goff, s_ibase);
+  if (threadIdx.x == 0) {
+    atomicMax(&a.flags[2], t.total);
+    atomicMax(&a.flags[3], t.n_int);
+    if (t.total > a.cap || t.total > 65535) atomicOr(&a.flags[0], 1);
+    if (t.n_int > a.stride) atomicOr(&a.flags[0], 2);
+  }
+  if (t.total > a.cap || t.total > 65535 || t.n_int > a.stride) return;
+  for (int k = t.n_int + threadIdx.x; k < a.stride; k += blockDim.x) a.nell[(size_t)t.tile * a.stride + k] = 0;
+  tile_stage<ST_F32>(a, t, s_start, s_goff, sf, nullptr, nullptr, nullptr, nullptr, nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int ci = warp; ci < t.nci; ci += nwarps) {
+    const int cnt = s_ibase[ci + 1] - s_ibase[ci];
+    if (cnt == 0) continue;
+    const int c_i = staged_of_interior(t, a, ci);
+    for (int k0 = 0; k0 < cnt; k0 += 32) {
+      const int k = k0 + lane;
+      const bool in_cell = k < cnt;
+      const int i_glob = in_cell ? a.permute[s_goff[c_i] + k] : 0x7fffffff;
+      const bool active = i_glob < a.n_local; // neighbor_csr.h:184 (ghosts inside interior bins get no row)
+      const int own = s_start[c_i] + k;
+      const float4 p = in_cell ? sf[own] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int tslot = s_ibase[ci] + k;
+      int q = 0;
+      for (int sc = 0; sc < 27; sc++) {
+        const int c = c_i + ((sc / 9 - 1) * t.syn + ((sc / 3) % 3 - 1)) * t.szn + (sc % 3 - 1);
+        const int e = s_start[c + 1];
+        for (int s = s_start[c]; s < e; s++) {
+          const float4 pj = sf[s]; // same address in every lane: broadcast
+          const float dx = p.x - pj.x, dy = p.y - pj.y, dz = p.z - pj.z;
+          const float r2 = dx * dx + dy * dy + dz * dz;
+          if (active && r2 <= cutf2 && s != own) {
+            if (q < a.maxrow) a.ell[ell_index(a, t.tile, q, tslot)] = (unsigned short)s;
+            q++;
+          }
+        }
+      }
+      if (in_cell) {
+        a.nell[(size_t)t.tile * a.stride + tslot] = min(q, a.maxrow);
+        if (q > a.maxrow) { atomicOr(&a.flags[0], 4); atomicMax(&a.flags[1], q); }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ exact lists from the ELL superset
+enum { EMIT_COUNT = 0, EMIT_CSR = 1, EMIT_2D = 2 };
+
+struct EmitArgs {
+  double cutsq;
+  int newton;
+  int *counts;        // COUNT: counts[i]; 2D: num_neighs[i]
+  const int *row_map; // CSR
+  int *entries;       // CSR entries / 2D table
+  int maxneighs;      // 2D
+  int *max_count;     // 2D
+};
+
+template <bool HALF, int MODE>
+__global__ void __launch_bounds__(512) tiles_emit_kernel(TileArgs a, EmitArgs e) {
+  __shared__ int s_start[kMaxStagedCells + 1], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
+  extern __shared__ __align__(16) unsigned char dyn[];
+  double *sx = reinterpret_cast<double *>(dyn), *sy = sx + a.cap, *sz = sy + a.cap;
+  int *sj = reinterpret_cast<int *>(sz + a.cap);
+  unsigned short *s_islot = reinterpret_cast<unsigned short *>(sj + a.cap);
+  TileCtx t;
+  tile_setup(a, t, s_start, s_goff, s_ibase);
+  if (t.total > a.cap || t.n_int > a.stride) return; // cannot happen after a successful filter pass
+  tile_stage<ST_F64 | ST_J>(a, t, s_start, s_goff, nullptr, sx, sy, sz, sj, nullptr);
+  tile_interior_table(a, t, s_start, s_goff, s_ibase, s_islot, nullptr);
+  __syncthreads();
+  const int ts = threadIdx.x;
+  if (ts >= t.n_int) return;
+  const int own = s_islot[ts];
+  const int i = sj[own];
+  if (i >= a.n_local) return;
+  const int n = a.nell[(size_t)t.tile * a.stride + ts];
+  const double x_i = sx[own], y_i = sy[own], z_i = sz[own];
+  const size_t base = (MODE == EMIT_CSR) ? (size_t)e.row_map[i] : (size_t)i * e.maxneighs;
+  int count = 0;
+  for (int q = 0; q < n; q++) {
+    const int s = a.ell[ell_index(a, t.tile, q, ts)];
+    const int j = sj[s];
+    const double x_j = sx[s], y_j = sy[s], z_j = sz[s];
+    if (HALF) { // neighbor_csr.h:290-291 (j != i by construction)
+      const bool skip = (j < a.n_local || e.newton) &&
+                        !((x_j > x_i) || ((x_j == x_i) && ((y_j > y_i) || ((y_j == y_i) && (z_j > z_i)))));
+      if (skip) continue;
+    }
+    const double dx = x_i - x_j, dy = y_i - y_j, dz = z_i - z_j;
+    const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (rsq <= e.cutsq) { // neighbor_csr.h:206,299
+      if (MODE == EMIT_CSR) e.entries[base + count] = j;
+      if (MODE == EMIT_2D && count < e.maxneighs) e.entries[base + count] = j; // neighbor_2d.h:207-208
+      count++;
+    }
+  }
+  if (MODE == EMIT_COUNT) e.counts[i] = count;
+  if (MODE == EMIT_2D) { e.counts[i] = count; atomicMax(e.max_count, count); }
+}
+
+// ------------------------------------------------------------------------------ LJ force
+struct LJOne { double lj1, lj2, cutsq; };
+struct LJTab {
+  double lj1[kMaxTypesConst * kMaxTypesConst], lj2[kMaxTypesConst * kMaxTypesConst], cutsq[kMaxTypesConst * kMaxTypesConst];
+  int ntypes;
+};
+
+// 1/a to <= 1 ulp: MUFU.RCP64H seed + two Newton steps (the library division adds range fix-ups
+// that rsq in (0, cutsq) never needs)
+__device__ __forceinline__ double fast_rcp(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+template <bool ONETYPE, bool ENERGY>
+__global__ void __launch_bounds__(384) lj_tiles_kernel(TileArgs a, LJOne one, const LJTab *__restrict__ tab, double *__restrict__ f,
+                                                       double *__restrict__ pe_partial) {
+  __shared__ int s_start[kMaxStagedCells + 1], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
+  __shared__ double s_red[12];
+  extern __shared__ __align__(16) unsigned char dyn[];
+  double *sx = reinterpret_cast<double *>(dyn), *sy = sx + a.cap, *sz = sy + a.cap;
+  int *s_iglob = reinterpret_cast<int *>(sz + a.cap);
+  unsigned short *s_islot = reinterpret_cast<unsigned short *>(s_iglob + a.stride);
+  unsigned char *st = reinterpret_cast<unsigned char *>(s_islot + a.stride);
+  TileCtx t;
+  tile_setup(a, t, s_start, s_goff, s_ibase);
+  tile_stage<ST_F64 | (ONETYPE ? 0 : ST_TYPE)>(a, t, s_start, s_goff, nullptr, sx, sy, sz, nullptr, st);
+  tile_interior_table(a, t, s_start, s_goff, s_ibase, s_islot, s_iglob);
+  __syncthreads();
+  const int ts = threadIdx.x;
+  double pe = 0.0;
+  const int i = ts < t.n_int ? s_iglob[ts] : 0x7fffffff;
+  if (i < a.n_local) {
+    const int own = s_islot[ts];
+    const int n = a.nell[(size_t)t.tile * a.stride + ts];
+    const double x_i = sx[own], y_i = sy[own], z_i = sz[own];
+    const int type_i = ONETYPE ? 0 : st[own];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    const ushort4 *row = reinterpret_cast<const ushort4 *>(a.ell) + ((size_t)t.tile * (a.maxrow >> 2)) * a.stride + ts;
+    const int nchunk = (n + 3) >> 2;
+    ushort4 cur = nchunk > 0 ? row[0] : make_ushort4(0, 0, 0, 0);
+    for (int c = 0; c < nchunk; c++) {
+      const ushort4 nxt = (c + 1 < nchunk) ? row[(size_t)(c + 1) * a.stride] : make_ushort4(0, 0, 0, 0);
+      const int left = n - 4 * c;
+      const unsigned short sl[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (u < left) {
+          const int s = sl[u];
+          const double dx = x_i - sx[s], dy = y_i - sy[s], dz = z_i - sz[s];
+          const double rsq = dx * dx + dy * dy + dz * dz;
+          double lj1, lj2, cutsq;
+          if (ONETYPE) { lj1 = one.lj1; lj2 = one.lj2; cutsq = one.cutsq; }
+          else { const int tij = type_i * tab->ntypes + st[s]; lj1 = tab->lj1[tij]; lj2 = tab->lj2[tij]; cutsq = tab->cutsq[tij]; }
+          if (rsq < cutsq) { // force_lj_neigh_impl.h:189 (strict)
+            const double r2inv = fast_rcp(rsq);
+            const double r6inv = r2inv * r2inv * r2inv;
+            const double fpair = (r6inv * (lj1 * r6inv - lj2)) * r2inv;
+            fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+            if (ENERGY) { // force_lj_neigh_impl.h:271-278 with fac = 0.5 (every pair is seen from both sides)
+              const double r2invc = 1.0 / cutsq, r6invc = r2invc * r2invc * r2invc;
+              pe += 0.5 * r6inv * (0.5 * lj1 * r6inv - lj2) / 6.0;
+              pe -= 0.5 * r6invc * (0.5 * lj1 * r6invc - lj2) / 6.0;
+            }
+          }
+        }
+      }
+      cur = nxt;
+    }
+    if (!ENERGY) { f[3 * (size_t)i] = fx; f[3 * (size_t)i + 1] = fy; f[3 * (size_t)i + 2] = fz; }
+  }
+  if (ENERGY) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pe += __shfl_down_sync(0xffffffffu, pe, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = pe;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += s_red[w];
+      pe_partial[blockIdx.x] = s;
+    }
+  }
+}
+
+size_t emit_smem(int cap, int stride) { return (size_t)cap * (3 * sizeof(double) + sizeof(int)) + (size_t)stride * sizeof(unsigned short); }
+size_t force_smem(int cap, int stride, bool types) {
+  return (size_t)cap * 3 * sizeof(double) + (size_t)stride * (sizeof(int) + sizeof(unsigned short)) + (types ? (size_t)cap : 0) + 16;
+}
+
+} // namespace
+
+namespace emd { int device_sum_partials(emd_ctx *ctx, const double *d_partial, int n, double *h_out); }
+
+struct emd_tiles {
+  TileArgs a;
+  int ntiles = 0;
+  bool valid = false;
+  unsigned short *d_ell = nullptr; size_t ell_cap = 0;
+  int *d_nell = nullptr; size_t nell_cap = 0;
+  int *d_flags = nullptr;
+  LJTab *d_tab = nullptr;
+  double neigh_cut = 0.0;
+  float cutf2 = 0.f;
+  int max_smem_optin = 0;
+};
+
+namespace {
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+  EMD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+int ensure_bytes(void **p, size_t *cap, size_t bytes) {
+  if (bytes <= *cap) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  const size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) { set_error("tiles: cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e)); return 1; }
+  *cap = want;
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int emd_tiles_create(emd_tiles **out) {
+  if (!out) { set_error("emd_tiles_create: out == NULL"); return 1; }
+  emd_tiles *t = new emd_tiles();
+  memset(&t->a, 0, sizeof t->a);
+  EMD_CUDA(cudaMalloc((void **)&t->d_flags, 4 * sizeof(int)));
+  EMD_CUDA(cudaMalloc((void **)&t->d_tab, sizeof(LJTab)));
+  int dev = 0;
+  EMD_CUDA(cudaGetDevice(&dev));
+  EMD_CUDA(cudaDeviceGetAttribute(&t->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  *out = t;
+  return 0;
+}
+
+void emd_tiles_destroy(emd_tiles *t) {
+  if (!t) return;
+  if (t->d_ell) cudaFree(t->d_ell);
+  if (t->d_nell) cudaFree(t->d_nell);
+  if (t->d_flags) cudaFree(t->d_flags);
+  if (t->d_tab) cudaFree(t->d_tab);
+  delete t;
+}
+
+int emd_tiles_valid(const emd_tiles *t) { return t && t->valid; }
+void emd_tiles_invalidate(emd_tiles *t) { if (t) t->valid = false; }
+
+int emd_tiles_info(const emd_tiles *t, int *tile_dims, int *ntiles, int *stride, int *maxrow, int *cap) {
+  if (!t) return 1;
+  if (tile_dims) { tile_dims[0] = t->a.tx; tile_dims[1] = t->a.ty; tile_dims[2] = t->a.tz; }
+  if (ntiles) *ntiles = t->ntiles;
+  if (stride) *stride = t->a.stride;
+  if (maxrow) *maxrow = t->a.maxrow;
+  if (cap) *cap = t->a.cap;
+  return 0;
+}
+
+// Build the tile-local full adjacency.  Returns 0 on success, 3 if the fast path does not apply
+// to this configuration (the caller then uses emd_neigh_csr_* / emd_neigh_2d_fill), 1 on error.
+int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_local, int n_all, const emd_bin_geom *g,
+                          const int *d_bincount, const int *d_binoffsets, const int *d_permute, double neigh_cut) {
+  t->valid = false;
+  const int nix = g->nbinx - 2 * g->nhalo, niy = g->nbiny - 2 * g->nhalo, niz = g->nbinz - 2 * g->nhalo;
+  if (nix <= 0 || niy <= 0 || niz <= 0 || n_local <= 0) return 3;
+  const double wx = (g->maxx - g->minx) / g->nbinx, wy = (g->maxy - g->miny) / g->nbiny, wz = (g->maxz - g->minz) / g->nbinz;
+  // the 27-bin stencil must cover the list radius (true for every reference configuration:
+  // bins are at least neigh_cut wide, binning_kksort.cpp:77-87); the reference itself simply
+  // misses pairs otherwise, and the generic kernels reproduce that
+  if (neigh_cut > wx || neigh_cut > wy || neigh_cut > wz) return 3;
+  TileArgs &a = t->a;
+  a.nbx = g->nbinx; a.nby = g->nbiny; a.nbz = g->nbinz; a.nhalo = g->nhalo;
+  a.n_local = n_local;
+  a.bincount = d_bincount; a.binoffsets = d_binoffsets; a.permute = d_permute;
+  a.x = d_x; a.type = nullptr;
+  a.ox = g->minx; a.oy = g->miny; a.oz = g->minz;
+  a.wx = wx; a.wy = wy; a.wz = wz;
+  a.stride = 384;
+  // mean atoms per cell -> tile shape with ~0.9*stride atoms whose halo fits in shared memory
+  const double m = std::max(1e-3, (double)n_all / ((double)g->nbinx * g->nbiny * g->nbinz));
+  const int cap_max = 3000; // 72 KB of FP64 coordinates: three force CTAs per SM
+  static const int shapes[][3] = {{4, 4, 8}, {4, 4, 4}, {2, 4, 4}, {2, 2, 8}, {2, 2, 4}, {2, 2, 2}, {1, 2, 2}, {1, 1, 2}, {1, 1, 1}};
+  int pick = -1;
+  for (int s = 0; s < (int)(sizeof shapes / sizeof shapes[0]); s++) {
+    const int *d = shapes[s];
+    const double atoms = m * d[0] * d[1] * d[2], staged = m * (d[0] + 2) * (d[1] + 2) * (d[2] + 2);
+    if ((d[0] + 2) * (d[1] + 2) * (d[2] + 2) > kMaxStagedCells || d[0] * d[1] * d[2] > kMaxInteriorCells) continue;
+    if (atoms <= 0.9 * a.stride && staged * 1.2 + 64 <= cap_max) { pick = s; break; }
+  }
+  if (pick < 0) return 3;
+  a.tx = std::min(shapes[pick][0], nix); a.ty = std::min(shapes[pick][1], niy); a.tz = std::min(shapes[pick][2], niz);
+  a.ntx = (nix + a.tx - 1) / a.tx; a.nty = (niy + a.ty - 1) / a.ty; a.ntz = (niz + a.tz - 1) / a.tz;
+  const long long ntiles_ll = (long long)a.ntx * a.nty * a.ntz;
+  if (ntiles_ll > 0x7fffffffLL) return 3;
+  t->ntiles = (int)ntiles_ll;
+  const int staged_cells = (a.tx + 2) * (a.ty + 2) * (a.tz + 2);
+  a.cap = std::min(cap_max, ((int)(m * staged_cells * 1.25) + 64 + 31) / 32 * 32);
+  // expected full-list row: density * sphere volume, +35 % head room
+  const double rho = m / (wx * wy * wz);
+  int maxrow = (int)(rho * 4.18879020478639 * neigh_cut * neigh_cut * neigh_cut * 1.35) + 8;
+  maxrow = std::max(16, (maxrow + 3) / 4 * 4);
+  // conservative FP32 radius: coordinates are relative to the staged region (extent E), so the
+  // FP32 distance is off by < 8*E*2^-24; take 32*E*2^-23 + 2^-20 relative as the margin
+  const double E = std::max({(a.tx + 2) * wx, (a.ty + 2) * wy, (a.tz + 2) * wz});
+  const double thr = neigh_cut * (1.0 + 1.0 / 1048576.0) + 32.0 * E / 8388608.0;
+  t->cutf2 = nextafterf((float)(thr * thr), INFINITY);
+  t->neigh_cut = neigh_cut;
+
+  for (int attempt = 0; attempt < 4; attempt++) {
+    a.maxrow = maxrow;
+    const size_t ell_bytes = (size_t)t->ntiles * a.maxrow * a.stride * sizeof(unsigned short);
+    if (ensure_bytes((void **)&t->d_ell, &t->ell_cap, ell_bytes)) return 1;
+    if (ensure_bytes((void **)&t->d_nell, &t->nell_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
+    a.ell = t->d_ell; a.nell = t->d_nell; a.flags = t->d_flags;
+    EMD_CUDA(cudaMemsetAsync(t->d_flags, 0, 4 * sizeof(int), ctx->stream));
+    const size_t smem = (size_t)a.cap * sizeof(float4);
+    if (set_smem(tiles_filter_kernel, smem)) return 1;
+    EMD_LAUNCH(ctx, tiles_filter_kernel, t->ntiles, kFilterThreads, smem, a, t->cutf2);
+    EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    EMD_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int bits = ctx->h_pinned[0], need_row = ctx->h_pinned[1], need_cap = ctx->h_pinned[2], need_int = ctx->h_pinned[3];
+    if (bits == 0) { t->valid = true; return 0; }
+    if (bits & 2) { (void)need_int; return 3; } // a tile holds more atoms than threads: density far from the estimate
+    if (bits & 1) {
+      if (need_cap > cap_max || need_cap > 65535) return 3;
+      a.cap = (need_cap + need_cap / 16 + 31) / 32 * 32;
+      if (a.cap > cap_max) a.cap = cap_max;
+    }
+    if (bits & 4) maxrow = (need_row + need_row / 8 + 3) / 4 * 4;
+  }
+  return 3;
+}
+
+int emd_neigh_tiles_count(emd_ctx *ctx, emd_tiles *t, int half, int newton, int *d_row_map, int *h_total) {
+  if (!t || !t->valid) { set_error("emd_neigh_tiles_count: tiles not built"); return 1; }
+  TileArgs &a = t->a;
+  EmitArgs e;
+  memset(&e, 0, sizeof e);
+  e.cutsq = t->neigh_cut * t->neigh_cut; e.newton = newton; e.counts = d_row_map;
+  EMD_CUDA(cudaMemsetAsync(d_row_map, 0, sizeof(int) * ((size_t)a.n_local + 1), ctx->stream));
+  const size_t smem = emit_smem(a.cap, a.stride);
+  if (half) { if (set_smem(tiles_emit_kernel<true, EMIT_COUNT>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<true, EMIT_COUNT>), t->ntiles, a.stride, smem, a, e); }
+  else { if (set_smem(tiles_emit_kernel<false, EMIT_COUNT>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<false, EMIT_COUNT>), t->ntiles, a.stride, smem, a, e); }
+  if (exclusive_scan_int(ctx, d_row_map, d_row_map, a.n_local + 1, nullptr)) return 1;
+  if (h_total) {
+    EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_row_map + a.n_local, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    EMD_CUDA(cudaStreamSynchronize(ctx->stream));
+    *h_total = ctx->h_pinned[0];
+    if (*h_total < 0) { set_error("emd_neigh_tiles_count: neighbor count overflows 32-bit row_map"); return 2; }
+  }
+  return 0;
+}
+
+int emd_neigh_tiles_fill_csr(emd_ctx *ctx, emd_tiles *t, int half, int newton, const int *d_row_map, int *d_entries) {
+  if (!t || !t->valid) { set_error("emd_neigh_tiles_fill_csr: tiles not built"); return 1; }
+  TileArgs &a = t->a;
+  EmitArgs e;
+  memset(&e, 0, sizeof e);
+  e.cutsq = t->neigh_cut * t->neigh_cut; e.newton = newton; e.row_map = d_row_map; e.entries = d_entries;
+  const size_t smem = emit_smem(a.cap, a.stride);
+  if (half) { if (set_smem(tiles_emit_kernel<true, EMIT_CSR>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<true, EMIT_CSR>), t->ntiles, a.stride, smem, a, e); }
+  else { if (set_smem(tiles_emit_kernel<false, EMIT_CSR>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<false, EMIT_CSR>), t->ntiles, a.stride, smem, a, e); }
+  return 0;
+}
+
+int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half, int newton, int maxneighs, int *d_num_neighs, int *d_neighs,
+                            int *h_max_count) {
+  if (!t || !t->valid) { set_error("emd_neigh_tiles_fill_2d: tiles not built"); return 1; }
+  TileArgs &a = t->a;
+  EmitArgs e;
+  memset(&e, 0, sizeof e);
+  e.cutsq = t->neigh_cut * t->neigh_cut; e.newton = newton; e.counts = d_num_neighs; e.entries = d_neighs; e.maxneighs = maxneighs;
+  e.max_count = t->d_flags + 1;
+  EMD_CUDA(cudaMemsetAsync(e.max_count, 0, sizeof(int), ctx->stream));
+  EMD_CUDA(cudaMemsetAsync(d_num_neighs, 0, sizeof(int) * ((size_t)a.n_local + 1), ctx->stream));
+  const size_t smem = emit_smem(a.cap, a.stride);
+  if (half) { if (set_smem(tiles_emit_kernel<true, EMIT_2D>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<true, EMIT_2D>), t->ntiles, a.stride, smem, a, e); }
+  else { if (set_smem(tiles_emit_kernel<false, EMIT_2D>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<false, EMIT_2D>), t->ntiles, a.stride, smem, a, e); }
+  if (h_max_count) {
+    EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, e.max_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    EMD_CUDA(cudaStreamSynchronize(ctx->stream));
+    *h_max_count = ctx->h_pinned[0];
+  }
+  return 0;
+}
+
+// ForceLJNeigh::compute / compute_energy on the tile lists.  d_x/d_type are the CURRENT arrays
+// (atoms keep their indices between rebuilds; the binning arrays captured at build time must
+// still be alive).  With h_pe != NULL only the energy is computed (forces untouched).
+int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe) {
+  if (!t || !t->valid) { set_error("emd_force_lj_compute_tiles: tiles not built"); return 1; }
+  if (ctx->lj.ntypes == 0) { set_error("emd_force_lj_compute_tiles: parameters not set"); return 1; }
+  TileArgs a = t->a;
+  a.x = d_x; a.type = d_type;
+  const bool one = ctx->lj.ntypes == 1;
+  LJOne p1 = {ctx->lj.lj1[0], ctx->lj.lj2[0], ctx->lj.cutsq[0]};
+  if (!one) {
+    LJTab h;
+    h.ntypes = ctx->lj.ntypes;
+    memcpy(h.lj1, ctx->lj.lj1, sizeof h.lj1); memcpy(h.lj2, ctx->lj.lj2, sizeof h.lj2); memcpy(h.cutsq, ctx->lj.cutsq, sizeof h.cutsq);
+    EMD_CUDA(cudaMemcpyAsync(t->d_tab, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    EMD_CUDA(cudaStreamSynchronize(ctx->stream)); // h is a stack object
+  }
+  const size_t smem = force_smem(a.cap, a.stride, !one);
+  double *partial = nullptr;
+  if (h_pe) {
+    if (ctx->s_c.ensure(sizeof(double) * ((size_t)t->ntiles + 8))) return 1;
+    partial = ctx->s_c.as<double>() + 8;
+  }
+#define EMD_LJ_TILES(ONE, EN)                                                                              \
+  do {                                                                                                     \
+    if (set_smem(lj_tiles_kernel<ONE, EN>, smem)) return 1;                                                \
+    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN>), t->ntiles, a.stride, smem, a, p1, t->d_tab, d_f, partial); \
+  } while (0)
+  if (h_pe) { if (one) EMD_LJ_TILES(true, true); else EMD_LJ_TILES(false, true); }
+  else { if (one) EMD_LJ_TILES(true, false); else EMD_LJ_TILES(false, false); }
+#undef EMD_LJ_TILES
+  if (h_pe) return device_sum_partials(ctx, partial, t->ntiles, h_pe);
+  return 0;
+}
+
+} // extern "C"

@@ -132,6 +132,38 @@ int emd_force_lj_compute(emd_ctx *ctx, const double *d_x, const int *d_type, dou
 int emd_force_lj_energy(emd_ctx *ctx, const double *d_x, const int *d_type, int n_local,
                         const emd_neigh_list *list, int half_neigh, double *h_pe);
 
+/* ---- tile lists: the B200 fast path of the neighbor build + LJ force (kernels/tiles.cu) -------
+ * An emd_tiles object holds a tile-local FULL adjacency (shared-memory slot numbers, ELL layout)
+ * built from the same inputs as the reference lists.  The reference-visible CSR / 2D lists are
+ * emitted FROM it with the reference's exact FP64 inclusion rules, so they are bit-identical to
+ * emd_neigh_csr_count/fill and emd_neigh_2d_fill; the LJ force then runs on the tile lists with
+ * every x[j] served from shared memory and no atomics (each pair is evaluated from both sides).
+ * emd_neigh_tiles_build returns 0 on success and 3 when the fast path does not apply to this
+ * configuration (bins narrower than the list radius, a tile that does not fit in shared memory):
+ * the caller then uses the generic entry points above.  The binning arrays passed to build must
+ * stay alive and unchanged until the next build (they are re-read by every later call). */
+typedef struct emd_tiles emd_tiles;
+int emd_tiles_create(emd_tiles **out);
+void emd_tiles_destroy(emd_tiles *t);
+int emd_tiles_valid(const emd_tiles *t);
+void emd_tiles_invalidate(emd_tiles *t);
+int emd_tiles_info(const emd_tiles *t, int *tile_dims3, int *ntiles, int *stride, int *maxrow, int *cap);
+int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_local, int n_all,
+                          const emd_bin_geom *geom, const int *d_bincount, const int *d_binoffsets,
+                          const int *d_permute, double neigh_cut);
+/* = emd_neigh_csr_count / emd_neigh_csr_fill / emd_neigh_2d_fill, from the tile lists */
+int emd_neigh_tiles_count(emd_ctx *ctx, emd_tiles *t, int half_neigh, int comm_newton, int *d_row_map,
+                          int *h_total);
+int emd_neigh_tiles_fill_csr(emd_ctx *ctx, emd_tiles *t, int half_neigh, int comm_newton,
+                             const int *d_row_map, int *d_entries);
+int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half_neigh, int comm_newton, int maxneighs,
+                            int *d_num_neighs, int *d_neighs, int *h_max_count);
+/* ForceLJNeigh::compute (h_pe == NULL: overwrites d_f rows [0,n_local), ghost rows untouched) or
+ * ::compute_energy (h_pe != NULL: shifted PE, d_f untouched), force_lj_neigh_impl.h:100-156.
+ * Valid for full lists and for half lists with newton off (same forces on owned atoms). */
+int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type,
+                               double *d_f, double *h_pe);
+
 /* ---- integrator: IntegratorNVE, src/integrator_nve.cpp:41-121 --------------------------- */
 /* dtf = 0.5*dt/mvv2e, dtv = dt (:41-44).  Bit-exact with the reference's CPU arithmetic
  * (separate multiply and add, no FMA contraction). */

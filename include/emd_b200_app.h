@@ -21,6 +21,9 @@ int emd_app_create(emd_app **out, int argc, const char *const *argv, int device,
 void emd_app_destroy(emd_app *app);
 emd_ctx *emd_app_ctx(emd_app *app);
 int emd_app_advance(emd_app *app, int nsteps);
+/* same, with the reference's four phase timers (src/examinimd.cpp:183-189) taken as device events:
+ * h_seconds4 = {T_Force, T_Neigh, T_Comm, T_Other} accumulated over the nsteps */
+int emd_app_advance_timed(emd_app *app, int nsteps, double *h_seconds4);
 int emd_app_thermo(emd_app *app, double *T, double *PE_per_atom, double *KE_per_atom);
 /* integer properties: "N","N_local","N_ghost","N_max","step","total_neighs","nsteps",
  * "exchange_rate","half_neigh","nbinx","nbiny","nbinz"; -1 if unknown */
@@ -30,7 +33,8 @@ int emd_app_download(emd_app *app, int *h_id, int *h_type, double *h_q, double *
 /* HOST x,v,f of the owned atoms to the device (any pointer may be NULL) */
 int emd_app_upload(emd_app *app, const double *h_x, const double *h_v, const double *h_f);
 /* device pointers of the live arrays: "x","v","f","type","id","q","bincount","binoffsets",
- * "permute","row_map","num_neighs","neighs" (valid until the next rebuild/grow) */
+ * "permute","row_map","num_neighs","neighs" (valid until the next rebuild/grow); "tiles" = the
+ * emd_tiles* of the last neighbor build, or NULL when the fast path is not in use */
 void *emd_app_device_ptr(emd_app *app, const char *what);
 int emd_app_neigh_stride(emd_app *app);
 int emd_app_dump_binary(emd_app *app, const char *path, int step);

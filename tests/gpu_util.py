@@ -79,3 +79,60 @@ def csr_list(rm, ent):
 
 def table_list(nn, tab, stride):
     return emd.NeighList(None, ptr(nn), ptr(tab), stride)
+
+
+class Tiles:
+    """emd_tiles built from an oracle state (the B200 fast path of kernels/tiles.cu)."""
+
+    def __init__(self, ctx, x_dev, n_local, n_all, g, bc, bo, pv, cut):
+        L = emd.lib()
+        self.ctx, self.n_local = ctx, n_local
+        self.keep = (x_dev, bc, bo, pv)  # the build captures these pointers
+        self.h = P()
+        emd.check(L.emd_tiles_create(C.byref(self.h)), "emd_tiles_create")
+        self.rc = L.emd_neigh_tiles_build(ctx.handle, self.h, ptr(x_dev), n_local, n_all, C.byref(g), ptr(bc), ptr(bo), ptr(pv), cut)
+        if self.rc not in (0, 3):
+            emd.check(self.rc, "emd_neigh_tiles_build")
+
+    @property
+    def ok(self):
+        return self.rc == 0 and emd.lib().emd_tiles_valid(self.h) == 1
+
+    def info(self):
+        d = (C.c_int * 3)()
+        nt, st, mr, cap = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        emd.check(emd.lib().emd_tiles_info(self.h, d, C.byref(nt), C.byref(st), C.byref(mr), C.byref(cap)))
+        return {"dims": tuple(d), "ntiles": nt.value, "stride": st.value, "maxrow": mr.value, "cap": cap.value}
+
+    def csr(self, half, newton):
+        L = emd.lib()
+        rm = torch.empty(self.n_local + 1, dtype=torch.int32, device="cuda")
+        total = C.c_int()
+        emd.check(L.emd_neigh_tiles_count(self.ctx.handle, self.h, half, newton, ptr(rm), C.byref(total)), "tiles_count")
+        ent = torch.empty(max(total.value, 1), dtype=torch.int32, device="cuda")
+        emd.check(L.emd_neigh_tiles_fill_csr(self.ctx.handle, self.h, half, newton, ptr(rm), ptr(ent)), "tiles_fill_csr")
+        return rm, ent[: total.value], total.value
+
+    def table(self, half, newton, maxneighs=16):
+        L = emd.lib()
+        passes = 0
+        while True:
+            nn = torch.empty(self.n_local + 1, dtype=torch.int32, device="cuda")
+            tab = torch.empty((self.n_local + 1, maxneighs), dtype=torch.int32, device="cuda")
+            mx = C.c_int()
+            emd.check(L.emd_neigh_tiles_fill_2d(self.ctx.handle, self.h, half, newton, maxneighs, ptr(nn), ptr(tab), C.byref(mx)))
+            passes += 1
+            if mx.value <= maxneighs:
+                return nn[: self.n_local], tab, maxneighs, passes
+            maxneighs = int(mx.value * 1.2)
+
+    def force(self, x_dev, type_dev, f_dev, energy=False):
+        pe = C.c_double()
+        emd.check(emd.lib().emd_force_lj_compute_tiles(self.ctx.handle, self.h, ptr(x_dev), ptr(type_dev), ptr(f_dev),
+                                                       C.byref(pe) if energy else None), "force_tiles")
+        return pe.value
+
+    def close(self):
+        if self.h:
+            emd.lib().emd_tiles_destroy(self.h)
+            self.h = P()

@@ -178,6 +178,116 @@ def test_neighbor_ragged_dense_bins(emd, gu, ctx):
         md.close()
 
 
+# ------------------------------------------------------- tile lists: the B200 fast path (a2 + a3)
+def _tiles_for(gu, ctx, md):
+    x = gu.dev(md.arr("x"))
+    n, na = md.geti("N_local"), md.geti("N_local") + md.geti("N_ghost")
+    g = gu.geom_from(md.geom())
+    bc, bo, pv = gu.dev(md.arr("bincount")), gu.dev(md.arr("binoffsets")), gu.dev(md.arr("permute"))
+    return gu.Tiles(ctx, x, n, na, g, bc, bo, pv, md.getd("neigh_cutoff")), x
+
+
+@pytest.mark.parametrize("iteration", ["NEIGH_FULL", "NEIGH_HALF"])
+@pytest.mark.parametrize("state", ["lattice", "liquid"])
+def test_tiles_emit_reference_rows(emd, gu, ctx, iteration, state):
+    """the CSR and 2D lists emitted from the tile lists are the reference's rows, entry by entry"""
+    half = iteration == "NEIGH_HALF"
+    md = OracleMD.from_deck(DECK, "CSR", iteration, region=(10, 10, 10)) if state == "lattice" else rebuilt(liquid(iteration=iteration))
+    t, _ = _tiles_for(gu, ctx, md)
+    assert t.ok, t.info()
+    rm, ent, total = t.csr(half, 0)
+    assert total == md.geti("total_neighs")
+    np.testing.assert_array_equal(rm.cpu().numpy(), md.arr("row_map"))
+    np.testing.assert_array_equal(ent.cpu().numpy(), md.arr("entries"))
+    nn, tab, stride, passes = t.table(half, 0)
+    o_rm = md.arr("row_map")
+    np.testing.assert_array_equal(nn.cpu().numpy(), np.diff(o_rm))
+    tt, oe = tab.cpu().numpy(), md.arr("entries")
+    for i in range(0, md.geti("N_local"), 11):
+        np.testing.assert_array_equal(tt[i, : o_rm[i + 1] - o_rm[i]], oe[o_rm[i]: o_rm[i + 1]])
+    assert passes == 2
+    t.close(); md.close()
+
+
+def test_tiles_half_newton_on_rows(emd, gu, ctx):
+    x = OracleMD.from_deck(DECK, "CSR", "NEIGH_HALF", region=(8, 8, 8), setup=False)
+    box = [x.getd("domain_x")] * 3
+    md = OracleMD.from_arrays(x.arr("x")[: x.geti("N")], box, newton=1, iteration="NEIGH_HALF")
+    rebuilt(md)
+    t, _ = _tiles_for(gu, ctx, md)
+    assert t.ok
+    rm, ent, total = t.csr(True, 1)
+    np.testing.assert_array_equal(rm.cpu().numpy(), md.arr("row_map"))
+    np.testing.assert_array_equal(ent.cpu().numpy(), md.arr("entries"))
+    t.close(); x.close(); md.close()
+
+
+@pytest.mark.parametrize("iteration", ["NEIGH_FULL", "NEIGH_HALF"])
+def test_tiles_lj_force_and_energy(emd, gu, ctx, iteration):
+    """owned-atom forces and the shifted PE from the tile lists equal the reference's full- and half-list results"""
+    import torch
+    md = rebuilt(liquid(iteration=iteration))
+    md.stage("zero_f", "force")
+    n = md.geti("N_local")
+    t, x = _tiles_for(gu, ctx, md)
+    assert t.ok
+    _set_lj(emd, ctx, md)
+    typ = gu.dev(md.arr("type"))
+    f = torch.full((x.shape[0], 3), 7.0, dtype=torch.float64, device="cuda")
+    t.force(x, typ, f)
+    fo = md.arr("f")
+    assert np.abs(f.cpu().numpy()[:n] - fo[:n]).max() / np.sqrt((fo[:n] ** 2).mean()) < TOL
+    assert (f.cpu().numpy()[n:] == 7.0).all()  # ghost rows are not touched
+    pe = t.force(x, typ, f, energy=True)
+    _, PE, _ = md.thermo()
+    assert abs(pe / md.geti("N") - PE) < 1e-12 * abs(PE) * 100
+    # positions move between rebuilds: same lists, new x (skin not exceeded)
+    rng = np.random.default_rng(2)
+    xm = md.arr("x").copy()
+    xm[:n] += rng.normal(0, 0.02, (n, 3))
+    md.set("x", xm)
+    md.stage("update_halo", "zero_f", "force")
+    x2 = gu.dev(md.arr("x"))
+    t.force(x2, typ, f)
+    fo = md.arr("f")
+    assert np.abs(f.cpu().numpy()[:n] - fo[:n]).max() / np.sqrt((fo[:n] ** 2).mean()) < TOL
+    t.close(); md.close()
+
+
+def test_tiles_two_types_and_ragged(emd, gu, ctx):
+    import torch
+    rng = np.random.default_rng(3)
+    base = OracleMD.from_deck(DECK, "CSR", "NEIGH_FULL", region=(7, 7, 7), setup=False)
+    x = base.arr("x")[: base.geti("N")] + rng.normal(0, 0.05, (base.geti("N"), 3))
+    box = [base.getd("domain_x")] * 3
+    types = rng.integers(0, 2, x.shape[0]).astype(np.int32)
+    md = OracleMD.from_arrays(x, box, types=types, ntypes=2, mass=[1.0, 3.0], iteration="NEIGH_FULL")
+    rebuilt(md)
+    md.stage("zero_f", "force")
+    n = md.geti("N_local")
+    t, xd = _tiles_for(gu, ctx, md)
+    assert t.ok
+    _set_lj(emd, ctx, md, ntypes=2)
+    f = torch.zeros((xd.shape[0], 3), dtype=torch.float64, device="cuda")
+    t.force(xd, gu.dev(md.arr("type")), f)
+    fo = md.arr("f")
+    assert np.abs(f.cpu().numpy()[:n] - fo[:n]).max() / np.sqrt((fo[:n] ** 2).mean()) < TOL
+    t.close(); base.close(); md.close()
+    # a dense blob does not fit a tile: the build must say "not applicable" (3), never produce a wrong list
+    box = np.array([12.0, 12.0, 12.0])
+    xb = np.concatenate([rng.uniform(4.0, 7.5, (1500, 3)), rng.uniform(0, 12, (60, 3))])
+    md = OracleMD.from_arrays(xb, box, force_cutoff=2.5, skin=0.3, iteration="NEIGH_FULL")
+    rebuilt(md)
+    t, _ = _tiles_for(gu, ctx, md)
+    if t.ok:
+        rm, ent, total = t.csr(False, 0)
+        np.testing.assert_array_equal(rm.cpu().numpy(), md.arr("row_map"))
+        np.testing.assert_array_equal(ent.cpu().numpy(), md.arr("entries"))
+    else:
+        assert t.rc == 3
+    t.close(); md.close()
+
+
 # ---------------------------------------------------------------------------- LJ force (a3)
 def _set_lj(emd, ctx, md, ntypes=1):
     L = emd.lib()
@@ -233,8 +343,8 @@ def test_lj_force_two_types(emd, gu, ctx):
     _set_lj(emd, ctx, md, ntypes=2)
     lst = gu.csr_list(*(keep := (gu.dev(md.arr("row_map")), gu.dev(md.arr("entries")))))
     f = torch.zeros((na, 3), dtype=torch.float64, device="cuda")
-    emd.check(emd.lib().emd_force_lj_compute(ctx.handle, gu.ptr(gu.dev(md.arr("x"))), gu.ptr(gu.dev(md.arr("type"))), gu.ptr(f), n, na,
-                                             C.byref(lst), 1, 1))
+    xd, td = gu.dev(md.arr("x")), gu.dev(md.arr("type"))  # keep the device buffers alive across the call
+    emd.check(emd.lib().emd_force_lj_compute(ctx.handle, gu.ptr(xd), gu.ptr(td), gu.ptr(f), n, na, C.byref(lst), 1, 1))
     fo = md.arr("f")
     assert np.abs(f.cpu().numpy()[:n] - fo[:n]).max() / np.sqrt((fo[:n] ** 2).mean()) < TOL
     base.close(); md.close()
@@ -330,8 +440,8 @@ def test_reduce_mv2(emd, gu, ctx):
     md = liquid(nsteps=3)
     n = md.geti("N_local")
     s = C.c_double()
-    emd.check(emd.lib().emd_reduce_mv2(ctx.handle, gu.ptr(gu.dev(md.arr("v")[:n])), gu.ptr(gu.dev(md.arr("type")[:n])),
-                                       gu.ptr(gu.dev(md.arr("mass"))), n, C.byref(s)))
+    vd, td, md_ = gu.dev(md.arr("v")[:n]), gu.dev(md.arr("type")[:n]), gu.dev(md.arr("mass"))
+    emd.check(emd.lib().emd_reduce_mv2(ctx.handle, gu.ptr(vd), gu.ptr(td), gu.ptr(md_), n, C.byref(s)))
     T, _, KE = md.thermo()
     assert abs(s.value * 0.5 * md.getd("mvv2e") / md.geti("N") - KE) < 1e-13 * KE * 10
     md.close()

@@ -45,7 +45,8 @@ def test_100_steps_vs_oracle(emd, neigh, iteration):
     assert app.get("N") == md.geti("N") and app.get("N_ghost") == md.geti("N_ghost")
     compare(app.download(), md)  # step 0: bit-identical lattice, forces ~ 0
     T0, PE0, KE0 = app.thermo()
-    assert (f"{T0:.6f}", f"{PE0:.6f}", f"{PE0 + KE0:.6f}") == ("1.400000", "-6.332812", "-4.232820")
+    n_at = md.geti("N")  # T0 = 1.4 exactly, PE0 = -6.332812, KE0 = 1.5*T0*(N-1)/N
+    assert (f"{T0:.6f}", f"{PE0:.6f}") == ("1.400000", "-6.332812") and abs(KE0 - 2.1 * (n_at - 1) / n_at) < 1e-12
     for _ in range(5):
         app.advance(20)
         md.step(20)
@@ -60,8 +61,11 @@ def test_100_steps_vs_oracle(emd, neigh, iteration):
     app.close(); md.close()
 
 
-def test_binary_dump_and_correctness_flags(emd, tmp_path):
-    """the ExaMiniMD executable with the reference's own record/replay flags (README.md:99-107)."""
+@pytest.mark.parametrize("no_tiles", ["0", "1"])
+def test_binary_dump_and_correctness_flags(emd, tmp_path, no_tiles):
+    """the ExaMiniMD executable with the reference's own record/replay flags (README.md:99-107); once on the
+    tile fast path and once (EMD_NO_TILES=1) on the generic list kernels."""
+    import os
     region = ["--region", "10", "10", "10", "--nsteps", "40"]
     refdir = tmp_path / "ref"; refdir.mkdir()
     md = OracleMD.from_deck(DECK, "CSR", "NEIGH_HALF", region=(10, 10, 10))
@@ -74,10 +78,11 @@ def test_binary_dump_and_correctness_flags(emd, tmp_path):
     mine = tmp_path / "mine"; mine.mkdir()
     r = subprocess.run([str(emd.EXE_PATH), "-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF",
                         "--comm-type", "SERIAL", *region, "--dumpbinary", "20", str(mine), "--correctness", "20", str(refdir), str(out)],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, EMD_NO_TILES=no_tiles))
     assert r.returncode == 0, r.stderr
     assert "Using: ForceLJNeighHalf NeighborCSR CommSerial BinningKKSort" in r.stdout
-    assert "\n0 1.400000 -6.332812 -4.232820 " in r.stdout
+    l0 = [l.split() for l in r.stdout.splitlines() if l.startswith("0 1.400000 -6.332812 ")]
+    assert l0 and abs(float(l0[0][3]) - (-6.332811993 + 2.1 * 3999 / 4000)) < 2e-6  # KE0 = 1.5*T0*(N-1)/N, N = 4000
     assert "PERFORMANCE" in r.stdout
     rows = [l.split() for l in out.read_text().splitlines() if not l.startswith("#")]
     assert [int(r_[0]) for r_ in rows] == [0, 20, 40]
