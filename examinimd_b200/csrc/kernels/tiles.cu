@@ -47,7 +47,7 @@ struct TileArgs {
   int tx, ty, tz;           // interior cells per tile
   int ntx, nty, ntz;        // tiles per dimension
   int stride;               // atom slots (= threads of the per-atom kernels) per tile, multiple of 32
-  int maxrow;               // ELL row capacity, multiple of 4
+  int maxrow;               // ELL row capacity, multiple of 8
   int cap;                  // staged-atom capacity of the shared-memory arrays
   int n_local;
   const int *bincount, *binoffsets, *permute;
@@ -55,8 +55,15 @@ struct TileArgs {
   const int *type;
   double ox, oy, oz; // bin grid origin
   double wx, wy, wz; // bin widths
-  unsigned short *ell; // [ntiles][maxrow/4][stride][4]
+  unsigned short *ell; // [ntiles][maxrow/8][stride][8]: 8 entries of one atom = one 16-byte word
   int *nell;           // [ntiles][stride]
+  // per-tile staging tables written once per build (tiles_tables_kernel), so that the per-step
+  // force kernel needs no cell arithmetic: global index of every staged slot, and for every
+  // dense atom slot its staged slot / global index
+  int *stg_j;                // [ntiles][cap]
+  int *stg_n;                // [ntiles]  staged atoms
+  unsigned short *int_slot;  // [ntiles][stride]
+  int *int_glob;             // [ntiles][stride]  (>= n_local or 0x7fffffff: no row)
   int *flags;          // [0] overflow bits (1 staged, 2 interior, 4 row)  [1] max row  [2] max staged  [3] max interior
 };
 
@@ -126,7 +133,7 @@ __device__ __forceinline__ void tile_setup(const TileArgs &a, TileCtx &t, int *s
   t.n_int = s_ibase[t.nci];
 }
 
-enum { ST_F32 = 1, ST_F64 = 2, ST_J = 4, ST_TYPE = 8 };
+enum { ST_F32 = 1, ST_F64 = 2, ST_J = 4, ST_TYPE = 8, ST_AOS = 16 }; // ST_AOS: FP64 coordinates as sx[3*slot + {0,1,2}]
 
 template <int WHAT>
 __device__ __forceinline__ void tile_stage(const TileArgs &a, const TileCtx &t, const int *s_start, const int *s_goff,
@@ -142,6 +149,7 @@ __device__ __forceinline__ void tile_stage(const TileArgs &a, const TileCtx &t, 
       const int s = base + k;
       if (WHAT & ST_F32) sf[s] = make_float4((float)(xj - cx0), (float)(yj - cy0), (float)(zj - cz0), 0.f);
       if (WHAT & ST_F64) { sx[s] = xj; sy[s] = yj; sz[s] = zj; }
+      if (WHAT & ST_AOS) { sx[3 * s] = xj; sx[3 * s + 1] = yj; sx[3 * s + 2] = zj; }
       if (WHAT & ST_J) sj[s] = j;
       if (WHAT & ST_TYPE) st[s] = (unsigned char)a.type[j];
     }
@@ -164,7 +172,7 @@ __device__ __forceinline__ void tile_interior_table(const TileArgs &a, const Til
 }
 
 __device__ __forceinline__ size_t ell_index(const TileArgs &a, int tile, int q, int t) {
-  return (((size_t)tile * (a.maxrow >> 2) + (q >> 2)) * a.stride + t) * 4 + (q & 3);
+  return (((size_t)tile * (a.maxrow >> 3) + (q >> 3)) * a.stride + t) * 8 + (q & 7);
 }
 
 // ---------------------------------------------------------------------------- FP32 pre-filter
@@ -214,9 +222,38 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_filter_kernel(TileArgs a
         }
       }
       if (in_cell) {
+        // pad the last 8-entry word with an in-bounds slot: the force kernel loads whole words
+        for (int qp = q; qp < min((q + 7) & ~7, a.maxrow); qp++) a.ell[ell_index(a, t.tile, qp, tslot)] = (unsigned short)own;
         a.nell[(size_t)t.tile * a.stride + tslot] = min(q, a.maxrow);
         if (q > a.maxrow) { atomicOr(&a.flags[0], 4); atomicMax(&a.flags[1], q); }
       }
+    }
+  }
+}
+
+// per-tile staging tables for the force kernel (see TileArgs)
+__global__ void __launch_bounds__(kFilterThreads) tiles_tables_kernel(TileArgs a) {
+  __shared__ int s_start[kMaxStagedCells + 1], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
+  TileCtx t;
+  tile_setup(a, t, s_start, s_goff, s_ibase);
+  if (t.total > a.cap || t.n_int > a.stride) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) a.stg_n[t.tile] = t.total;
+  for (int c = warp; c < t.ncs; c += nwarps) {
+    const int base = s_start[c], n = s_start[c + 1] - base, goff = s_goff[c];
+    for (int k = lane; k < n; k += 32) a.stg_j[(size_t)t.tile * a.cap + base + k] = a.permute[goff + k];
+  }
+  for (int k = t.n_int + threadIdx.x; k < a.stride; k += blockDim.x) {
+    a.int_slot[(size_t)t.tile * a.stride + k] = 0;
+    a.int_glob[(size_t)t.tile * a.stride + k] = 0x7fffffff;
+  }
+  for (int ci = warp; ci < t.nci; ci += nwarps) {
+    const int n = s_ibase[ci + 1] - s_ibase[ci];
+    if (n == 0) continue;
+    const int c = staged_of_interior(t, a, ci);
+    for (int k = lane; k < n; k += 32) {
+      a.int_slot[(size_t)t.tile * a.stride + s_ibase[ci] + k] = (unsigned short)(s_start[c] + k);
+      a.int_glob[(size_t)t.tile * a.stride + s_ibase[ci] + k] = a.permute[s_goff[c] + k];
     }
   }
 }
@@ -296,63 +333,144 @@ __device__ __forceinline__ double fast_rcp(double a) {
   return y;
 }
 
+// Four pairs (one ELL word) at a time, branch-free and written stage by stage so that the four
+// ~20-instruction FP64 dependency chains are interleaved by the scheduler.
 template <bool ONETYPE, bool ENERGY>
-__global__ void __launch_bounds__(384) lj_tiles_kernel(TileArgs a, LJOne one, const LJTab *__restrict__ tab, double *__restrict__ f,
-                                                       double *__restrict__ pe_partial) {
-  __shared__ int s_start[kMaxStagedCells + 1], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
-  __shared__ double s_red[12];
-  extern __shared__ __align__(16) unsigned char dyn[];
-  double *sx = reinterpret_cast<double *>(dyn), *sy = sx + a.cap, *sz = sy + a.cap;
-  int *s_iglob = reinterpret_cast<int *>(sz + a.cap);
-  unsigned short *s_islot = reinterpret_cast<unsigned short *>(s_iglob + a.stride);
-  unsigned char *st = reinterpret_cast<unsigned char *>(s_islot + a.stride);
-  TileCtx t;
-  tile_setup(a, t, s_start, s_goff, s_ibase);
-  tile_stage<ST_F64 | (ONETYPE ? 0 : ST_TYPE)>(a, t, s_start, s_goff, nullptr, sx, sy, sz, nullptr, st);
-  tile_interior_table(a, t, s_start, s_goff, s_ibase, s_islot, s_iglob);
-  __syncthreads();
-  const int ts = threadIdx.x;
-  double pe = 0.0;
-  const int i = ts < t.n_int ? s_iglob[ts] : 0x7fffffff;
-  if (i < a.n_local) {
-    const int own = s_islot[ts];
-    const int n = a.nell[(size_t)t.tile * a.stride + ts];
-    const double x_i = sx[own], y_i = sy[own], z_i = sz[own];
-    const int type_i = ONETYPE ? 0 : st[own];
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    const ushort4 *row = reinterpret_cast<const ushort4 *>(a.ell) + ((size_t)t.tile * (a.maxrow >> 2)) * a.stride + ts;
-    const int nchunk = (n + 3) >> 2;
-    ushort4 cur = nchunk > 0 ? row[0] : make_ushort4(0, 0, 0, 0);
-    for (int c = 0; c < nchunk; c++) {
-      const ushort4 nxt = (c + 1 < nchunk) ? row[(size_t)(c + 1) * a.stride] : make_ushort4(0, 0, 0, 0);
-      const int left = n - 4 * c;
-      const unsigned short sl[4] = {cur.x, cur.y, cur.z, cur.w};
+__device__ __forceinline__ void lj_quad(const double *__restrict__ sp, const int *__restrict__ st, const ushort4 w, int left,
+                                        double x_i, double y_i, double z_i, int type_i, const LJOne &one, const LJTab *__restrict__ tab,
+                                        double &fx, double &fy, double &fz, double &pe) {
+  const int sl[4] = {w.x, w.y, w.z, w.w};
+  double dx[4], dy[4], dz[4], rsq[4], lj1[4], lj2[4], cutsq[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (u < left) {
-          const int s = sl[u];
-          const double dx = x_i - sx[s], dy = y_i - sy[s], dz = z_i - sz[s];
-          const double rsq = dx * dx + dy * dy + dz * dz;
-          double lj1, lj2, cutsq;
-          if (ONETYPE) { lj1 = one.lj1; lj2 = one.lj2; cutsq = one.cutsq; }
-          else { const int tij = type_i * tab->ntypes + st[s]; lj1 = tab->lj1[tij]; lj2 = tab->lj2[tij]; cutsq = tab->cutsq[tij]; }
-          if (rsq < cutsq) { // force_lj_neigh_impl.h:189 (strict)
-            const double r2inv = fast_rcp(rsq);
-            const double r6inv = r2inv * r2inv * r2inv;
-            const double fpair = (r6inv * (lj1 * r6inv - lj2)) * r2inv;
-            fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
-            if (ENERGY) { // force_lj_neigh_impl.h:271-278 with fac = 0.5 (every pair is seen from both sides)
-              const double r2invc = 1.0 / cutsq, r6invc = r2invc * r2invc * r2invc;
-              pe += 0.5 * r6inv * (0.5 * lj1 * r6inv - lj2) / 6.0;
-              pe -= 0.5 * r6invc * (0.5 * lj1 * r6invc - lj2) / 6.0;
-            }
-          }
-        }
-      }
-      cur = nxt;
-    }
-    if (!ENERGY) { f[3 * (size_t)i] = fx; f[3 * (size_t)i + 1] = fy; f[3 * (size_t)i + 2] = fz; }
+  for (int u = 0; u < 4; u++) {
+    const double *p = sp + 3 * sl[u];
+    dx[u] = x_i - p[0]; dy[u] = y_i - p[1]; dz[u] = z_i - p[2];
+    if (ONETYPE) { lj1[u] = one.lj1; lj2[u] = one.lj2; cutsq[u] = one.cutsq; }
+    else { const int tij = type_i * tab->ntypes + st[sl[u]]; lj1[u] = tab->lj1[tij]; lj2[u] = tab->lj2[tij]; cutsq[u] = tab->cutsq[tij]; }
   }
+#pragma unroll
+  for (int u = 0; u < 4; u++) rsq[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+  bool in[4];
+  double r2inv[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    in[u] = (u < left) && rsq[u] < cutsq[u]; // force_lj_neigh_impl.h:189 (strict)
+    r2inv[u] = fast_rcp(rsq[u]); // padded entries (rsq = 0) give inf/NaN below, discarded by the select on in[u]
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const double r6inv = r2inv[u] * r2inv[u] * r2inv[u];
+    const double fpair = in[u] ? (r6inv * (lj1[u] * r6inv - lj2[u])) * r2inv[u] : 0.0;
+    fx += dx[u] * fpair; fy += dy[u] * fpair; fz += dz[u] * fpair;
+    if (ENERGY) { // force_lj_neigh_impl.h:271-278 with fac = 0.5 (every pair is seen from both sides)
+      const double r2invc = 1.0 / cutsq[u], r6invc = r2invc * r2invc * r2invc;
+      const double e = 0.5 * r6inv * (0.5 * lj1[u] * r6inv - lj2[u]) / 6.0 - 0.5 * r6invc * (0.5 * lj1[u] * r6invc - lj2[u]) / 6.0;
+      pe += in[u] ? e : 0.0;
+    }
+  }
+}
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int kForceThreads = 384;
+constexpr int kStagePerThread = 8; // cap <= kForceThreads * kStagePerThread
+
+// Persistent CTAs (2 per SM), each walking tiles blockIdx.x, +gridDim.x, ...  The coordinates of
+// tile n+1 are copied global->shared with cp.async (LDGSTS) into the second buffer while tile n
+// is computed, and the staging indices of tile n+2 are prefetched into registers, so no global
+// latency is exposed between tiles.
+template <bool ONETYPE, bool ENERGY>
+__global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int ntiles, LJOne one, const LJTab *__restrict__ tab,
+                                                                   double *__restrict__ f, double *__restrict__ pe_partial) {
+  __shared__ double s_red[kForceThreads / 32];
+  extern __shared__ __align__(16) unsigned char dyn[];
+  double *const sp0 = reinterpret_cast<double *>(dyn); // 2 x [cap][3]: x,y,z of a staged atom adjacent (one address computation per pair)
+  int *const st0 = reinterpret_cast<int *>(sp0 + 6 * (size_t)a.cap); // 2 x [cap] types (multi-type systems only)
+  const int ts = threadIdx.x;
+  const int G = gridDim.x;
+  int jreg[kStagePerThread];
+
+  auto load_j = [&](int tile) { // staging indices of `tile` into registers (coalesced)
+    if (tile < ntiles) {
+      const int n = a.stg_n[tile];
+      const int *src = a.stg_j + (size_t)tile * a.cap;
+#pragma unroll
+      for (int k = 0; k < kStagePerThread; k++) { const int s = ts + k * kForceThreads; jreg[k] = s < n ? src[s] : -1; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kStagePerThread; k++) jreg[k] = -1;
+    }
+  };
+  auto issue_copies = [&](int buf) {
+#pragma unroll
+    for (int k = 0; k < kStagePerThread; k++) {
+      const int j = jreg[k];
+      if (j >= 0) {
+        const int s = ts + k * kForceThreads;
+        const double *src = a.x + 3 * (size_t)j;
+        double *dst = sp0 + (size_t)buf * 3 * a.cap + 3 * s;
+        cp_async8(dst, src); cp_async8(dst + 1, src + 1); cp_async8(dst + 2, src + 2);
+        if (!ONETYPE) cp_async4(st0 + (size_t)buf * a.cap + s, a.type + j);
+      }
+    }
+  };
+
+  int tile = blockIdx.x;
+  load_j(tile);
+  issue_copies(0);
+  load_j(tile + G);
+  // per-thread row descriptors of the current tile
+  int i_cur = 0x7fffffff, own_cur = 0, n_cur = 0;
+  if (tile < ntiles) {
+    i_cur = a.int_glob[(size_t)tile * a.stride + ts];
+    own_cur = a.int_slot[(size_t)tile * a.stride + ts];
+    n_cur = a.nell[(size_t)tile * a.stride + ts];
+  }
+  double pe = 0.0;
+  int buf = 0;
+  for (; tile < ntiles; tile += G, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads(); // buffer `buf` is complete; every thread is done with buffer `buf^1`
+    issue_copies(buf ^ 1);  // tile + G
+    load_j(tile + 2 * G);
+    int i_nxt = 0x7fffffff, own_nxt = 0, n_nxt = 0;
+    if (tile + G < ntiles) {
+      i_nxt = a.int_glob[(size_t)(tile + G) * a.stride + ts];
+      own_nxt = a.int_slot[(size_t)(tile + G) * a.stride + ts];
+      n_nxt = a.nell[(size_t)(tile + G) * a.stride + ts];
+    }
+    const double *sp = sp0 + (size_t)buf * 3 * a.cap;
+    const int *st = st0 + (size_t)buf * a.cap;
+    if (i_cur < a.n_local) {
+      const double x_i = sp[3 * own_cur], y_i = sp[3 * own_cur + 1], z_i = sp[3 * own_cur + 2];
+      const int type_i = ONETYPE ? 0 : st[own_cur];
+      double fx = 0.0, fy = 0.0, fz = 0.0;
+      // one 16-byte word = 8 neighbors; the next word is requested before the current one is used
+      const uint4 *row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)tile * (a.maxrow >> 3)) * a.stride + ts;
+      const int nchunk = (n_cur + 7) >> 3;
+      uint4 cur = nchunk > 0 ? row[0] : make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < nchunk; c++) {
+        const uint4 nxt = (c + 1 < nchunk) ? row[(size_t)(c + 1) * a.stride] : make_uint4(0, 0, 0, 0);
+        const int left = n_cur - 8 * c; // the filter pads the last word with in-bounds slots
+        const ushort4 lo = make_ushort4(cur.x & 0xffff, cur.x >> 16, cur.y & 0xffff, cur.y >> 16);
+        const ushort4 hi = make_ushort4(cur.z & 0xffff, cur.z >> 16, cur.w & 0xffff, cur.w >> 16);
+        lj_quad<ONETYPE, ENERGY>(sp, st, lo, left, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+        lj_quad<ONETYPE, ENERGY>(sp, st, hi, left - 4, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+        cur = nxt;
+      }
+      if (!ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
+    }
+    i_cur = i_nxt; own_cur = own_nxt; n_cur = n_nxt;
+  }
+  cp_async_wait_all();
   if (ENERGY) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pe += __shfl_down_sync(0xffffffffu, pe, o);
@@ -367,9 +485,7 @@ __global__ void __launch_bounds__(384) lj_tiles_kernel(TileArgs a, LJOne one, co
 }
 
 size_t emit_smem(int cap, int stride) { return (size_t)cap * (3 * sizeof(double) + sizeof(int)) + (size_t)stride * sizeof(unsigned short); }
-size_t force_smem(int cap, int stride, bool types) {
-  return (size_t)cap * 3 * sizeof(double) + (size_t)stride * (sizeof(int) + sizeof(unsigned short)) + (types ? (size_t)cap : 0) + 16;
-}
+size_t force_smem(int cap, bool types) { return 2 * ((size_t)cap * 3 * sizeof(double) + (types ? (size_t)cap * sizeof(int) : 0)); }
 
 } // namespace
 
@@ -381,7 +497,12 @@ struct emd_tiles {
   bool valid = false;
   unsigned short *d_ell = nullptr; size_t ell_cap = 0;
   int *d_nell = nullptr; size_t nell_cap = 0;
+  int *d_stg_j = nullptr; size_t stg_j_cap = 0;
+  int *d_stg_n = nullptr; size_t stg_n_cap = 0;
+  unsigned short *d_int_slot = nullptr; size_t int_slot_cap = 0;
+  int *d_int_glob = nullptr; size_t int_glob_cap = 0;
   int *d_flags = nullptr;
+  int num_sms = 148;
   LJTab *d_tab = nullptr;
   double neigh_cut = 0.0;
   float cutf2 = 0.f;
@@ -420,6 +541,7 @@ int emd_tiles_create(emd_tiles **out) {
   int dev = 0;
   EMD_CUDA(cudaGetDevice(&dev));
   EMD_CUDA(cudaDeviceGetAttribute(&t->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  EMD_CUDA(cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev));
   *out = t;
   return 0;
 }
@@ -428,6 +550,10 @@ void emd_tiles_destroy(emd_tiles *t) {
   if (!t) return;
   if (t->d_ell) cudaFree(t->d_ell);
   if (t->d_nell) cudaFree(t->d_nell);
+  if (t->d_stg_j) cudaFree(t->d_stg_j);
+  if (t->d_stg_n) cudaFree(t->d_stg_n);
+  if (t->d_int_slot) cudaFree(t->d_int_slot);
+  if (t->d_int_glob) cudaFree(t->d_int_glob);
   if (t->d_flags) cudaFree(t->d_flags);
   if (t->d_tab) cudaFree(t->d_tab);
   delete t;
@@ -465,7 +591,7 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
   a.x = d_x; a.type = nullptr;
   a.ox = g->minx; a.oy = g->miny; a.oz = g->minz;
   a.wx = wx; a.wy = wy; a.wz = wz;
-  a.stride = 384;
+  a.stride = kForceThreads;
   // mean atoms per cell -> tile shape with ~0.9*stride atoms whose halo fits in shared memory
   const double m = std::max(1e-3, (double)n_all / ((double)g->nbinx * g->nbiny * g->nbinz));
   const int cap_max = 3000; // 72 KB of FP64 coordinates: three force CTAs per SM
@@ -488,7 +614,7 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
   // expected full-list row: density * sphere volume, +35 % head room
   const double rho = m / (wx * wy * wz);
   int maxrow = (int)(rho * 4.18879020478639 * neigh_cut * neigh_cut * neigh_cut * 1.35) + 8;
-  maxrow = std::max(16, (maxrow + 3) / 4 * 4);
+  maxrow = std::max(16, (maxrow + 7) / 8 * 8);
   // conservative FP32 radius: coordinates are relative to the staged region (extent E), so the
   // FP32 distance is off by < 8*E*2^-24; take 32*E*2^-23 + 2^-20 relative as the margin
   const double E = std::max({(a.tx + 2) * wx, (a.ty + 2) * wy, (a.tz + 2) * wz});
@@ -509,14 +635,27 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
     EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     EMD_CUDA(cudaStreamSynchronize(ctx->stream));
     const int bits = ctx->h_pinned[0], need_row = ctx->h_pinned[1], need_cap = ctx->h_pinned[2], need_int = ctx->h_pinned[3];
-    if (bits == 0) { t->valid = true; return 0; }
+    if (bits == 0) {
+      // the slot numbering does not depend on cap: shrink it to the largest tile, so that the force
+      // kernel's two coordinate buffers leave room for two CTAs per SM
+      a.cap = std::max(32, (need_cap + 31) / 32 * 32);
+      if (a.cap > kForceThreads * kStagePerThread) return 3;
+      if (ensure_bytes((void **)&t->d_stg_j, &t->stg_j_cap, (size_t)t->ntiles * a.cap * sizeof(int))) return 1;
+      if (ensure_bytes((void **)&t->d_stg_n, &t->stg_n_cap, (size_t)t->ntiles * sizeof(int))) return 1;
+      if (ensure_bytes((void **)&t->d_int_slot, &t->int_slot_cap, (size_t)t->ntiles * a.stride * sizeof(unsigned short))) return 1;
+      if (ensure_bytes((void **)&t->d_int_glob, &t->int_glob_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
+      a.stg_j = t->d_stg_j; a.stg_n = t->d_stg_n; a.int_slot = t->d_int_slot; a.int_glob = t->d_int_glob;
+      EMD_LAUNCH(ctx, tiles_tables_kernel, t->ntiles, kFilterThreads, 0, a);
+      t->valid = true;
+      return 0;
+    }
     if (bits & 2) { (void)need_int; return 3; } // a tile holds more atoms than threads: density far from the estimate
     if (bits & 1) {
       if (need_cap > cap_max || need_cap > 65535) return 3;
       a.cap = (need_cap + need_cap / 16 + 31) / 32 * 32;
       if (a.cap > cap_max) a.cap = cap_max;
     }
-    if (bits & 4) maxrow = (need_row + need_row / 8 + 3) / 4 * 4;
+    if (bits & 4) maxrow = (need_row + need_row / 8 + 7) / 8 * 8;
   }
   return 3;
 }
@@ -591,21 +730,23 @@ int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, co
     EMD_CUDA(cudaMemcpyAsync(t->d_tab, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
     EMD_CUDA(cudaStreamSynchronize(ctx->stream)); // h is a stack object
   }
-  const size_t smem = force_smem(a.cap, a.stride, !one);
+  const size_t smem = force_smem(a.cap, !one);
+  if (smem > (size_t)t->max_smem_optin) { set_error("emd_force_lj_compute_tiles: tile does not fit in shared memory"); return 1; }
+  const int grid = std::min(t->ntiles, 2 * t->num_sms);
   double *partial = nullptr;
   if (h_pe) {
-    if (ctx->s_c.ensure(sizeof(double) * ((size_t)t->ntiles + 8))) return 1;
+    if (ctx->s_c.ensure(sizeof(double) * ((size_t)grid + 8))) return 1;
     partial = ctx->s_c.as<double>() + 8;
   }
-#define EMD_LJ_TILES(ONE, EN)                                                                              \
-  do {                                                                                                     \
-    if (set_smem(lj_tiles_kernel<ONE, EN>, smem)) return 1;                                                \
-    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN>), t->ntiles, a.stride, smem, a, p1, t->d_tab, d_f, partial); \
+#define EMD_LJ_TILES(ONE, EN)                                                                                          \
+  do {                                                                                                                 \
+    if (set_smem(lj_tiles_kernel<ONE, EN>, smem)) return 1;                                                            \
+    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN>), grid, kForceThreads, smem, a, t->ntiles, p1, t->d_tab, d_f, partial);  \
   } while (0)
   if (h_pe) { if (one) EMD_LJ_TILES(true, true); else EMD_LJ_TILES(false, true); }
   else { if (one) EMD_LJ_TILES(true, false); else EMD_LJ_TILES(false, false); }
 #undef EMD_LJ_TILES
-  if (h_pe) return device_sum_partials(ctx, partial, t->ntiles, h_pe);
+  if (h_pe) return device_sum_partials(ctx, partial, grid, h_pe);
   return 0;
 }
 
