@@ -47,26 +47,44 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------ CPU baseline
-def run_oracle(region, nsteps, threads=None):
-    exe = REPO / "oracle" / "oracle_md_omp"
-    if not exe.exists():
-        subprocess.run(["make", "-C", str(REPO / "oracle"), "oracle_md_omp"], check=True, capture_output=True)
+REF_OMP = REPO / "oracle" / "_ref" / "ExaMiniMD_ref_omp"  # the UNMODIFIED reference over the host-only Kokkos stand-in (oracle/Makefile.ref)
+PERF_RE = re.compile(r"^(\d+) (\d+) \| (\S+) (\S+) (\S+) (\S+) (\S+) \| (\S+) (\S+) (\S+) PERFORMANCE", re.M)
+
+
+def cpu_env(cores):
+    return dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close", OMP_PLACES="cores")
+
+
+def run_reference_cpu(region, nsteps, threads=None):
+    """the reference's own CPU implementation of the path on all host cores: oracle/_ref when it was built (kind
+    "reference"), else the oracle port (kind "port").  Returns the numbers of its PERFORMANCE line."""
     cores = threads or os.cpu_count() or 1
-    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close", OMP_PLACES="cores")
-    cmd = [str(exe), "-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--region", *map(str, region),
-           "--nsteps", str(nsteps)]
     t0 = time.time()
-    out = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True).stdout
-    m = re.search(r"^(\d+) (\d+) \| (\S+) (\S+) (\S+) (\S+) (\S+) \| (\S+) (\S+) (\S+) PERFORMANCE", out, re.M)
-    return {"value": float(m.group(9)), "atoms": int(m.group(2)), "loop_s": float(m.group(3)), "cores": cores,
+    if REF_OMP.exists():
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:  # the reference has no --region/--nsteps flags: edit the deck's region/run lines
+            deck = Path(td) / "in.deck"
+            txt = re.sub(r"region\s+box block.*", "region\t\tbox block 0 %d 0 %d 0 %d" % tuple(region), DECK.read_text())
+            deck.write_text(re.sub(r"run\s+\d+", "run\t\t%d" % nsteps, txt))
+            out = subprocess.run([str(REF_OMP), "-il", str(deck), "--comm-type", "SERIAL", "--neigh-type", "CSR", "--force-iteration",
+                                  "NEIGH_HALF"], capture_output=True, text=True, env=cpu_env(cores), check=True).stdout
+        kind, what = "reference", "oracle/_ref/ExaMiniMD_ref_omp (unmodified ExaMiniMD sources over the OpenMP Kokkos stand-in)"
+    else:
+        exe = REPO / "oracle" / "oracle_md_omp"
+        if not exe.exists():
+            subprocess.run(["make", "-C", str(REPO / "oracle"), "oracle_md_omp"], check=True, capture_output=True)
+        out = subprocess.run([str(exe), "-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--region",
+                              *map(str, region), "--nsteps", str(nsteps)], capture_output=True, text=True, env=cpu_env(cores), check=True).stdout
+        kind, what = "port", "oracle_md_omp (OpenMP restatement of the reference)"
+    m = PERF_RE.search(out)
+    return {"value": float(m.group(9)), "atoms": int(m.group(2)), "loop_s": float(m.group(3)), "cores": cores, "kind": kind, "what": what,
             "wall_s": time.time() - t0}
 
 
 def cpu_baseline(nsteps):
-    r = run_oracle((40, 40, 40), nsteps)
-    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-            "sample": f"oracle_md_omp (OpenMP restatement of the reference), in.lj 256000 atoms x {nsteps} steps, half CSR, "
-                      f"loop {r['loop_s']:.2f} s"}
+    r = run_reference_cpu((40, 40, 40), nsteps)
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+            "sample": f"{r['what']}, in.lj 256000 atoms x {nsteps} steps, half CSR, loop {r['loop_s']:.2f} s"}
 
 
 def reference_arm(args):
@@ -74,14 +92,14 @@ def reference_arm(args):
     if rank != 0:
         return
     total = args.steps + args.warmup
-    r = run_oracle((40, 40, 40), total)
+    r = run_reference_cpu((40, 40, 40), total)
     ms = 1e3 * r["loop_s"] / total
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": "256000-atom in.lj sample of the workload per step (CPU-bounded)"},
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                             "sample": f"in.lj 256000 atoms x {total} steps, half CSR, OpenMP oracle"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                             "sample": f"{r['what']}, in.lj 256000 atoms x {total} steps, half CSR"},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -285,7 +303,7 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(40)
+                line["cpu_baseline"] = cpu_baseline(20)
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
