@@ -32,8 +32,16 @@ CASES = [  # name, region, nsteps, newton, neigh, iteration, dump steps
 ]
 
 
-def make_deck(path, region, nsteps, newton):
-    txt = DECK.read_text()
+SNAP_DIR = REPO / "input" / "snap"
+SNAP_CASES = [  # name, deck, region, nsteps, neigh, dump steps  (newton on, full list: the only mode ForceSNAP accepts)
+    ("snap_W_4x4x4_csr", "in.snap.W", (4, 4, 4), 4, "CSR", (0, 1, 4)),
+    ("snap_W_4x5x6_2d", "in.snap.W", (4, 5, 6), 2, "2D", (0, 2)),
+    ("snap_Ta06A_4x4x4_csr", "in.snap.Ta06A", (4, 4, 4), 4, "CSR", (0, 1, 4)),
+]
+
+
+def make_deck(path, region, nsteps, newton, deck=DECK):
+    txt = Path(deck).read_text()
     txt = re.sub(r"region\s+box block.*", "region\t\tbox block 0 %d 0 %d 0 %d" % region, txt)
     txt = re.sub(r"run\s+\d+", "run\t\t%d" % nsteps, txt)
     txt = re.sub(r"newton \w+", "newton %s" % newton, txt)
@@ -53,14 +61,16 @@ def read_dump(p):
     return out
 
 
-def run_reference(region, nsteps, newton, neigh, iteration, dump_steps, exe=REF):
+def run_reference(region, nsteps, newton, neigh, iteration, dump_steps, exe=REF, deck_src=DECK):
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
         deck = td / "in.deck"
-        make_deck(deck, region, nsteps, newton)
+        make_deck(deck, region, nsteps, newton, deck_src)
+        for f in SNAP_DIR.glob("*.snap*"):  # coefficient files are opened relative to the working directory
+            (td / f.name).write_bytes(f.read_bytes())
         (td / "dump").mkdir()
         r = subprocess.run([str(exe), "-il", str(deck), "--comm-type", "SERIAL", "--neigh-type", neigh, "--force-iteration", iteration,
-                            "--dumpbinary", "1", str(td / "dump")], capture_output=True, text=True, check=True)
+                            "--dumpbinary", "1", str(td / "dump")], capture_output=True, text=True, check=True, cwd=td)
         thermo = np.array([[float(t) for t in l.split()[:4]] for l in r.stdout.splitlines() if re.match(r"^\d+ -?\d+\.\d+ ", l)])
         out = {"thermo": thermo, "region": np.array(region), "nsteps": np.array(nsteps)}
         for s in dump_steps:
@@ -79,6 +89,14 @@ def main():
         out["newton"] = np.array(1 if newton == "on" else 0)
         out["neigh"] = np.array(neigh)
         out["iteration"] = np.array(iteration)
+        np.savez_compressed(HERE / (name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items() if k.startswith("s0_") or k == "thermo"})
+    for name, deck, region, nsteps, neigh, steps in SNAP_CASES:
+        out = run_reference(region, nsteps, "on", neigh, "NEIGH_FULL", steps, deck_src=SNAP_DIR / deck)
+        out["newton"] = np.array(1)
+        out["neigh"] = np.array(neigh)
+        out["iteration"] = np.array("NEIGH_FULL")
+        out["deck"] = np.array(deck)
         np.savez_compressed(HERE / (name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith("s0_") or k == "thermo"})
 

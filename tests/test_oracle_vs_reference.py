@@ -20,10 +20,13 @@ REF_EXE = REPO / "oracle" / "_ref" / "ExaMiniMD_ref"
 sys.path.insert(0, str(REPO / "tests" / "golden"))
 
 
-def deck_for(tmp_path, region, nsteps, newton):
+SNAP_DIR = REPO / "input" / "snap"
+
+
+def deck_for(tmp_path, region, nsteps, newton, deck=None):
     import make_golden
     p = tmp_path / "in.deck"
-    make_golden.make_deck(p, tuple(int(r) for r in region), int(nsteps), "on" if newton else "off")
+    make_golden.make_deck(p, tuple(int(r) for r in region), int(nsteps), "on" if newton else "off", deck or make_golden.DECK)
     return p
 
 
@@ -41,8 +44,9 @@ def check_against(md, g, steps):
 @pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
 def test_oracle_reproduces_reference_dumps_bit_for_bit(oracle_lib, tmp_path, path):
     g = np.load(path)
-    deck = deck_for(tmp_path, g["region"], g["nsteps"], int(g["newton"]))
-    md = OracleMD.from_deck(deck, str(g["neigh"]), str(g["iteration"]))
+    snap = "deck" in g.files  # SNAP fixtures name the shipped deck they derive from (input/snap/)
+    deck = deck_for(tmp_path, g["region"], g["nsteps"], int(g["newton"]), SNAP_DIR / str(g["deck"]) if snap else None)
+    md = OracleMD.from_deck(deck, str(g["neigh"]), str(g["iteration"]), coeff_dir=SNAP_DIR if snap else None)
     steps = sorted(int(m.group(1)) for k in g.files if (m := re.match(r"s(\d+)_x", k)))
     assert steps[0] == 0
     np.testing.assert_array_equal(md.arr("type")[: md.geti("N_local")], g["s0_type"])
