@@ -43,6 +43,14 @@ class NeighList(C.Structure):
     _fields_ = [("d_row_map", C.c_void_p), ("d_num_neighs", C.c_void_p), ("d_neighs", C.c_void_p), ("stride", C.c_int)]
 
 
+class SnapParams(C.Structure):
+    """emd_snap_params (include/emd_b200.h)."""
+
+    _fields_ = [("twojmax", C.c_int), ("switchflag", C.c_int), ("ntypes", C.c_int), ("nelements", C.c_int), ("ncoeffall", C.c_int),
+                ("rcutfac", C.c_double), ("rfac0", C.c_double), ("rmin0", C.c_double), ("wself", C.c_double),
+                ("elem_of_type", C.c_int * 12), ("radelem", C.c_void_p), ("wjelem", C.c_void_p), ("coeffelem", C.c_void_p)]
+
+
 _P = C.c_void_p
 _D3 = C.c_double * 3
 _SIGS = {
@@ -88,6 +96,12 @@ _SIGS = {
     "emd_neigh_tiles_fill_csr": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "emd_neigh_tiles_fill_2d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "emd_force_lj_compute_tiles": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
+    "emd_snap_create": (C.c_int, [C.POINTER(_P), C.POINTER(SnapParams)]),
+    "emd_snap_destroy": (None, [_P]),
+    "emd_snap_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "emd_snap_device_ptr": (_P, [_P, C.c_char_p]),
+    "emd_force_snap_compute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NeighList)]),
     "emd_nve_initial_integrate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double]),
     "emd_nve_final_integrate": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double]),
     "emd_comm_wrap": (C.c_int, [_P, _P, C.c_int, _D3]),

@@ -107,6 +107,10 @@ void *emd_app_device_ptr(emd_app *a, const char *what) {
   if (!strcmp(what, "binoffsets")) return a->md->binning->binoffsets;
   if (!strcmp(what, "permute")) return a->md->binning->permute_vector;
   if (!strcmp(what, "tiles")) return a->md->neighbor->tiles();
+  if (!strcmp(what, "snap")) { // the emd_snap* of a ForceSNAP (function-level tests), else NULL
+    ForceSNAP *fs = dynamic_cast<ForceSNAP *>(a->md->force);
+    return fs ? fs->handle() : nullptr;
+  }
   const emd_neigh_list l = a->md->neighbor->list_view();
   if (!strcmp(what, "row_map")) return const_cast<int *>(l.d_row_map);
   if (!strcmp(what, "num_neighs")) return const_cast<int *>(l.d_num_neighs);

@@ -1,4 +1,7 @@
 // ForceSNAP -- SNAP bispectrum potential (src/force_types/force_snap_neigh.h).
+// Same three-way header as the reference module; the class parses the pair_coeff line and the two
+// coefficient files exactly like ForceSNAP<>::init_coeff/read_files and hands the result to the
+// sm_100a kernels of kernels/snap.cu through emd_snap_create / emd_force_snap_compute.
 #ifdef MODULES_OPTION_CHECK
 #endif
 #ifdef FORCE_MODULES_INSTANTIATION
@@ -11,19 +14,34 @@
 #ifndef FORCE_SNAP_NEIGH_H
 #define FORCE_SNAP_NEIGH_H
 #include "../force.h"
+#include <string>
+#include <vector>
 
 class ForceSNAP : public Force {
   System *sys;
-  struct Impl;
-  Impl *impl;
+  emd_snap *snap;
+
+  // what init_coeff / read_files leave behind (force_snap_neigh.h:95-130)
+  int nelements, ncoeffall, ncoeff;
+  std::vector<std::string> elements;
+  std::vector<double> radelem, wjelem, coeffelem; // [nelements], [nelements][ncoeffall]
+  std::vector<int> map;                          // [ntypes+1], filled from index 1 (:293-306)
+  double rcutfac, rfac0, rmin0, rcutmax;
+  int twojmax, diagonalstyle, switchflag, bzeroflag, quadraticflag;
+
+  void read_files(const char *coefffilename, const char *paramfilename);
 
 public:
   ForceSNAP(char **args, System *system, bool half_neigh_);
   ~ForceSNAP();
   void init_coeff(int nargs, char **args);
   void compute(System *system, Binning *binning, Neighbor *neighbor);
+  // Force::compute_energy is NOT overridden, as in the reference (thermo PE prints 0, src/force.h:54)
   bool zeroes_forces() const { return false; }
   const char *name();
+  T_F_FLOAT cutoff() const { return rcutmax; }
+  int num_coeff() const { return ncoeff; }
+  emd_snap *handle() const { return snap; }
 };
 #endif
 #endif

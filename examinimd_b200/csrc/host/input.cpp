@@ -207,6 +207,11 @@ void Input::read_file(const char *filename) {
 }
 
 void Input::read_lammps_file(const char *filename) {
+  {
+    const std::string path(filename);
+    const size_t slash = path.find_last_of('/');
+    system->input_dir = slash == std::string::npos ? std::string(".") : path.substr(0, slash);
+  }
   input_data.allocate_words(100);
   std::ifstream file(filename);
   if (!file.good()) {

@@ -6,6 +6,7 @@
 // cell sort (BinningKKSort swaps instead of copying back), and a host staging mirror is used
 // by Input (lattice creation) and the binary dump.
 #pragma once
+#include <string>
 #include <vector>
 #include "types.h"
 
@@ -44,6 +45,7 @@ public:
   bool do_print, print_lammps;
 
   emd_ctx *ctx; // device context all modules launch on
+  std::string input_dir; // directory of the input deck (second place ForceSNAP looks for its coefficient files)
 
   System();
   ~System();

@@ -1,0 +1,699 @@
+// snap.cu -- SNAP bispectrum force on B200 (FP64).
+//
+// Replaces ForceSNAP<>::compute (src/force_types/force_snap_neigh_impl.h:159-208, team kernel
+// :589-725) and the SNA class it drives (src/force_types/sna_impl.hpp).  The reference evaluates,
+// per atom, U_tot -> Z(j1,j2,j) -> and per neighbor dU -> dB(j1,j2,j) -> sum_k beta_k dB_k, with
+// 0.94 MB of global scratch per atom in flight.  Here the same force is evaluated in the adjoint
+// order (the one BASELINE.json names: ui / yi / duidrj / deidrj):
+//
+//   Y(j)      = sum_{(j1>=j2)} betaj(j1,j2,j) Z(j1,j2,j)          (beta folded in once per atom)
+//   F_ij      = 2 sum_{j,mb<=j/2,ma} w(j,mb,ma) Re( conj(dU_j(mb,ma)) Y_j(mb,ma) ) - 1.5e6 rij/r^14
+//
+// which is the reference's sum regrouped (compute_dbidrj's three conj(dU).Z sums, sna_impl.hpp:
+// 393-527, each land on the Z block whose LAST index is the dU level); betaj carries the
+// (j+1)/(j1+1), (j+1)/(j2+1) factors and w the half-column weights (1, 1/2 on the diagonal of the
+// middle column, 0 below it).  No per-neighbor dB and no Z array exist: per atom the state is
+// U_tot and Y on the half range mb <= j/2 (155 complex numbers each at 2J=8 instead of 2 x 9^5).
+//
+// Kernels (FP64 FMA pipe is the bound; nothing here is a dense contraction, so no tensor cores):
+//   snap_pairs_*   in-cutoff pair list (count, scan, fill): lanes stay dense in the two pair kernels
+//   snap_ui        lanes = 32 atoms, one warp per column mb of the Wigner recursion (VMK 4.8.2,
+//                  compute_uarray :641-720); a column is independent of the others except for its
+//                  first level, which each warp re-derives (levels 2k,2k+1 of columns k<mb: every
+//                  warp ends up with the same 45 element updates per neighbor at 2J=8); U_tot is
+//                  accumulated in shared memory without atomics or cross-lane reductions
+//   snap_yi        lanes = 32 atoms, U_tot of the batch expanded to the full (ma,mb) range in
+//                  146 KB of shared memory ([element][lane], conflict-free); warps take output
+//                  strips (j, ma) from a cost-sorted queue and run the Clebsch-Gordan double sum
+//                  (compute_zi :196-283) for every mb of the strip, accumulating beta*Z in registers
+//   snap_deidrj    lanes = in-cutoff pairs; the dU recursion (compute_duarray :728-893) runs
+//                  column by column IN PLACE in registers (9 + 3x9 complex) and every finished
+//                  level is contracted with Y on the fly; f_i += F_ij, f_j -= F_ij with RED.F64
+//                  (57 per atom-step: three orders of magnitude below the RED rate of the part)
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+using namespace emd;
+
+namespace {
+
+constexpr int kMaxJ = 8;              // twojmax <= 8
+constexpr int kMaxCol = kMaxJ / 2 + 1;
+constexpr int kMaxTriples = 125;
+constexpr int kMaxStrips = 45;
+constexpr int kRootDim = kMaxJ + 2;   // rootpq[p][q], p,q in 0..twojmax+1
+constexpr double kPi = 3.14159265358979323846;
+
+struct Triple { short j1, j2, j, pad; int cgoff; };
+
+struct SnapTab {
+  int twojmax, ncol, nuh, nuf, ntriples, nstrips, ncg, ntypes, nelements, switchflag;
+  double rcutfac, rfac0, rmin0, wself, cutsq;
+  int uh_block[kMaxJ + 1];   // half layout: (j,mb,ma), mb <= j/2, at uh_block[j] + mb*(j+1) + ma
+  int uf_block[kMaxJ + 1];   // full layout: (j,ma,mb) at uf_block[j] + ma*(j+1) + mb  (the reference's u(j,ma,mb))
+  double rootpq[kRootDim * kRootDim];
+  Triple triple[kMaxTriples];         // sorted by j
+  int tri_begin[kMaxJ + 2];           // triples of output level j: [tri_begin[j], tri_begin[j+1])
+  short strip_j[kMaxStrips], strip_ma[kMaxStrips]; // output strips, most expensive first
+  int elem_of_type[kMaxTypesConst];
+  double radelem[kMaxTypesConst], wjelem[kMaxTypesConst];
+};
+
+// ------------------------------------------------------------------ host: index lists and tables
+int imin(int a, int b) { return a < b ? a : b; }
+int imax(int a, int b) { return a > b ? a : b; }
+
+double factorial(int n) { // sna_impl.hpp:962-968
+  double r = 1.0;
+  for (int i = 1; i <= n; i++) r *= 1.0 * i;
+  return r;
+}
+double deltacg(int j1, int j2, int j) { // sna_impl.hpp:975-981
+  const double sfaccg = factorial((j1 + j2 + j) / 2 + 1);
+  return sqrt(factorial((j1 + j2 - j) / 2) * factorial((j1 - j2 + j) / 2) * factorial((-j1 + j2 + j) / 2) / sfaccg);
+}
+// Clebsch-Gordan coefficient cgarray(j1,j2,j,m1,m2), quasi-binomial formula VMK 8.2.1(3) (sna_impl.hpp:991-1046)
+double clebsch_gordan(int j1, int j2, int j, int m1, int m2) {
+  const int aa2 = 2 * m1 - j1, bb2 = 2 * m2 - j2;
+  const int m = (aa2 + bb2 + j) / 2;
+  if (m < 0 || m > j) return 0.0;
+  double sum = 0.0;
+  for (int z = imax(0, imax(-(j - j2 + aa2) / 2, -(j - j1 - bb2) / 2)); z <= imin((j1 + j2 - j) / 2, imin((j1 - aa2) / 2, (j2 + bb2) / 2)); z++) {
+    const int ifac = z % 2 ? -1 : 1;
+    sum += ifac / (factorial(z) * factorial((j1 + j2 - j) / 2 - z) * factorial((j1 - aa2) / 2 - z) * factorial((j2 + bb2) / 2 - z) *
+                   factorial((j - j2 + aa2) / 2 + z) * factorial((j - j1 - bb2) / 2 + z));
+  }
+  const int cc2 = 2 * m - j;
+  const double dcg = deltacg(j1, j2, j);
+  const double sfaccg = sqrt(factorial((j1 + aa2) / 2) * factorial((j1 - aa2) / 2) * factorial((j2 + bb2) / 2) * factorial((j2 - bb2) / 2) *
+                             factorial((j + cc2) / 2) * factorial((j - cc2) / 2) * (j + 1));
+  return sum * dcg * sfaccg;
+}
+
+} // namespace
+
+struct emd_snap {
+  SnapTab h;              // host copy of the tables
+  SnapTab *d_tab = nullptr;
+  double *d_cg = nullptr;     // compact Clebsch-Gordan blocks, one (j1+1)x(j2+1) block per triple
+  double *d_betaj = nullptr;  // [nelements][ntriples]
+  int ncoeff = 0;
+  // work arrays (grow-only)
+  Scratch ulist, ylist, cnt, pair_i, pair_j, queue;
+  int ucap = 0;           // atoms the U/Y arrays are sized for (= row stride of ulist)
+  int npairs = 0;
+  int max_smem_optin = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ void row_of(const emd_neigh_list &l, int i, const int *&row, int &n) {
+  if (l.d_row_map) {
+    const int b = l.d_row_map[i];
+    n = l.d_row_map[i + 1] - b;
+    row = l.d_neighs + b;
+  } else {
+    n = l.d_num_neighs[i];
+    row = l.d_neighs + (size_t)i * l.stride;
+  }
+}
+
+// ------------------------------------------------------------------------------ in-cutoff pairs
+// force_snap_neigh_impl.h:612-656: neighbors with rsq < rcutmax^2 (strict), in list order
+template <bool FILL>
+__global__ void __launch_bounds__(128) snap_pairs_kernel(const double *__restrict__ x, int n_local, emd_neigh_list list, double cutsq,
+                                                         int *__restrict__ cnt, int *__restrict__ pair_i, int *__restrict__ pair_j) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_local) return;
+  const double x_i = x[3 * (size_t)i], y_i = x[3 * (size_t)i + 1], z_i = x[3 * (size_t)i + 2];
+  const int *row;
+  int n;
+  row_of(list, i, row, n);
+  int c = FILL ? cnt[i] : 0;
+  for (int jj = 0; jj < n; jj++) {
+    const int j = row[jj];
+    const double dx = x[3 * (size_t)j] - x_i, dy = x[3 * (size_t)j + 1] - y_i, dz = x[3 * (size_t)j + 2] - z_i;
+    const double rsq = dx * dx + dy * dy + dz * dz;
+    if (rsq < cutsq) {
+      if (FILL) { pair_i[c] = i; pair_j[c] = j; }
+      c++;
+    }
+  }
+  if (!FILL) cnt[i] = c;
+}
+
+// Cayley-Klein parameters and switching function of one pair (compute_ui :166-181, compute_uarray :650-656,
+// compute_sfac :1098-1111)
+struct PairGeom {
+  double a_r, a_i, b_r, b_i, sfac;
+};
+
+__device__ __forceinline__ double sfac_of(const SnapTab &t, double r, double rcut) {
+  if (t.switchflag == 0) return 1.0;
+  if (r <= t.rmin0) return 1.0;
+  if (r > rcut) return 0.0;
+  const double rcutfac = kPi / (rcut - t.rmin0);
+  return 0.5 * (cos((r - t.rmin0) * rcutfac) + 1.0);
+}
+__device__ __forceinline__ double dsfac_of(const SnapTab &t, double r, double rcut) {
+  if (t.switchflag == 0) return 0.0;
+  if (r <= t.rmin0) return 0.0;
+  if (r > rcut) return 0.0;
+  const double rcutfac = kPi / (rcut - t.rmin0);
+  return -0.5 * sin((r - t.rmin0) * rcutfac) * rcutfac;
+}
+
+// One level of the Wigner-U recursion for column mb, in place (sna_impl.hpp:667-692):
+//   u_j(ma) = rootpq(j-ma, j-mb) conj(a) u_{j-1}(ma) - rootpq(ma, j-mb) conj(b) u_{j-1}(ma-1)
+// walked from ma = j down so that u_{j-1}(ma-1) is still the old value.
+__device__ __forceinline__ void u_level(double2 (&u)[kMaxJ + 1], int j, int mb, const double *__restrict__ s_rootpq, double a_r, double a_i,
+                                        double b_r, double b_i) {
+#pragma unroll
+  for (int ma = kMaxJ; ma >= 0; --ma) {
+    if (ma <= j) {
+      double nr = 0.0, ni = 0.0;
+      if (ma < j) {
+        const double c1 = s_rootpq[(j - ma) * kRootDim + (j - mb)];
+        nr = c1 * (a_r * u[ma].x + a_i * u[ma].y);
+        ni = c1 * (a_r * u[ma].y - a_i * u[ma].x);
+      }
+      if (ma > 0) {
+        const double c2 = s_rootpq[ma * kRootDim + (j - mb)];
+        nr -= c2 * (b_r * u[ma - 1].x + b_i * u[ma - 1].y);
+        ni -= c2 * (b_r * u[ma - 1].y - b_i * u[ma - 1].x);
+      }
+      u[ma] = make_double2(nr, ni);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ snap_ui
+// block = 32 atoms (lanes) x ncol warps (warp = column mb).  Dynamic shared memory:
+//   acc  [nuh][32] double2   U_tot accumulators of the batch (each warp touches only its column)
+//   boot [kMaxJ][blockDim] double2  hand-over of the inversion-symmetry image that starts the next column
+__global__ void __launch_bounds__(32 * kMaxCol) snap_ui_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ x,
+                                                               const int *__restrict__ type, int n_local, const int *__restrict__ poff,
+                                                               const int *__restrict__ pair_j, double2 *__restrict__ ulist, int ustride) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ double s_rootpq[kRootDim * kRootDim];
+  const SnapTab &t = *tab;
+  const int twojmax = t.twojmax, nuh = t.nuh;
+  double2 *acc = reinterpret_cast<double2 *>(dyn);
+  double2 *boot = acc + (size_t)nuh * 32;
+  const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < kRootDim * kRootDim; k += blockDim.x) s_rootpq[k] = t.rootpq[k];
+  for (int j = 2 * col; j <= twojmax; j++)
+    for (int ma = 0; ma <= j; ma++) acc[(size_t)(t.uh_block[j] + col * (j + 1) + ma) * 32 + lane] = make_double2(0.0, 0.0);
+  __syncthreads();
+
+  const int i = blockIdx.x * 32 + lane;
+  const bool valid = i < n_local;
+  const int ic = valid ? i : 0;
+  const double x_i = x[3 * (size_t)ic], y_i = x[3 * (size_t)ic + 1], z_i = x[3 * (size_t)ic + 2];
+  const int elem_i = t.elem_of_type[type[ic]];
+  const double rad_i = t.radelem[elem_i];
+  const int pbeg = valid ? poff[i] : 0, pcnt = valid ? poff[i + 1] - pbeg : 0;
+  int nmax = pcnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+
+  double2 u[kMaxJ + 1];
+  double2 *myboot = boot + threadIdx.x;
+  const int bstride = blockDim.x;
+  for (int k = 0; k < nmax; k++) {
+    const bool act = k < pcnt;
+    const int j = act ? pair_j[pbeg + k] : ic;
+    double dx = x[3 * (size_t)j] - x_i, dy = x[3 * (size_t)j + 1] - y_i, dz = x[3 * (size_t)j + 2] - z_i;
+    if (!act) { dx = 1.0; dy = 0.0; dz = 0.0; }
+    const int elem_j = t.elem_of_type[type[j]];
+    const double rcut = (rad_i + t.radelem[elem_j]) * t.rcutfac;
+    const double rsq = dx * dx + dy * dy + dz * dz;
+    const double r = sqrt(rsq);
+    const double theta0 = (r - t.rmin0) * t.rfac0 * kPi / (rcut - t.rmin0);
+    double sn, cs;
+    sincos(theta0, &sn, &cs);
+    const double z0 = r * cs / sn; // = r / tan(theta0), compute_ui :178
+    const double r0inv = 1.0 / sqrt(r * r + z0 * z0);
+    const double a_r = r0inv * z0, a_i = -r0inv * dz, b_r = r0inv * dy, b_i = -r0inv * dx;
+    const double sfac = act ? sfac_of(t, r, rcut) * t.wjelem[elem_j] : 0.0;
+
+    u[0] = make_double2(1.0, 0.0);
+    if (col == 0) { // level 0 belongs to column 0 (add_uarraytot :612-635)
+      double2 &q = acc[(size_t)t.uh_block[0] * 32 + lane];
+      q.x += sfac;
+    }
+    for (int c = 0; c <= col; c++) {
+      if (c > 0) { // level 2c-1 of column c = image of column c-1, written below
+#pragma unroll
+        for (int ma = 0; ma <= kMaxJ; ma++)
+          if (ma <= 2 * c - 1) u[ma] = myboot[ma * bstride];
+      }
+      const int jend = (c == col) ? twojmax : 2 * c + 1;
+      for (int jl = max(1, 2 * c); jl <= jend; jl++) {
+        u_level(u, jl, c, s_rootpq, a_r, a_i, b_r, b_i);
+        if (c == col) {
+          double2 *q = acc + (size_t)(t.uh_block[jl] + col * (jl + 1)) * 32 + lane;
+#pragma unroll
+          for (int ma = 0; ma <= kMaxJ; ma++)
+            if (ma <= jl) { double2 v = q[ma * 32]; v.x += sfac * u[ma].x; v.y += sfac * u[ma].y; q[ma * 32] = v; }
+        }
+      }
+      if (c < col) {
+        // inversion symmetry VMK 4.4(2) (:697-717): u(J, J-ma, J-mb) = (-1)^(ma+mb) conj(u(J, ma, mb)), J = 2c+1, mb = c
+        const int J = 2 * c + 1;
+#pragma unroll
+        for (int s = 0; s <= kMaxJ; s++)
+          if (s <= J) {
+            const double sg = ((s + c) & 1) ? -1.0 : 1.0;
+            myboot[(J - s) * bstride] = make_double2(sg * u[s].x, -sg * u[s].y);
+          }
+      }
+    }
+  }
+  // self term (addself_uarraytot :594-605) and write-out of this warp's column
+  if (valid) {
+    for (int j = 2 * col; j <= twojmax; j++)
+      for (int ma = 0; ma <= j; ma++) {
+        const int e = t.uh_block[j] + col * (j + 1) + ma;
+        double2 v = acc[(size_t)e * 32 + lane];
+        if (ma == col) v.x += t.wself;
+        ulist[(size_t)e * ustride + i] = v;
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------ snap_yi
+// block = 32 atoms (lanes) x W warps.  Dynamic shared memory: sU [nuf][32] double2 (full U_tot of the batch).
+constexpr int kYiWarps = 16;
+
+__global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ cg,
+                                                                const double *__restrict__ betaj, const int *__restrict__ type, int n_local,
+                                                                const double2 *__restrict__ ulist, int ustride, double2 *__restrict__ ylist) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ int s_next;
+  const SnapTab &t = *tab;
+  double2 *sU = reinterpret_cast<double2 *>(dyn);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const bool valid = i < n_local;
+  if (threadIdx.x == 0) s_next = 0;
+  // expand the half range to the full (ma,mb) range with the inversion symmetry
+  for (int j = 0; j <= t.twojmax; j++) {
+    const int nhalf = (j / 2 + 1) * (j + 1);
+    for (int k = warp; k < nhalf; k += nwarps) {
+      const int mb = k / (j + 1), ma = k - mb * (j + 1);
+      const double2 v = valid ? ulist[(size_t)(t.uh_block[j] + k) * ustride + i] : make_double2(0.0, 0.0);
+      sU[(size_t)(t.uf_block[j] + ma * (j + 1) + mb) * 32 + lane] = v;
+      if (2 * mb != j) {
+        const double sg = ((ma + mb) & 1) ? -1.0 : 1.0;
+        sU[(size_t)(t.uf_block[j] + (j - ma) * (j + 1) + (j - mb)) * 32 + lane] = make_double2(sg * v.x, -sg * v.y);
+      }
+    }
+  }
+  __syncthreads();
+  const int elem_i = valid ? t.elem_of_type[type[i]] : 0;
+  const double *beta_i = betaj + (size_t)elem_i * t.ntriples;
+  const double2 *U = sU + lane;
+
+  for (;;) {
+    int s = 0;
+    if (lane == 0) s = atomicAdd(&s_next, 1);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (s >= t.nstrips) break;
+    const int J = t.strip_j[s], ma = t.strip_ma[s];
+    double yr[kMaxCol], yi[kMaxCol];
+#pragma unroll
+    for (int mb = 0; mb < kMaxCol; mb++) { yr[mb] = 0.0; yi[mb] = 0.0; }
+    for (int tr = t.tri_begin[J]; tr < t.tri_begin[J + 1]; tr++) {
+      const int j1 = t.triple[tr].j1, j2 = t.triple[tr].j2;
+      const double *cgb = cg + t.triple[tr].cgoff; // cgarray(j1,j2,J,m1,m2) at m1*(j2+1)+m2
+      const double bj = beta_i[tr];
+      const int u1b = t.uf_block[j1], u2b = t.uf_block[j2];
+      const int ma1lo = max(0, (2 * ma - J - j2 + j1) / 2), ma1hi = min(j1, (2 * ma - J + j2 + j1) / 2);
+#pragma unroll
+      for (int mb = 0; mb < kMaxCol; mb++) {
+        if (2 * mb <= J && !(2 * mb == J && ma > mb)) { // compute_zi :228-270 for one (ma, mb)
+          const int mb1lo = max(0, (2 * mb - J - j2 + j1) / 2), mb1hi = min(j1, (2 * mb - J + j2 + j1) / 2);
+          double zr = 0.0, zi = 0.0;
+          for (int ma1 = ma1lo; ma1 <= ma1hi; ma1++) {
+            const int ma2 = (2 * ma - J - (2 * ma1 - j1) + j2) / 2;
+            const int mb2lo = (2 * mb - J - (2 * mb1lo - j1) + j2) / 2;
+            const double2 *p1 = U + (size_t)(u1b + ma1 * (j1 + 1) + mb1lo) * 32;
+            const double2 *p2 = U + (size_t)(u2b + ma2 * (j2 + 1) + mb2lo) * 32;
+            const double *pc = cgb + mb1lo * (j2 + 1) + mb2lo;
+            double sr = 0.0, si = 0.0;
+            for (int mb1 = mb1lo; mb1 <= mb1hi; mb1++) {
+              const double2 a = *p1, b = *p2;
+              const double c = __ldg(pc);
+              sr += c * (a.x * b.x - a.y * b.y);
+              si += c * (a.x * b.y + a.y * b.x);
+              p1 += 32; p2 -= 32; pc += j2;
+            }
+            const double ca = __ldg(cgb + ma1 * (j2 + 1) + ma2);
+            zr += sr * ca;
+            zi += si * ca;
+          }
+          yr[mb] += bj * zr;
+          yi[mb] += bj * zi;
+        }
+      }
+    }
+    if (valid) {
+      double2 *Y = ylist + (size_t)i * t.nuh + t.uh_block[J] + ma;
+#pragma unroll
+      for (int mb = 0; mb < kMaxCol; mb++)
+        if (2 * mb <= J) {
+          // half-column weights of compute_dbidrj (:393-424): 1, and on the middle column of even J: 1 above the
+          // diagonal, 1/2 on it, 0 below
+          const double w = (2 * mb < J) ? 1.0 : (ma < mb ? 1.0 : (ma == mb ? 0.5 : 0.0));
+          Y[mb * (J + 1)] = make_double2(w * yr[mb], w * yi[mb]);
+        }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- snap_deidrj
+constexpr int kDeThreads = 128;
+
+// one level of the dU recursion for column mb, in place, all three directions (compute_duarray :786-838)
+__device__ __forceinline__ void du_level(double2 (&u)[kMaxJ + 1], double2 (&du)[3][kMaxJ + 1], int j, int mb, const double *__restrict__ s_rootpq,
+                                         double a_r, double a_i, double b_r, double b_i, const double (&da_r)[3], const double (&da_i)[3],
+                                         const double (&db_r)[3], const double (&db_i)[3]) {
+#pragma unroll
+  for (int ma = kMaxJ; ma >= 0; --ma) {
+    if (ma <= j) {
+      double c1 = 0.0, c2 = 0.0;
+      double2 uo = make_double2(0.0, 0.0), um = make_double2(0.0, 0.0);
+      if (ma < j) { c1 = s_rootpq[(j - ma) * kRootDim + (j - mb)]; uo = u[ma]; }
+      if (ma > 0) { c2 = s_rootpq[ma * kRootDim + (j - mb)]; um = u[ma - 1]; }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        double2 dq = make_double2(0.0, 0.0), dm = make_double2(0.0, 0.0);
+        if (ma < j) dq = du[k][ma];
+        if (ma > 0) dm = du[k][ma - 1];
+        const double t1r = da_r[k] * uo.x + da_i[k] * uo.y + a_r * dq.x + a_i * dq.y;
+        const double t1i = da_r[k] * uo.y - da_i[k] * uo.x + a_r * dq.y - a_i * dq.x;
+        const double t2r = db_r[k] * um.x + db_i[k] * um.y + b_r * dm.x + b_i * dm.y;
+        const double t2i = db_r[k] * um.y - db_i[k] * um.x + b_r * dm.y - b_i * dm.x;
+        du[k][ma] = make_double2(c1 * t1r - c2 * t2r, c1 * t1i - c2 * t2i);
+      }
+      const double t1r = a_r * uo.x + a_i * uo.y, t1i = a_r * uo.y - a_i * uo.x;
+      const double t2r = b_r * um.x + b_i * um.y, t2i = b_r * um.y - b_i * um.x;
+      u[ma] = make_double2(c1 * t1r - c2 * t2r, c1 * t1i - c2 * t2i);
+    }
+  }
+}
+
+// lanes = in-cutoff pairs.  Dynamic shared memory: boot [kMaxJ][4][blockDim] double2.
+__global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ x,
+                                                                 const int *__restrict__ type, const int *__restrict__ pair_i,
+                                                                 const int *__restrict__ pair_j, int npairs,
+                                                                 const double2 *__restrict__ ylist, double *__restrict__ f) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ double s_rootpq[kRootDim * kRootDim];
+  const SnapTab &t = *tab;
+  for (int k = threadIdx.x; k < kRootDim * kRootDim; k += blockDim.x) s_rootpq[k] = t.rootpq[k];
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  double2 *boot = reinterpret_cast<double2 *>(dyn) + threadIdx.x;
+  const int bs = blockDim.x;
+  const int twojmax = t.twojmax, ncol = t.ncol;
+  const int i = pair_i[p], j = pair_j[p];
+  const double dx = x[3 * (size_t)j] - x[3 * (size_t)i], dy = x[3 * (size_t)j + 1] - x[3 * (size_t)i + 1],
+               dz = x[3 * (size_t)j + 2] - x[3 * (size_t)i + 2];
+  const int elem_i = t.elem_of_type[type[i]], elem_j = t.elem_of_type[type[j]];
+  const double rcut = (t.radelem[elem_i] + t.radelem[elem_j]) * t.rcutfac;
+  const double wj = t.wjelem[elem_j];
+  // compute_duidrj :290-321, compute_duarray :740-771
+  const double rsq = dx * dx + dy * dy + dz * dz;
+  const double r = sqrt(rsq);
+  const double rscale0 = t.rfac0 * kPi / (rcut - t.rmin0);
+  const double theta0 = (r - t.rmin0) * rscale0;
+  double sn, cs;
+  sincos(theta0, &sn, &cs);
+  const double z0 = r * cs / sn;
+  const double dz0dr = z0 / r - (r * rscale0) * (rsq + z0 * z0) / rsq;
+  const double rinv = 1.0 / r;
+  const double uhat[3] = {dx * rinv, dy * rinv, dz * rinv};
+  const double r0inv = 1.0 / sqrt(r * r + z0 * z0);
+  const double a_r = z0 * r0inv, a_i = -dz * r0inv, b_r = dy * r0inv, b_i = -dx * r0inv;
+  const double dr0invdr = -(r0inv * r0inv * r0inv) * (r + z0 * dz0dr);
+  double da_r[3], da_i[3], db_r[3], db_i[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double dr0inv = dr0invdr * uhat[k], dz0 = dz0dr * uhat[k];
+    da_r[k] = dz0 * r0inv + z0 * dr0inv;
+    da_i[k] = -dz * dr0inv;
+    db_r[k] = dy * dr0inv;
+    db_i[k] = -dx * dr0inv;
+  }
+  da_i[2] += -r0inv;
+  db_i[0] += -r0inv;
+  db_r[1] += r0inv;
+  const double sfac = sfac_of(t, r, rcut) * wj, dsfac = dsfac_of(t, r, rcut) * wj;
+
+  const double2 *Y = ylist + (size_t)i * t.nuh;
+  double S0 = 0.0, S[3] = {0.0, 0.0, 0.0};
+  double2 u[kMaxJ + 1], du[3][kMaxJ + 1];
+  u[0] = make_double2(1.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < 3; k++) du[k][0] = make_double2(0.0, 0.0);
+  S0 += Y[t.uh_block[0]].x; // level 0: u = 1, du = 0
+
+  for (int c = 0; c < ncol; c++) {
+    if (c > 0) {
+#pragma unroll
+      for (int ma = 0; ma <= kMaxJ; ma++)
+        if (ma <= 2 * c - 1) {
+          u[ma] = boot[(ma * 4 + 0) * bs];
+#pragma unroll
+          for (int k = 0; k < 3; k++) du[k][ma] = boot[(ma * 4 + 1 + k) * bs];
+        }
+    }
+    for (int jl = max(1, 2 * c); jl <= twojmax; jl++) {
+      du_level(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i, da_r, da_i, db_r, db_i);
+      const double2 *Yl = Y + t.uh_block[jl] + c * (jl + 1);
+#pragma unroll
+      for (int ma = 0; ma <= kMaxJ; ma++)
+        if (ma <= jl) {
+          const double2 y = Yl[ma];
+          S0 += u[ma].x * y.x + u[ma].y * y.y;
+#pragma unroll
+          for (int k = 0; k < 3; k++) S[k] += du[k][ma].x * y.x + du[k][ma].y * y.y;
+        }
+      if (jl == 2 * c + 1 && c + 1 < ncol) { // image that starts column c+1 (:840-864)
+#pragma unroll
+        for (int s = 0; s <= kMaxJ; s++)
+          if (s <= jl) {
+            const double sg = ((s + c) & 1) ? -1.0 : 1.0;
+            boot[((jl - s) * 4 + 0) * bs] = make_double2(sg * u[s].x, -sg * u[s].y);
+#pragma unroll
+            for (int k = 0; k < 3; k++) boot[((jl - s) * 4 + 1 + k) * bs] = make_double2(sg * du[k][s].x, -sg * du[k][s].y);
+          }
+      }
+    }
+  }
+  // dU_full = dsfac u uhat + sfac dU (:873-892); F_ij = 2 sum w Re(conj(dU_full) Y) + rij * (-1.5e6 / r^14) (force_snap_neigh_impl.h:698-711)
+  const double rsq7 = (rsq * rsq * rsq) * (rsq * rsq * rsq) * rsq;
+  const double fdivr = -1.5e6 / rsq7;
+  const double rij[3] = {dx, dy, dz};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double fk = 2.0 * (dsfac * uhat[k] * S0 + sfac * S[k]) + rij[k] * fdivr;
+    atomicAdd(&f[3 * (size_t)i + k], fk);
+    atomicAdd(&f[3 * (size_t)j + k], -fk);
+  }
+}
+
+size_t ui_smem(const SnapTab &h) { return ((size_t)h.nuh * 32 + (size_t)kMaxJ * 32 * h.ncol) * sizeof(double2); }
+size_t yi_smem(const SnapTab &h) { return (size_t)h.nuf * 32 * sizeof(double2); }
+size_t de_smem() { return (size_t)kMaxJ * 4 * kDeThreads * sizeof(double2); }
+
+} // namespace
+
+extern "C" {
+
+int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
+  if (!out || !p) { set_error("emd_snap_create: NULL argument"); return 1; }
+  if (p->twojmax < 0 || p->twojmax > kMaxJ) { set_error("emd_snap_create: twojmax %d not in [0,%d]", p->twojmax, kMaxJ); return 1; }
+  if (p->ntypes < 1 || p->ntypes > kMaxTypesConst || p->nelements < 1 || p->nelements > kMaxTypesConst) {
+    set_error("emd_snap_create: ntypes/nelements out of range"); return 1;
+  }
+  emd_snap *s = new emd_snap();
+  SnapTab &h = s->h;
+  memset(&h, 0, sizeof h);
+  const int J2 = p->twojmax;
+  h.twojmax = J2; h.ncol = J2 / 2 + 1; h.ntypes = p->ntypes; h.nelements = p->nelements; h.switchflag = p->switchflag;
+  h.rcutfac = p->rcutfac; h.rfac0 = p->rfac0; h.rmin0 = p->rmin0; h.wself = p->wself;
+  int nuh = 0, nuf = 0;
+  for (int j = 0; j <= J2; j++) { h.uh_block[j] = nuh; nuh += (j / 2 + 1) * (j + 1); h.uf_block[j] = nuf; nuf += (j + 1) * (j + 1); }
+  h.nuh = nuh; h.nuf = nuf;
+  for (int pp = 1; pp <= J2; pp++) // init_rootpqarray, sna_impl.hpp:1053-1061
+    for (int q = 1; q <= J2; q++) h.rootpq[pp * kRootDim + q] = sqrt(static_cast<double>(pp) / q);
+  double rcutmax = 0.0; // force_snap_neigh_impl.h:321-329
+  for (int e = 0; e < p->nelements; e++) {
+    h.radelem[e] = p->radelem[e]; h.wjelem[e] = p->wjelem[e];
+    rcutmax = std::max(2.0 * p->radelem[e] * p->rcutfac, rcutmax);
+  }
+  h.cutsq = rcutmax * rcutmax;
+  for (int ty = 0; ty < p->ntypes; ty++) h.elem_of_type[ty] = p->elem_of_type[ty];
+
+  // index lists (build_indexlist, sna_impl.hpp:86-132, diagonalstyle 3): idxj = the ncoeff bispectrum components,
+  // idxj_full = every (j1 >= j2, j) block of Z
+  struct T3 { int j1, j2, j; };
+  std::vector<T3> idxj, full;
+  for (int j1 = 0; j1 <= J2; j1++)
+    for (int j2 = 0; j2 <= j1; j2++)
+      for (int j = abs(j1 - j2); j <= imin(J2, j1 + j2); j += 2) {
+        if (j >= j1) idxj.push_back({j1, j2, j});
+        full.push_back({j1, j2, j});
+      }
+  s->ncoeff = (int)idxj.size();
+  if (s->ncoeff != p->ncoeffall - 1) { // :315-318
+    set_error("emd_snap_create: coefficient count %d does not match twojmax %d (expected %d + 1)", p->ncoeffall, J2, s->ncoeff);
+    delete s; return 1;
+  }
+  std::stable_sort(full.begin(), full.end(), [](const T3 &a, const T3 &b) { return a.j < b.j; });
+  h.ntriples = (int)full.size();
+  std::vector<double> cg;
+  for (int tI = 0; tI < h.ntriples; tI++) {
+    const T3 &q = full[tI];
+    h.triple[tI].j1 = (short)q.j1; h.triple[tI].j2 = (short)q.j2; h.triple[tI].j = (short)q.j; h.triple[tI].cgoff = (int)cg.size();
+    for (int m1 = 0; m1 <= q.j1; m1++)
+      for (int m2 = 0; m2 <= q.j2; m2++) cg.push_back(clebsch_gordan(q.j1, q.j2, q.j, m1, m2));
+  }
+  h.ncg = (int)cg.size();
+  for (int j = 0, tI = 0; j <= J2 + 1; j++) {
+    while (tI < h.ntriples && full[tI].j < j) tI++;
+    h.tri_begin[j] = tI;
+  }
+  auto tri_index = [&](int a, int b, int c) {
+    for (int tI = 0; tI < h.ntriples; tI++)
+      if (full[tI].j1 == a && full[tI].j2 == b && full[tI].j == c) return tI;
+    return -1;
+  };
+  // betaj: the coefficient of every Z block in Y (fold of compute_dbidrj's three sums, :393-527, with beta)
+  std::vector<double> betaj((size_t)p->nelements * h.ntriples, 0.0);
+  for (int e = 0; e < p->nelements; e++) {
+    const double *coeff = p->coeffelem + (size_t)e * p->ncoeffall;
+    double *bj = betaj.data() + (size_t)e * h.ntriples;
+    for (int JJ = 0; JJ < s->ncoeff; JJ++) {
+      const int j1 = idxj[JJ].j1, j2 = idxj[JJ].j2, j = idxj[JJ].j;
+      const double b = coeff[JJ + 1];
+      const int t1 = tri_index(imax(j1, j2), imin(j1, j2), j);
+      const int t2 = tri_index(imax(j, j2), imin(j, j2), j1);
+      const int t3 = tri_index(imax(j1, j), imin(j1, j), j2);
+      if (t1 < 0 || t2 < 0 || t3 < 0) { set_error("emd_snap_create: internal index error"); delete s; return 1; }
+      bj[t1] += b;
+      bj[t2] += b * ((j + 1) / (j1 + 1.0));
+      bj[t3] += b * ((j + 1) / (j2 + 1.0));
+    }
+  }
+  // output strips (j, ma) sorted by their Clebsch-Gordan term count, most expensive first
+  struct Strip { int j, ma; long cost; };
+  std::vector<Strip> strips;
+  for (int j = 0; j <= J2; j++)
+    for (int ma = 0; ma <= j; ma++) {
+      long cost = 0;
+      for (int tI = h.tri_begin[j]; tI < h.tri_begin[j + 1]; tI++) {
+        const int j1 = full[tI].j1, j2 = full[tI].j2;
+        const long na = imin(j1, (2 * ma - j + j2 + j1) / 2) - imax(0, (2 * ma - j - j2 + j1) / 2) + 1;
+        for (int mb = 0; 2 * mb <= j; mb++) {
+          const long nb = imin(j1, (2 * mb - j + j2 + j1) / 2) - imax(0, (2 * mb - j - j2 + j1) / 2) + 1;
+          cost += na * nb + na;
+        }
+      }
+      strips.push_back({j, ma, cost});
+    }
+  std::stable_sort(strips.begin(), strips.end(), [](const Strip &a, const Strip &b) { return a.cost > b.cost; });
+  h.nstrips = (int)strips.size();
+  for (int k = 0; k < h.nstrips; k++) { h.strip_j[k] = (short)strips[k].j; h.strip_ma[k] = (short)strips[k].ma; }
+
+  EMD_CUDA(cudaMalloc((void **)&s->d_tab, sizeof(SnapTab)));
+  EMD_CUDA(cudaMemcpy(s->d_tab, &h, sizeof(SnapTab), cudaMemcpyHostToDevice));
+  EMD_CUDA(cudaMalloc((void **)&s->d_cg, sizeof(double) * cg.size()));
+  EMD_CUDA(cudaMemcpy(s->d_cg, cg.data(), sizeof(double) * cg.size(), cudaMemcpyHostToDevice));
+  EMD_CUDA(cudaMalloc((void **)&s->d_betaj, sizeof(double) * betaj.size()));
+  EMD_CUDA(cudaMemcpy(s->d_betaj, betaj.data(), sizeof(double) * betaj.size(), cudaMemcpyHostToDevice));
+  int dev = 0;
+  EMD_CUDA(cudaGetDevice(&dev));
+  EMD_CUDA(cudaDeviceGetAttribute(&s->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (yi_smem(h) > (size_t)s->max_smem_optin) { set_error("emd_snap_create: U_tot batch does not fit in shared memory"); delete s; return 1; }
+  EMD_CUDA(cudaFuncSetAttribute(snap_ui_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ui_smem(h)));
+  EMD_CUDA(cudaFuncSetAttribute(snap_yi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yi_smem(h)));
+  EMD_CUDA(cudaFuncSetAttribute(snap_deidrj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)de_smem()));
+  *out = s;
+  return 0;
+}
+
+void emd_snap_destroy(emd_snap *s) {
+  if (!s) return;
+  if (s->d_tab) cudaFree(s->d_tab);
+  if (s->d_cg) cudaFree(s->d_cg);
+  if (s->d_betaj) cudaFree(s->d_betaj);
+  s->ulist.release(); s->ylist.release(); s->cnt.release(); s->pair_i.release(); s->pair_j.release(); s->queue.release();
+  delete s;
+}
+
+int emd_snap_info(const emd_snap *s, int *ncoeff, int *nuh, int *ntriples, double *rcutmax, int *npairs, int *ustride) {
+  if (!s) return 1;
+  if (ncoeff) *ncoeff = s->ncoeff;
+  if (nuh) *nuh = s->h.nuh;
+  if (ntriples) *ntriples = s->h.ntriples;
+  if (rcutmax) *rcutmax = sqrt(s->h.cutsq);
+  if (npairs) *npairs = s->npairs;
+  if (ustride) *ustride = s->ucap;
+  return 0;
+}
+
+void *emd_snap_device_ptr(emd_snap *s, const char *what) {
+  if (!s || !what) return nullptr;
+  if (!strcmp(what, "ulist")) return s->ulist.p;
+  if (!strcmp(what, "ylist")) return s->ylist.p;
+  if (!strcmp(what, "pair_i")) return s->pair_i.p;
+  if (!strcmp(what, "pair_j")) return s->pair_j.p;
+  if (!strcmp(what, "pair_offsets")) return s->cnt.p;
+  return nullptr;
+}
+
+int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const int *d_type, double *d_f, int n_local, int n_all,
+                           const emd_neigh_list *list) {
+  if (!ctx || !s || !list) { set_error("emd_force_snap_compute: NULL argument"); return 1; }
+  (void)n_all;
+  if (n_local <= 0) return 0;
+  const SnapTab &h = s->h;
+  // in-cutoff pairs: count -> exclusive scan -> fill
+  if (s->cnt.ensure(sizeof(int) * ((size_t)n_local + 1))) return 1;
+  int *cnt = s->cnt.as<int>();
+  EMD_CUDA(cudaMemsetAsync(cnt + n_local, 0, sizeof(int), ctx->stream));
+  EMD_LAUNCH(ctx, (snap_pairs_kernel<false>), grid_for(n_local, 128), 128, 0, d_x, n_local, *list, h.cutsq, cnt, nullptr, nullptr);
+  if (exclusive_scan_int(ctx, cnt, cnt, n_local + 1, nullptr)) return 1;
+  EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, cnt + n_local, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  EMD_CUDA(cudaStreamSynchronize(ctx->stream)); // like the reference's max_neighs read-back (:181)
+  const int npairs = ctx->h_pinned[0];
+  if (npairs < 0) { set_error("emd_force_snap_compute: pair count overflows 32 bits"); return 2; }
+  s->npairs = npairs;
+  if (s->pair_i.ensure(sizeof(int) * ((size_t)npairs + 1)) || s->pair_j.ensure(sizeof(int) * ((size_t)npairs + 1))) return 1;
+  if (n_local > s->ucap) {
+    const int want = (n_local + n_local / 8 + 31) / 32 * 32;
+    if (s->ulist.ensure(sizeof(double2) * (size_t)h.nuh * want) || s->ylist.ensure(sizeof(double2) * (size_t)h.nuh * want)) { s->ucap = 0; return 1; }
+    s->ucap = want;
+  }
+  int *pair_i = s->pair_i.as<int>(), *pair_j = s->pair_j.as<int>();
+  EMD_LAUNCH(ctx, (snap_pairs_kernel<true>), grid_for(n_local, 128), 128, 0, d_x, n_local, *list, h.cutsq, cnt, pair_i, pair_j);
+  double2 *ulist = s->ulist.as<double2>(), *ylist = s->ylist.as<double2>();
+  const int nbatch = grid_for(n_local, 32);
+  EMD_LAUNCH(ctx, snap_ui_kernel, nbatch, 32 * h.ncol, ui_smem(h), s->d_tab, d_x, d_type, n_local, cnt, pair_j, ulist, s->ucap);
+  EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h), s->d_tab, s->d_cg, s->d_betaj, d_type, n_local, ulist, s->ucap, ylist);
+  if (npairs > 0)
+    EMD_LAUNCH(ctx, snap_deidrj_kernel, grid_for(npairs, kDeThreads), kDeThreads, de_smem(), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
+               ylist, d_f);
+  return 0;
+}
+
+} // extern "C"

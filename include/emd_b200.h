@@ -164,6 +164,39 @@ int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half_neigh, int comm
 int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type,
                                double *d_f, double *h_pe);
 
+/* ---- SNAP force: ForceSNAP<> + SNA, src/force_types/force_snap_neigh_impl.h, sna_impl.hpp ------- */
+/* What init_coeff/read_files (force_snap_neigh_impl.h:227-336, 340-587) leave behind, as plain values.
+ * elem_of_type[t] = map[t] exactly as the reference's kernel reads it (:597: indexed by the 0-based atom
+ * type); radelem/wjelem/coeffelem are HOST arrays, copied.  Only diagonalstyle 3 (the only style for
+ * which the reference builds its index lists, sna_impl.hpp:86-132) and linear SNAP (quadraticflag 0). */
+typedef struct {
+  int twojmax, switchflag, ntypes, nelements, ncoeffall;
+  double rcutfac, rfac0, rmin0, wself;
+  int elem_of_type[12];
+  const double *radelem;   /* [nelements] */
+  const double *wjelem;    /* [nelements] */
+  const double *coeffelem; /* [nelements][ncoeffall], coeffelem[e][0] = the constant term (unused by forces) */
+} emd_snap_params;
+typedef struct emd_snap emd_snap;
+/* SNA::SNA + SNA::init (sna_impl.hpp:25-53,136-140): index lists, Clebsch-Gordan and sqrt(p/q) tables,
+ * plus the beta-folded block coefficients of the adjoint formulation; uploads them to the device */
+int emd_snap_create(emd_snap **out, const emd_snap_params *p);
+void emd_snap_destroy(emd_snap *s);
+/* ncoeff (sna.ncoeff), U/Y elements per atom on the half range, Z blocks, rcutmax (:321-327), and of the
+ * last compute: in-cutoff pairs and the atom stride of the U array.  Any pointer may be NULL. */
+int emd_snap_info(const emd_snap *s, int *ncoeff, int *nuh, int *ntriples, double *rcutmax, int *npairs, int *ustride);
+/* device arrays of the last compute, for function-level parity tests: "ulist" double[nuh][ustride][2]
+ * (U_tot on mb <= j/2, element (j,mb,ma) at block(j) + mb*(j+1) + ma), "ylist" double[n_local][nuh][2]
+ * (weighted adjoint Y), "pair_i"/"pair_j" int[npairs], "pair_offsets" int[n_local+1] */
+void *emd_snap_device_ptr(emd_snap *s, const char *what);
+/* ForceSNAP::compute (force_snap_neigh_impl.h:159-208 + team kernel :589-725) over a FULL neighbor list
+ * with newton on: f_i += F_ij and f_j -= F_ij for every listed j with rsq < rcutmax^2, ghosts included
+ * (the caller folds ghost forces back with update_force, examinimd.cpp:241-245).  Accumulates onto d_f,
+ * which the caller has zeroed (examinimd.cpp:232).  Synchronises once (pair count read-back), like the
+ * reference's max_neighs reduction (:181). */
+int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const int *d_type, double *d_f,
+                           int n_local, int n_all, const emd_neigh_list *list);
+
 /* ---- integrator: IntegratorNVE, src/integrator_nve.cpp:41-121 --------------------------- */
 /* dtf = 0.5*dt/mvv2e, dtv = dt (:41-44).  Bit-exact with the reference's CPU arithmetic
  * (separate multiply and add, no FMA contraction). */

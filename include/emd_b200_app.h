@@ -33,7 +33,8 @@ int emd_app_download(emd_app *app, int *h_id, int *h_type, double *h_q, double *
 /* HOST x,v,f of the owned atoms to the device (any pointer may be NULL) */
 int emd_app_upload(emd_app *app, const double *h_x, const double *h_v, const double *h_f);
 /* device pointers of the live arrays: "x","v","f","type","id","q","bincount","binoffsets",
- * "permute","row_map","num_neighs","neighs" (valid until the next rebuild/grow); "tiles" = the
+ * "permute","row_map","num_neighs","neighs" (valid until the next rebuild/grow); "snap" = the emd_snap* of a
+ * ForceSNAP (NULL for other forces); "tiles" = the
  * emd_tiles* of the last neighbor build, or NULL when the fast path is not in use */
 void *emd_app_device_ptr(emd_app *app, const char *what);
 int emd_app_neigh_stride(emd_app *app);

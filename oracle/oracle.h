@@ -168,6 +168,11 @@ void orc_snap_atom(orc_force_snap *f, int ninside, const double *rij, const doub
                    const double *rcutij, double *utot_r, double *utot_i, double *dbvec /* [n][ncoeff][3] */,
                    double *fij /* [n][3] */);
 
+/* the same on the live system: atom i with its neighbor row; returns the number of in-cutoff neighbors */
+int orc_force_snap_probe(orc_force_snap *f, const orc_system *s, const orc_neighbor *n, int i, double *utot_r, double *utot_i,
+                         int *inside, double *fij);
+int orc_force_snap_jdim(const orc_force_snap *f);
+
 /* whole application: src/examinimd.cpp:60-294 (single rank, CommSerial) */
 typedef struct {
   orc_input in;

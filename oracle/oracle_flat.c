@@ -194,3 +194,11 @@ int orcf_set(void *h, const char *w, const void *in, int n) {
 }
 
 int orcf_dump(void *h, const char *path, int step) { return orc_dump_binary(&((orc_md *)h)->sys, path, step, 0); }
+
+/* SNAP function-level probe (see orc_force_snap_probe); returns ninside, -1 without a SNAP force */
+int orcf_snap_probe(void *h, int i, double *utot_r, double *utot_i, int *inside, double *fij) {
+  orc_md *md = (orc_md *)h;
+  if (!md->snap) return -1;
+  return orc_force_snap_probe(md->snap, &md->sys, &md->neigh, i, utot_r, utot_i, inside, fij);
+}
+int orcf_snap_jdim(void *h) { orc_md *md = (orc_md *)h; return md->snap ? orc_force_snap_jdim(md->snap) : -1; }

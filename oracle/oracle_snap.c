@@ -648,3 +648,42 @@ void orc_snap_atom(orc_force_snap *f, int ninside, const double *rij, const doub
     if (fij) memcpy(fij + 3 * jj, fj, sizeof(double) * 3);
   }
 }
+
+/* function-level probe on the live system: atom i of s with its row of n -> U_tot (r,i: [jdim]^3, index
+ * (j*jdim+ma)*jdim+mb), the in-cutoff neighbor indices and F_ij of each (inside[k], fij[3k..]); returns ninside */
+int orc_force_snap_probe(orc_force_snap *f, const orc_system *s, const orc_neighbor *n, int i, double *utot_r, double *utot_i,
+                         int *inside, double *fij) {
+  const double cutsq = f->rcutmax * f->rcutmax;
+  const double x_i = s->x[3 * i], y_i = s->x[3 * i + 1], z_i = s->x[3 * i + 2];
+  const int elem_i = f->map[s->type[i]];
+  const double radi = f->radelem[elem_i];
+  int num_neighs;
+  const int *row = orc_neigh_row(n, i, &num_neighs);
+  grow_nmax(f, num_neighs);
+  int ninside = 0;
+  for (int jj = 0; jj < num_neighs; jj++) {
+    const int j = row[jj];
+    const double dx = s->x[3 * j] - x_i, dy = s->x[3 * j + 1] - y_i, dz = s->x[3 * j + 2] - z_i;
+    const double rsq = dx * dx + dy * dy + dz * dz;
+    const int elem_j = f->map[s->type[j]];
+    if (rsq < cutsq) {
+      f->rij[3 * ninside] = dx; f->rij[3 * ninside + 1] = dy; f->rij[3 * ninside + 2] = dz;
+      f->inside[ninside] = j;
+      f->wj[ninside] = f->wjelem[elem_j];
+      f->rcutij[ninside] = (radi + f->radelem[elem_j]) * f->rcutfac;
+      ninside++;
+    }
+  }
+  compute_ui(f, ninside);
+  const size_t j3 = (size_t)f->jdim * f->jdim * f->jdim;
+  if (utot_r) memcpy(utot_r, f->utot_r, sizeof(double) * j3);
+  if (utot_i) memcpy(utot_i, f->utot_i, sizeof(double) * j3);
+  if (inside) memcpy(inside, f->inside, sizeof(int) * (size_t)ninside);
+  if (fij) {
+    compute_zi(f);
+    const double *coeffi = f->coeffelem + (size_t)elem_i * f->ncoeffall;
+    for (int jj = 0; jj < ninside; jj++) neighbor_force(f, jj, coeffi, fij + 3 * jj);
+  }
+  return ninside;
+}
+int orc_force_snap_jdim(const orc_force_snap *f) { return f->jdim; }

@@ -48,6 +48,12 @@ def make_deck(path, region, nsteps, newton, deck=DECK):
     path.write_text(txt)
 
 
+def lattice_constant(deck):
+    """cell edge of the deck's `lattice` command (src/input.cpp:312-330: sc a | fcc rho* -> (4/rho)^(1/3))"""
+    m = re.search(r"^lattice\s+(\w+)\s+([\d.eE+-]+)", Path(deck).read_text(), re.M)
+    return float(m.group(2)) if m.group(1) == "sc" else (4.0 / float(m.group(2))) ** (1.0 / 3.0)
+
+
 def read_dump(p):
     raw = p.read_bytes()
     n = int(np.frombuffer(raw[:4], np.int32)[0])

@@ -44,6 +44,10 @@ def load() -> C.CDLL:
     L.orcf_copy.restype = C.c_longlong
     L.orcf_set.argtypes = [P, C.c_char_p, P, C.c_int]
     L.orcf_dump.argtypes = [P, C.c_char_p, C.c_int]
+    L.orcf_snap_probe.argtypes = [P, C.c_int, P, P, P, P]
+    L.orcf_snap_probe.restype = C.c_int
+    L.orcf_snap_jdim.argtypes = [P]
+    L.orcf_snap_jdim.restype = C.c_int
     _lib = L
     return L
 
@@ -139,6 +143,16 @@ class OracleMD:
         m = self.geti("maxneighs")
         t = self.arr("neighs2d").reshape(n, m)
         return [t[i, :nn[i]] for i in range(n)]
+
+    def snap_probe(self, i, with_forces=True):
+        """U_tot [jdim,jdim,jdim] complex (index j,ma,mb), in-cutoff neighbor indices and F_ij of atom i."""
+        jd = self.L.orcf_snap_jdim(self.h)
+        ur, ui = np.zeros(jd ** 3), np.zeros(jd ** 3)
+        inside, fij = np.zeros(512, np.int32), np.zeros((512, 3))
+        n = self.L.orcf_snap_probe(self.h, i, ur.ctypes.data, ui.ctypes.data, inside.ctypes.data, fij.ctypes.data if with_forces else None)
+        if n < 0:
+            raise RuntimeError("no SNAP force in this oracle")
+        return (ur + 1j * ui).reshape(jd, jd, jd), inside[:n].copy(), fij[:n].copy()
 
     def close(self):
         if self.h:
