@@ -92,7 +92,7 @@ def reference_arm(args):
     if rank != 0:
         return
     total = args.steps + args.warmup
-    r = run_reference_cpu((40, 40, 40), total)
+    r = run_reference_cpu(tuple(args.region) if args.region else (40, 40, 40), total)
     ms = 1e3 * r["loop_s"] / total
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

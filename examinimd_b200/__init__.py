@@ -51,6 +51,13 @@ class SnapParams(C.Structure):
                 ("elem_of_type", C.c_int * 12), ("radelem", C.c_void_p), ("wjelem", C.c_void_p), ("coeffelem", C.c_void_p)]
 
 
+class Decomp(C.Structure):
+    """emd_decomp (include/emd_b200.h)."""
+
+    _fields_ = [("nranks", C.c_int), ("rank", C.c_int), ("grid", C.c_int * 3), ("pos", C.c_int * 3), ("neighbor_send", C.c_int * 6),
+                ("neighbor_recv", C.c_int * 6), ("sub", C.c_double * 3), ("sub_lo", C.c_double * 3), ("sub_hi", C.c_double * 3)]
+
+
 _P = C.c_void_p
 _D3 = C.c_double * 3
 _SIGS = {
@@ -109,6 +116,24 @@ _SIGS = {
                                       C.c_double, C.POINTER(C.c_int)]),
     "emd_comm_halo_update_phase": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _D3]),
     "emd_comm_force_fold_phase": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
+    "emd_comm_decompose": (C.c_int, [C.c_int, C.c_int, _D3, C.POINTER(Decomp)]),
+    "emd_comm_wrap_dims": (C.c_int, [_P, _P, C.c_int, _D3, C.c_int * 3]),
+    "emd_comm_exchange_pack": (C.c_int, [_P, C.c_int, C.POINTER(Decomp), _D3, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.POINTER(C.c_int)]),
+    "emd_comm_halo_pack": (C.c_int, [_P, C.c_int, C.POINTER(Decomp), _D3, C.c_double, _P, _P, _P, _P, _P, C.c_int, _P, _P, C.c_int,
+                                     C.POINTER(C.c_int)]),
+    "emd_comm_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "emd_comm_exchange_compact": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "emd_comm_halo_update_pack": (C.c_int, [_P, C.c_int, C.POINTER(Decomp), _D3, _P, _P, C.c_int, _P]),
+    "emd_comm_halo_update_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "emd_comm_force_unpack": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "emd_net_unique_id": (C.c_int, [_P]),
+    "emd_net_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, _P]),
+    "emd_net_destroy": (None, [_P]),
+    "emd_net_sendrecv": (C.c_int, [_P, _P, C.c_ulonglong, C.c_int, _P, C.c_ulonglong, C.c_int]),
+    "emd_net_exchange_count": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "emd_net_allreduce": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    "emd_net_scan_int": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "emd_net_barrier": (C.c_int, [_P]),
     "emd_reduce_mv2": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(C.c_double)]),
     # session API (include/emd_b200_app.h)
     "emd_app_create": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(C.c_char_p), C.c_int, _P]),

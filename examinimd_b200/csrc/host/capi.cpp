@@ -67,6 +67,8 @@ long long emd_app_get(emd_app *a, const char *what) {
   if (!strcmp(what, "nbinx")) return a->md->binning->nbinx;
   if (!strcmp(what, "nbiny")) return a->md->binning->nbiny;
   if (!strcmp(what, "nbinz")) return a->md->binning->nbinz;
+  if (!strcmp(what, "rank")) return a->md->comm->process_rank();
+  if (!strcmp(what, "nranks")) return a->md->comm->num_processes();
   return -1;
 }
 

@@ -1,0 +1,221 @@
+// CommMPI host class: sequencing of the six phases, buffer growth and the count handshakes of
+// src/comm_types/comm_mpi.cpp:193-466.  All arithmetic on atoms is in kernels/comm_mpi.cu / comm.cu.
+#include "comm_mpi.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+static const size_t kParticleBytes = 72; // sizeof(Particle), src/system.h:43-55
+
+static int env_int(const char *a, const char *b, const char *c, int dflt) {
+  const char *names[3] = {a, b, c};
+  for (const char *n : names)
+    if (n)
+      if (const char *v = getenv(n)) return atoi(v);
+  return dflt;
+}
+
+CommMPI::CommMPI(System *s, T_X_FLOAT comm_depth_) : Comm(s, comm_depth_), net(nullptr) {
+  proc_rank = env_int("RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", 0);
+  proc_size = env_int("WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", 1);
+  if (proc_size < 1) proc_size = 1;
+  memset(&dec, 0, sizeof dec);
+  for (int p = 0; p < 6; p++) proc_num_send[p] = proc_num_recv[p] = num_ghost[p] = ghost_offsets[p] = 0;
+  if (proc_size > 1 && emd_net_create(&net, system->ctx, proc_size, proc_rank, nullptr)) fail("emd_net_create");
+  system->do_print = system->do_print && proc_rank == 0; // src/system.cpp:61-67: only rank 0 prints
+}
+
+CommMPI::~CommMPI() { if (net) emd_net_destroy(net); }
+
+void CommMPI::init() {}
+
+void CommMPI::fail(const char *what) {
+  fprintf(stderr, "CommMPI[rank %d]: %s: %s\n", proc_rank, what, emd_last_error());
+  exit(1);
+}
+
+void CommMPI::ensure_bytes(DeviceArray<char> &b, size_t bytes) {
+  if (bytes <= b.extent()) return;
+  if (!b.alloc(bytes + bytes / 8 + 1024)) fail("buffer allocation");
+}
+
+// src/comm_types/comm_mpi.cpp:52-147
+void CommMPI::create_domain_decomposition() {
+  const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
+  if (emd_comm_decompose(proc_size, proc_rank, L, &dec)) fail("decompose");
+  system->sub_domain_x = dec.sub[0]; system->sub_domain_y = dec.sub[1]; system->sub_domain_z = dec.sub[2];
+  system->sub_domain_lo_x = dec.sub_lo[0]; system->sub_domain_lo_y = dec.sub_lo[1]; system->sub_domain_lo_z = dec.sub_lo[2];
+  system->sub_domain_hi_x = dec.sub_hi[0]; system->sub_domain_hi_y = dec.sub_hi[1]; system->sub_domain_hi_z = dec.sub_hi[2];
+}
+
+// src/comm_types/comm_mpi.cpp:193-289
+void CommMPI::exchange() {
+  emd_ctx *ctx = system->ctx;
+  const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
+  T_INT N_local = system->N_local, N_ghost = 0;
+  const int wrap[3] = {dec.grid[0] == 1, dec.grid[1] == 1, dec.grid[2] == 1};
+  if (emd_comm_wrap_dims(ctx, system->x, N_local, L, wrap)) fail("wrap");
+  T_INT N_total_recv = 0, N_total_send = 0;
+  for (int phase = 0; phase < 6; phase++) {
+    T_INT send = 0, recv = 0;
+    if (decomposed(phase)) {
+      for (int attempt = 0; attempt < 2; attempt++) {
+        const int cap = (int)(pack_buffer.extent() / kParticleBytes);
+        int count = 0;
+        if (emd_comm_exchange_pack(ctx, phase, &dec, L, system->x, system->v, system->q, system->id, system->type, N_local + N_ghost,
+                                   pack_buffer.ptr, cap, &count))
+          fail("exchange_pack");
+        send = count;
+        if (count <= cap) break;
+        ensure_bytes(pack_buffer, (size_t)(count * 1.1 + 16) * kParticleBytes); // :230-238
+      }
+      if (emd_net_exchange_count(net, send, dec.neighbor_send[phase], dec.neighbor_recv[phase], &recv)) fail("count handshake");
+      ensure_bytes(unpack_buffer, (size_t)recv * kParticleBytes);
+      if (N_local + N_ghost + recv > system->N_max) system->grow(N_local + N_ghost + recv + recv / 4 + 16);
+      if (emd_net_sendrecv(net, pack_buffer.ptr, (size_t)send * kParticleBytes, dec.neighbor_send[phase], unpack_buffer.ptr,
+                           (size_t)recv * kParticleBytes, dec.neighbor_recv[phase]))
+        fail("sendrecv");
+      if (emd_comm_unpack(ctx, unpack_buffer.ptr, recv, N_local + N_ghost, system->x, system->v, system->q, system->id, system->type))
+        fail("unpack");
+    }
+    N_ghost += recv;
+    N_total_recv += recv;
+    N_total_send += send;
+  }
+  const T_INT N_local_start = N_local, N_exchange = N_ghost;
+  N_local = N_local + N_total_recv - N_total_send; // :259
+  if (emd_comm_exchange_compact(ctx, system->x, system->v, system->q, system->id, system->type, N_local, N_local_start + N_exchange))
+    fail("compact");
+  system->N_local = N_local;
+  system->N_ghost = 0;
+}
+
+// src/comm_types/comm_mpi.cpp:291-380
+void CommMPI::exchange_halo() {
+  emd_ctx *ctx = system->ctx;
+  const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
+  const T_INT N_local = system->N_local;
+  T_INT N_ghost = 0;
+  for (int phase = 0; phase < 6; phase++) {
+    // an odd phase does not re-scan the ghosts its even twin just received (:306,:346)
+    const T_INT nparticles = N_local + N_ghost - ((phase % 2 == 1) ? proc_num_recv[phase - 1] : 0);
+    int count = 0;
+    if (decomposed(phase)) {
+      for (int attempt = 0; attempt < 2; attempt++) {
+        const int cap = (int)std::min(pack_buffer.extent() / kParticleBytes, pack_indicies[phase].extent());
+        if (emd_comm_halo_pack(ctx, phase, &dec, L, comm_depth, system->x, system->v, system->q, system->id, system->type, nparticles,
+                               pack_indicies[phase].ptr, pack_buffer.ptr, cap, &count))
+          fail("halo_pack");
+        if (count <= cap) break;
+        ensure_bytes(pack_buffer, (size_t)(count * 1.1 + 16) * kParticleBytes); // :319-327
+        if ((size_t)count > pack_indicies[phase].extent() && !pack_indicies[phase].alloc((size_t)(count * 1.1) + 16)) fail("alloc pack_indicies");
+      }
+      proc_num_send[phase] = count;
+      int recv = 0;
+      if (emd_net_exchange_count(net, count, dec.neighbor_send[phase], dec.neighbor_recv[phase], &recv)) fail("count handshake");
+      proc_num_recv[phase] = recv;
+      ensure_bytes(unpack_buffer, (size_t)recv * kParticleBytes);
+      if (N_local + N_ghost + recv > system->N_max) system->grow(N_local + N_ghost + recv + recv / 4 + 16);
+      if (emd_net_sendrecv(net, pack_buffer.ptr, (size_t)count * kParticleBytes, dec.neighbor_send[phase], unpack_buffer.ptr,
+                           (size_t)recv * kParticleBytes, dec.neighbor_recv[phase]))
+        fail("sendrecv");
+      if (emd_comm_unpack(ctx, unpack_buffer.ptr, recv, N_local + N_ghost, system->x, system->v, system->q, system->id, system->type))
+        fail("unpack");
+      count = recv;
+    } else { // the in-process twin of the phase, same kernels as CommSerial (:344-371)
+      const double lo[3] = {system->sub_domain_lo_x, system->sub_domain_lo_y, system->sub_domain_lo_z};
+      const double hi[3] = {system->sub_domain_hi_x, system->sub_domain_hi_y, system->sub_domain_hi_z};
+      for (int attempt = 0; attempt < 2; attempt++) {
+        if (emd_comm_halo_phase(ctx, phase, system->x, system->v, system->q, system->id, system->type, nparticles, N_local + N_ghost,
+                                system->N_max, pack_indicies[phase].ptr, (int)pack_indicies[phase].extent(), L, lo, hi, comm_depth, &count))
+          fail("halo_phase");
+        bool redo = false;
+        if (N_local + N_ghost + count > system->N_max) { system->grow(N_local + N_ghost + count + count / 4); redo = true; }
+        if ((size_t)count > pack_indicies[phase].extent()) {
+          if (!pack_indicies[phase].alloc((size_t)(count * 1.1) + 1)) fail("alloc pack_indicies");
+          redo = true;
+        }
+        if (!redo) break;
+      }
+      proc_num_send[phase] = proc_num_recv[phase] = count;
+    }
+    num_ghost[phase] = count;
+    N_ghost += count;
+  }
+  system->N_ghost = N_ghost;
+  // the per-step refresh ships 24 B per atom in either direction: make sure both buffers hold the largest phase
+  size_t most = 0;
+  for (int p = 0; p < 6; p++) most = std::max(most, (size_t)std::max(proc_num_send[p], proc_num_recv[p]));
+  ensure_bytes(pack_buffer, most * kParticleBytes);
+  ensure_bytes(unpack_buffer, most * kParticleBytes);
+}
+
+// src/comm_types/comm_mpi.cpp:382-423: no host synchronisation anywhere in here
+void CommMPI::update_halo() {
+  emd_ctx *ctx = system->ctx;
+  const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
+  T_INT N_ghost = 0;
+  for (int phase = 0; phase < 6; phase++) {
+    const T_INT ghost_begin = system->N_local + N_ghost;
+    if (decomposed(phase)) {
+      if (emd_comm_halo_update_pack(ctx, phase, &dec, L, system->x, pack_indicies[phase].ptr, proc_num_send[phase], (double *)pack_buffer.ptr))
+        fail("halo_update_pack");
+      if (emd_net_sendrecv(net, pack_buffer.ptr, (size_t)proc_num_send[phase] * 24, dec.neighbor_send[phase], unpack_buffer.ptr,
+                           (size_t)proc_num_recv[phase] * 24, dec.neighbor_recv[phase]))
+        fail("sendrecv");
+      if (emd_comm_halo_update_unpack(ctx, system->x, ghost_begin, proc_num_recv[phase], (const double *)unpack_buffer.ptr))
+        fail("halo_update_unpack");
+    } else {
+      if (emd_comm_halo_update_phase(ctx, phase, system->x, system->v, system->q, system->id, system->type, pack_indicies[phase].ptr,
+                                     proc_num_send[phase], ghost_begin, L))
+        fail("halo_update_phase");
+    }
+    N_ghost += proc_num_recv[phase];
+  }
+}
+
+// src/comm_types/comm_mpi.cpp:425-466: reverse direction, phases 5..0; the ghost rows of f are contiguous and go out in place
+void CommMPI::update_force() {
+  emd_ctx *ctx = system->ctx;
+  ghost_offsets[0] = system->N_local;
+  for (int phase = 1; phase < 6; phase++) ghost_offsets[phase] = ghost_offsets[phase - 1] + proc_num_recv[phase - 1];
+  for (int phase = 5; phase >= 0; phase--) {
+    if (decomposed(phase)) {
+      if (emd_net_sendrecv(net, system->f + 3 * (size_t)ghost_offsets[phase], (size_t)proc_num_recv[phase] * 24, dec.neighbor_recv[phase],
+                           pack_buffer.ptr, (size_t)proc_num_send[phase] * 24, dec.neighbor_send[phase]))
+        fail("sendrecv");
+      if (emd_comm_force_unpack(ctx, system->f, pack_indicies[phase].ptr, proc_num_send[phase], (const double *)pack_buffer.ptr))
+        fail("force_unpack");
+    } else {
+      if (emd_comm_force_fold_phase(ctx, system->f, pack_indicies[phase].ptr, proc_num_send[phase], ghost_offsets[phase]))
+        fail("force_fold_phase");
+    }
+  }
+}
+
+// src/comm_types/comm_mpi.cpp:150-191.  NB the reference's reduce_min_* call MPI_MAX (:183,:189); they are unused by the
+// hot path and implemented here as what their names say would need a MIN transport op, so they keep the reference's behaviour.
+void CommMPI::reduce_float(T_FLOAT *v, T_INT N) { if (net && emd_net_allreduce(net, v, N, 1, 0)) fail("allreduce"); }
+void CommMPI::reduce_int(T_INT *v, T_INT N) { if (net && emd_net_allreduce(net, v, N, 0, 0)) fail("allreduce"); }
+void CommMPI::reduce_max_float(T_FLOAT *v, T_INT N) { if (net && emd_net_allreduce(net, v, N, 1, 1)) fail("allreduce"); }
+void CommMPI::reduce_max_int(T_INT *v, T_INT N) { if (net && emd_net_allreduce(net, v, N, 0, 1)) fail("allreduce"); }
+void CommMPI::reduce_min_float(T_FLOAT *v, T_INT N) { reduce_max_float(v, N); }
+void CommMPI::reduce_min_int(T_INT *v, T_INT N) { reduce_max_int(v, N); }
+void CommMPI::scan_int(T_INT *v, T_INT N) {
+  if (!net) return;
+  for (T_INT k = 0; k < N; k++)
+    if (emd_net_scan_int(net, &v[k])) fail("scan");
+}
+void CommMPI::weighted_reduce_float(T_FLOAT *, T_INT *, T_INT) {} // declared by the reference's Comm, defined nowhere, never called
+
+int CommMPI::process_rank() { return proc_rank; }
+int CommMPI::num_processes() { return proc_size; }
+
+void CommMPI::error(const char *errormsg) { // :472-476 (MPI_Abort): a non-zero exit makes the launcher tear the job down
+  if (proc_rank == 0) printf("%s\n", errormsg);
+  fflush(stdout);
+  exit(1);
+}
+
+const char *CommMPI::name() { return "CommMPI"; }

@@ -1,3 +1,3 @@
 // Include Module header files for comm
-#include "comm_types/comm_nccl.h"
+#include "comm_types/comm_mpi.h"
 #include "comm_types/comm_serial.h"

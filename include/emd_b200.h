@@ -228,6 +228,63 @@ int emd_comm_halo_update_phase(emd_ctx *ctx, int phase, double *d_x, double *d_v
 int emd_comm_force_fold_phase(emd_ctx *ctx, double *d_f, const int *d_pack_indicies, int count,
                               int ghost_begin);
 
+/* ---- multi-GPU comm: CommMPI, src/comm_types/comm_mpi.{h,cpp} ----------------------------------
+ * One process per GPU; the host class (csrc/host/comm_types/comm_mpi.cpp) sequences the six phases and
+ * owns the buffers, these entry points are the pack/unpack kernels and the transport (kernels/comm_mpi.cu). */
+typedef struct {
+  int nranks, rank;
+  int grid[3], pos[3];                   /* proc_grid, proc_pos (comm_mpi.cpp:58-92) */
+  int neighbor_send[6], neighbor_recv[6]; /* per phase 0:+x 1:-x 2:+y 3:-y 4:+z 5:-z; -1 = dimension not decomposed (:94-130) */
+  double sub[3], sub_lo[3], sub_hi[3];   /* brick extent and bounds (:132-140) */
+} emd_decomp;
+/* CommMPI::create_domain_decomposition (comm_mpi.cpp:52-147): minimum-surface processor grid (first found wins
+ * on ties), rank = x + px*(y + py*z), periodic neighbors, brick bounds.  Pure host arithmetic (no GPU needed). */
+int emd_comm_decompose(int nranks, int rank, const double domain[3], emd_decomp *out);
+/* TagExchangeSelf (comm_mpi.h:134-153): periodic wrap in the dimensions with wrap_dim[d] != 0 (grid[d] == 1) */
+int emd_comm_wrap_dims(emd_ctx *ctx, double *d_x, int n_local, const double domain[3], const int wrap_dim[3]);
+/* TagExchangePack (comm_mpi.h:155-226): atoms of [0,n_scan) with type >= 0 strictly beyond the phase's face are
+ * packed (72-byte Particles, ascending index, shifted by the box length on the boundary rank) and marked
+ * type = -1.  *h_count = how many (host sync, comm_mpi.cpp:229); nothing is written if count > capacity. */
+int emd_comm_exchange_pack(emd_ctx *ctx, int phase, const emd_decomp *dec, const double domain[3], double *d_x, double *d_v,
+                           double *d_q, int *d_id, int *d_type, int n_scan, void *d_pack_buffer, int capacity, int *h_count);
+/* TagHaloPack (comm_mpi.h:349-430): atoms of [0,n_scan) within comm_depth of the phase's face; also records the
+ * source indices for update_halo / update_force */
+int emd_comm_halo_pack(emd_ctx *ctx, int phase, const emd_decomp *dec, const double domain[3], double comm_depth, double *d_x,
+                       double *d_v, double *d_q, int *d_id, int *d_type, int n_scan, int *d_pack_indicies, void *d_pack_buffer,
+                       int capacity, int *h_count);
+/* TagUnpack (comm_mpi.h:432-436): set_particle(dst_begin + i, buffer[i]) */
+int emd_comm_unpack(emd_ctx *ctx, const void *d_unpack_buffer, int count, int dst_begin, double *d_x, double *d_v, double *d_q,
+                    int *d_id, int *d_type);
+/* TagExchangeCreateDestList + TagExchangeCompact (comm_mpi.h:229-250, comm_mpi.cpp:262-284): the holes (type < 0)
+ * below n_new are filled with the live atoms of [n_new, n_end), taken from the end downwards */
+int emd_comm_exchange_compact(emd_ctx *ctx, double *d_x, double *d_v, double *d_q, int *d_id, int *d_type, int n_new, int n_end);
+/* TagHaloUpdatePack / TagHaloUpdateUnpack (comm_mpi.h:462-490): positions only, 24 B per ghost */
+int emd_comm_halo_update_pack(emd_ctx *ctx, int phase, const emd_decomp *dec, const double domain[3], const double *d_x,
+                              const int *d_pack_indicies, int count, double *d_buffer);
+int emd_comm_halo_update_unpack(emd_ctx *ctx, double *d_x, int ghost_begin, int count, const double *d_buffer);
+/* TagHaloForceUnpack (comm_mpi.h:487-497): f[pack_indicies[ii]] += buffer[ii].  (TagHaloForcePack needs no kernel:
+ * the ghost rows of f are contiguous and are sent in place.) */
+int emd_comm_force_unpack(emd_ctx *ctx, double *d_f, const int *d_pack_indicies, int count, const double *d_buffer);
+
+/* transport: NCCL send/recv over NVLink on the context's stream (takes the place of MPI in comm_mpi.cpp) */
+typedef struct emd_net emd_net;
+/* 128-byte NCCL unique id, for hosts that distribute it themselves (e.g. through torch.distributed) */
+int emd_net_unique_id(void *out128);
+/* unique_id128 == NULL: rank 0 creates the id and hands it to the others over TCP (MASTER_ADDR, MASTER_PORT+29
+ * or EMD_RENDEZVOUS_PORT) */
+int emd_net_create(emd_net **out, emd_ctx *ctx, int nranks, int rank, const void *unique_id128);
+void emd_net_destroy(emd_net *n);
+/* one phase's message pair (MPI_Irecv + MPI_Send + MPI_Wait, comm_mpi.cpp:245-251,333-337,401-404,449-452),
+ * stream-ordered, no host synchronisation; either side may be 0 bytes */
+int emd_net_sendrecv(emd_net *n, const void *d_send, unsigned long long send_bytes, int peer_send, void *d_recv,
+                     unsigned long long recv_bytes, int peer_recv);
+/* the count handshake of a phase (comm_mpi.cpp:235-238, 325-328); synchronises */
+int emd_net_exchange_count(emd_net *n, int send_count, int peer_send, int peer_recv, int *h_recv_count);
+/* MPI_Allreduce(IN_PLACE) / MPI_Scan on HOST scalars (comm_mpi.cpp:150-191): is_double 0 int / 1 double, op 0 sum / 1 max */
+int emd_net_allreduce(emd_net *n, void *h_values, int count, int is_double, int op);
+int emd_net_scan_int(emd_net *n, int *h_value);
+int emd_net_barrier(emd_net *n);
+
 /* ---- thermo: Temperature/KinE functor, src/property_temperature.h:55-57 ------------------ */
 /* sum_i m[type_i] * |v_i|^2 over [0,n_local) (deterministic two-stage reduction), host result */
 int emd_reduce_mv2(emd_ctx *ctx, const double *d_v, const int *d_type, const double *d_mass,

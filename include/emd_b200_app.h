@@ -26,7 +26,7 @@ int emd_app_advance(emd_app *app, int nsteps);
 int emd_app_advance_timed(emd_app *app, int nsteps, double *h_seconds4);
 int emd_app_thermo(emd_app *app, double *T, double *PE_per_atom, double *KE_per_atom);
 /* integer properties: "N","N_local","N_ghost","N_max","step","total_neighs","nsteps",
- * "exchange_rate","half_neigh","nbinx","nbiny","nbinz"; -1 if unknown */
+ * "exchange_rate","half_neigh","nbinx","nbiny","nbinz","rank","nranks"; -1 if unknown */
 long long emd_app_get(emd_app *app, const char *what);
 /* owned atoms [0,N_local) to HOST arrays (any pointer may be NULL) */
 int emd_app_download(emd_app *app, int *h_id, int *h_type, double *h_q, double *h_x, double *h_v, double *h_f);
