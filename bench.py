@@ -104,6 +104,78 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------- SNAP
+SNAP_DIR = REPO / "input" / "snap"
+
+
+def snap_deck(td, region, nsteps):
+    txt = re.sub(r"region\s+box block.*", "region\t\tbox block 0 %d 0 %d 0 %d" % tuple(region), (SNAP_DIR / "in.snap.W").read_text())
+    txt = re.sub(r"run\s+\d+", "run\t\t%d" % nsteps, txt)
+    (td / "in.deck").write_text(txt)
+    for f in SNAP_DIR.glob("*.snap*"):
+        (td / f.name).write_bytes(f.read_bytes())
+    return td / "in.deck"
+
+
+def snap_section(device, steps=10):
+    """BASELINE.json configs[2]: SNAP tungsten (input/snap/in.snap.W, 2J=8), full list, 250 000 atoms, one B200.
+    FP64-pipe roofline: flops of the formulation actually executed (adjoint ui/yi/duidrj/deidrj, SURVEY.md 8(d):
+    464 546 + n_in * 28 446 per atom-step) against the FP64 peak measured on this pool (profiles/r01_microbench_b200.json)."""
+    import tempfile
+    import examinimd_b200 as emd
+    L = emd.lib()
+    out = {"metric": "atom_steps_per_s_snap_W_250k", "unit": UNIT,
+           "workload": "SNAP W (in.snap.W: sc 3.1803, 2J=8, rcut 4.73442 + skin 1.0, re-neighbor every step, newton on), region 50x50x100 = 250000 atoms, full CSR list"}
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        app = emd.App(["-il", str(snap_deck(td, (50, 50, 100), steps)), "--neigh-type", "CSR", "--comm-type", "SERIAL"], device=device)
+        n = app.get("N")
+        app.advance(3)
+        ms = C.c_float()
+        l0 = app.launches()
+        emd.check(L.emd_ctx_tic(app.ctx))
+        app.advance(steps)
+        emd.check(L.emd_ctx_toc(app.ctx, C.byref(ms)))
+        launches = app.launches() - l0
+        ph = app.advance_timed(steps)
+        snap = C.c_void_p(L.emd_app_device_ptr(app.handle, b"snap"))
+        npairs = C.c_int()
+        emd.check(L.emd_snap_info(snap, None, None, None, None, C.byref(npairs), None))
+        T, _, _ = app.thermo()
+        app.close()
+    value = n * steps / (ms.value * 1e-3)
+    n_in = npairs.value / n
+    flops = 464546 + n_in * 28446
+    fp64_peak, kind = 36.8, "measured (tools/microbench.cu on this pool, profiles/r01_microbench_b200.json)"
+    mb = REPO / "profiles" / "r01_microbench_b200.json"
+    if mb.exists():
+        fp64_peak = json.loads(mb.read_text())["fp64_tflops_sustained"]
+    force_ms = 1e3 * ph["force"] / steps
+    out.update({"value": value, "ms_per_step": ms.value / steps, "steps": steps, "atoms": n, "gpu_launches": launches,
+                "phase_ms_per_step": {k: 1e3 * v / steps for k, v in ph.items()}, "T_after": T,
+                "roofline": {"bound": "fp64", "formulation": "adjoint (ui, yi, duidrj, deidrj)", "n_inside_mean": n_in,
+                             "flops_per_atom_step": flops, "achieved": flops * n / (force_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                             "unit": "TFLOP/s", "frac": flops * n / (force_ms * 1e-3) / 1e12 / fp64_peak, "peak_kind": kind,
+                             "kernel": "ForceSNAP::compute = snap_pairs + snap_ui + snap_yi + snap_deidrj", "kernel_ms": force_ms}})
+    return out
+
+
+def snap_cpu_baseline(nsteps=4):
+    """the reference's own SNAP on the box's host cores: in.snap.W as shipped (256 atoms)"""
+    import tempfile
+    if not REF_OMP.exists():
+        return None
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        deck = snap_deck(td, (4, 8, 8), nsteps)
+        outp = subprocess.run([str(REF_OMP), "-il", str(deck), "--comm-type", "SERIAL", "--neigh-type", "CSR"], capture_output=True, text=True,
+                              env=cpu_env(cores), check=True, cwd=td).stdout
+    m = PERF_RE.search(outp)
+    return {"value": float(m.group(9)), "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"oracle/_ref/ExaMiniMD_ref_omp, in.snap.W as shipped (256 atoms) x {nsteps} steps, loop {float(m.group(3)):.2f} s"}
+
+
 # ---------------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
@@ -154,6 +226,7 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--region", type=int, nargs=3, default=None, help="override the lattice (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-snap", action="store_true", help="skip the SNAP (configs[2]) section of the single-GPU line")
     ap.add_argument("--iteration", default="NEIGH_HALF", help="force iteration (debug; the headline config is NEIGH_HALF)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -177,16 +250,29 @@ def main():
 
     W = max(args.warmup, 3)
     K = args.steps
-    region = tuple(args.region) if args.region else (80, 80, 80)
-    # TODO(round 1): N>1 = 3-D brick decomposition through CommNCCL; until it lands every rank runs
-    # its own replica of the single-GPU workload ("replicas only") and the aggregate is the sum.
+    brick = tuple(args.region) if args.region else (80, 80, 80)
+    # N > 1: weak scaling, ONE global system cut into `world` bricks of the single-GPU size by CommMPI (3-D domain
+    # decomposition, NCCL halo exchange over NVLink every step).  The processor grid is the reference's minimum-surface
+    # rule (comm_mpi.cpp:58-89), which for these boxes is (1,1,2), (1,2,2), (2,2,2).
+    L = emd.lib()
+    grid = (1, 1, 1)
+    if world > 1:
+        g = {2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world)
+        if g is None:
+            raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
+        region = tuple(b * k for b, k in zip(brick, g))
+        dec = emd.Decomp()
+        emd.check(L.emd_comm_decompose(world, rank, emd.vec3([r * 1.0 for r in region]), C.byref(dec)))
+        assert tuple(dec.grid) == g, (tuple(dec.grid), g)
+        grid = g
+    else:
+        region = brick
     half = 1 if args.iteration == "NEIGH_HALF" else 0
-    argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", args.iteration, "--comm-type", "SERIAL",
+    argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", args.iteration, "--comm-type", "MPI" if world > 1 else "SERIAL",
             "--region", *map(str, region)]
     app = emd.App(argv, device=local_rank)
-    L = emd.lib()
     ctx = app.ctx
-    n_atoms = app.get("N")
+    n_atoms = app.get("N")  # global atom count
 
     def barrier():
         app.sync()
@@ -214,7 +300,7 @@ def main():
     if dist:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     step_ms = float(t_ms.item()) / K
-    value = world * n_atoms * K / (float(t_ms.item()) * 1e-3)
+    value = n_atoms * K / (float(t_ms.item()) * 1e-3)
 
     # ---- dominant kernel: LJ force (with its fused zero-f), timed alone on the live state ----
     n_local, n_ghost = app.get("N_local"), app.get("N_ghost")
@@ -248,20 +334,28 @@ def main():
     peak, peak_kind = peaks()
     achieved = force_bytes / (force_ms * 1e-3) / 1e9
     b_lj = 208 + 100 * g + 52 * (g - 1) + 4 * nbar
+    value_per_gpu = value / world
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": "lj_tiles_kernel" if tiles else "lj_force_kernel<half> + zero_rows_kernel", "kernel_ms": force_ms, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_atom": force_bytes / n_local, "nbar": nbar, "g": g,
-                "whole_step": {"B_LJ_bytes_per_atom_step": b_lj, "achieved_gbs": b_lj * value / world / 1e9,
-                               "frac": b_lj * value / world / 1e9 / peak}}
+                "whole_step": {"B_LJ_bytes_per_atom_step": b_lj, "achieved_gbs": b_lj * value_per_gpu / 1e9,
+                               "frac": b_lj * value_per_gpu / 1e9 / peak}}
 
     # ---- e2e: host buffers in and out every step ---------------------------------------------
     st = app.download()
-    hx = torch.from_numpy(st["x"]).pin_memory(); hv = torch.from_numpy(st["v"]).pin_memory(); hf = torch.from_numpy(st["f"]).pin_memory()
-    hid = torch.from_numpy(st["id"]).pin_memory(); htype = torch.from_numpy(st["type"]).pin_memory()
+    cap = int(n_local * 1.05) + 4096  # head-room: with CommMPI the owned-atom count drifts as atoms migrate between bricks
+
+    def pinned(a, width):
+        t = torch.zeros((cap, width) if width > 1 else (cap,), dtype=torch.from_numpy(a).dtype).pin_memory()
+        t[: a.shape[0]] = torch.from_numpy(a)
+        return t
+
+    hx, hv, hf = pinned(st["x"], 3), pinned(st["v"], 3), pinned(st["f"], 3)
+    hid, htype = pinned(st["id"], 1), pinned(st["type"], 1)
     Ke = min(K, 40)
-    h2d = 72 * n_local
-    d2h = 72 * n_local
-    d2h_rebuild = 8 * n_local
+    h2d = 72 * n_local * world      # whole job, every step: x, v, f of the owned atoms of every rank
+    d2h = 72 * n_local * world
+    d2h_rebuild = 8 * n_local * world
 
     def e2e_step():
         emd.check(L.emd_app_upload(app.handle, P(hx.data_ptr()), P(hv.data_ptr()), P(hf.data_ptr())))
@@ -283,7 +377,7 @@ def main():
     t_e = torch.tensor([max(ms.value * 1e-3, e2e_wall)], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_atoms * Ke / float(t_e.item())
+    e2e_value = n_atoms * Ke / float(t_e.item())
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + d2h_rebuild / rate,
            "steps": Ke, "api": "emd_app_upload -> emd_app_advance(1) -> emd_app_download (pinned host x,v,f)"}
 
@@ -294,12 +388,23 @@ def main():
     T, PE, KE = app.thermo()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.region else f"LJ fcc region {region} (debug override)",
-                       "atoms_per_gpu": n_atoms, "ghosts": n_ghost, "neigh_entries": total_neighs,
-                       "l2": "state + list (>400 MB) exceed the 126 MB L2; no flush between steps",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} replicas (CommNCCL pending)"},
+            "config": {"workload": (WORKLOAD if not args.region else f"LJ fcc brick {brick} per GPU (debug override)") +
+                       ("" if world == 1 else f"; weak scaling: that brick per GPU, global region {region}"),
+                       "atoms_total": n_atoms, "atoms_per_gpu": n_atoms // world, "ghosts_rank0": n_ghost, "neigh_entries_rank0": total_neighs,
+                       "l2": "state + list (>400 MB per GPU) exceed the 126 MB L2; no flush between steps",
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"3-D domain decomposition {grid[0]}x{grid[1]}x{grid[2]} (CommMPI), NCCL halo exchange every step, one process per GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "phase_ms_per_step": phases,
             "thermo_after": {"T": T, "PE": PE, "E": PE + KE}}
+    app.close()
+    app = None
+    if world == 1 and not args.no_snap and not args.region:
+        try:
+            line["snap"] = snap_section(local_rank)
+            if not args.no_cpu_baseline:
+                line["snap"]["cpu_baseline"] = snap_cpu_baseline()
+        except Exception as e:
+            line["snap"] = {"error": str(e)}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -307,7 +412,6 @@ def main():
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
-    app.close()
     if dist:
         dist.destroy_process_group()
 
