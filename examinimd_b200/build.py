@@ -45,7 +45,7 @@ def sources() -> list[Path]:
 
 
 def headers_mtime() -> float:
-    hs = list(CSRC.rglob("*.h")) + list(CSRC.rglob("*.cuh")) + list((REPO / "include").glob("*.h"))
+    hs = list(CSRC.rglob("*.h")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.inc")) + list((REPO / "include").glob("*.h"))
     return max(p.stat().st_mtime for p in hs)
 
 

@@ -56,7 +56,7 @@ struct SnapTab {
   int uf_block[kMaxJ + 1];   // full layout: (j,ma,mb) at uf_block[j] + ma*(j+1) + mb  (the reference's u(j,ma,mb))
   double rootpq[kRootDim * kRootDim];
   Triple triple[kMaxTriples];         // sorted by j
-  int tri_begin[kMaxJ + 2];           // triples of output level j: [tri_begin[j], tri_begin[j+1])
+  int tri_begin[kMaxJ + 2];           // blocks of output level j: [tri_begin[j], tri_begin[j+1]) (twojmax = 8 list)
   short strip_j[kMaxStrips], strip_ma[kMaxStrips]; // output strips, most expensive first
   int elem_of_type[kMaxTypesConst];
   double radelem[kMaxTypesConst], wjelem[kMaxTypesConst];
@@ -98,7 +98,6 @@ double clebsch_gordan(int j1, int j2, int j, int m1, int m2) {
 struct emd_snap {
   SnapTab h;              // host copy of the tables
   SnapTab *d_tab = nullptr;
-  double *d_cg = nullptr;     // compact Clebsch-Gordan blocks, one (j1+1)x(j2+1) block per triple
   double *d_betaj = nullptr;  // [nelements][ntriples]
   int ncoeff = 0;
   // work arrays (grow-only)
@@ -288,11 +287,80 @@ __global__ void __launch_bounds__(32 * kMaxCol) snap_ui_kernel(const SnapTab *__
 
 // ------------------------------------------------------------------------------------ snap_yi
 // block = 32 atoms (lanes) x W warps.  Dynamic shared memory: sU [nuf][32] double2 (full U_tot of the batch).
+//
+// Register tiling of compute_zi's inner loop (sna_impl.hpp:248-262).  A warp takes an output STRIP (j, ma) = all
+// NMB = j/2+1 values of mb at once.  For one row pair (ma1, ma2) of a block (j1,j2,j) the products are
+//     z(mb) += cg(mb1, mb2) u_j1(ma1, mb1) u_j2(ma2, mb2),   mb2 = mb + C - mb1,  C = (j1+j2-j)/2,
+// so while mb1 walks up its row, the NMB elements of the other row that the strip needs form a WINDOW that slides
+// down by one element per step: one new element of each row is read from shared memory per step and feeds NMB
+// products (2 LDS.128 per 6*NMB FP64 instructions instead of 2 per 6), the Clebsch-Gordan factors are consecutive
+// constant-memory words fetched through the uniform datapath.  Measured history at 250 000 atoms: plain loop nest
+// 14.5 ms (shared-memory bound, 60 % LSU / 23 % FP64 pipe); fully unrolled per-block code (125 template
+// instantiations, 380 KB of SASS) 24 ms free-running and 13.5 ms with the warps held on one block by barriers
+// (instruction-fetch bound: 18 no-instruction stalls per issue); this generic sliding window: see profiles/.
 constexpr int kYiWarps = 16;
+constexpr int kNumCg = 4098; // see snap_triples.inc
+constexpr int kCgPad = 8;    // zero words before and after the table: a strip's window may look up to 4 words outside a block row
+__constant__ double c_cg[kNumCg + 2 * kCgPad]; // compact Clebsch-Gordan blocks for twojmax = 8 (a 2J = 6 run uses a subset)
 
-__global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ cg,
-                                                                const double *__restrict__ betaj, const int *__restrict__ type, int n_local,
-                                                                const double2 *__restrict__ ulist, int ustride, double2 *__restrict__ ylist) {
+template <int NMB>
+__device__ __forceinline__ void z_block(const double2 *__restrict__ U, const SnapTab &t, int tr, int J, int ma, double bj,
+                                        double (&yr)[kMaxCol], double (&yi)[kMaxCol]) {
+  const int j1 = t.triple[tr].j1, j2 = t.triple[tr].j2, cgoff = t.triple[tr].cgoff + kCgPad;
+  const int C = (j1 + j2 - J) / 2;
+  const int lo1 = max(0, C - j2), hi1 = min(j1, C + NMB - 1); // union of the mb1 ranges of the strip's outputs
+  const int ma1lo = max(0, (2 * ma - J - j2 + j1) / 2), ma1hi = min(j1, (2 * ma - J + j2 + j1) / 2);
+  double zr[NMB], zi[NMB];
+#pragma unroll
+  for (int k = 0; k < NMB; k++) { zr[k] = 0.0; zi[k] = 0.0; }
+  for (int ma1 = ma1lo; ma1 <= ma1hi; ma1++) {
+    const int ma2 = (2 * ma - J - (2 * ma1 - j1) + j2) / 2;
+    const double2 *r1 = U + (size_t)(t.uf_block[j1] + ma1 * (j1 + 1) + lo1) * 32; // next element of row 1 (walks up)
+    const double2 *r2 = U + (size_t)(t.uf_block[j2] + ma2 * (j2 + 1)) * 32;
+    const double cga = c_cg[cgoff + ma1 * (j2 + 1) + ma2];
+    // The window is a ring of NMB registers: at step s = mb1 - lo1 output k reads slot (k - s) mod NMB, which holds
+    // u_j2(ma2, k + C - mb1); elements outside 0..j2 are zero (their products vanish).  The mb1 loop is unrolled NMB-fold
+    // so every slot index is a compile-time constant and nothing is ever moved.
+    double2 w[NMB];
+#pragma unroll
+    for (int k = 0; k < NMB; k++) {
+      const int mb2 = k + C - lo1;
+      w[k] = (mb2 >= 0 && mb2 <= j2) ? r2[mb2 * 32] : make_double2(0.0, 0.0);
+    }
+    int nb2 = C - lo1 - 1;                      // row-2 index entering the window after the current step
+    const double2 *r2n = r2 + nb2 * 32;
+    const double *pc = c_cg + cgoff + lo1 * j2 + C; // cg(mb1, k + C - mb1), k = 0..NMB-1: consecutive words; advances by j2 per step
+    double sr[NMB], si[NMB];
+#pragma unroll
+    for (int k = 0; k < NMB; k++) { sr[k] = 0.0; si[k] = 0.0; }
+    for (int mb1 = lo1; mb1 <= hi1; mb1 += NMB) {
+#pragma unroll
+      for (int r = 0; r < NMB; r++) {
+        if (mb1 + r <= hi1) {
+          const double2 a = *r1;
+#pragma unroll
+          for (int k = 0; k < NMB; k++) {
+            const double2 wk = w[(k - r + NMB) % NMB];
+            const double c = pc[k];
+            sr[k] += c * (a.x * wk.x - a.y * wk.y);
+            si[k] += c * (a.x * wk.y + a.y * wk.x);
+          }
+          // the slot of output NMB-1 is free now: it receives the element output 0 needs at the next step
+          w[(NMB - 1 - r + NMB) % NMB] = (nb2 >= 0 && nb2 <= j2) ? *r2n : make_double2(0.0, 0.0);
+          r1 += 32; r2n -= 32; nb2--; pc += j2;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NMB; k++) { zr[k] += cga * sr[k]; zi[k] += cga * si[k]; }
+  }
+#pragma unroll
+  for (int k = 0; k < NMB; k++) { yr[k] += bj * zr[k]; yi[k] += bj * zi[k]; }
+}
+
+__global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ betaj,
+                                                                const int *__restrict__ type, int n_local, const double2 *__restrict__ ulist,
+                                                                int ustride, double2 *__restrict__ ylist) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_next;
   const SnapTab &t = *tab;
@@ -300,9 +368,10 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const bool valid = i < n_local;
+  const int twojmax = t.twojmax;
   if (threadIdx.x == 0) s_next = 0;
   // expand the half range to the full (ma,mb) range with the inversion symmetry
-  for (int j = 0; j <= t.twojmax; j++) {
+  for (int j = 0; j <= twojmax; j++) {
     const int nhalf = (j / 2 + 1) * (j + 1);
     for (int k = warp; k < nhalf; k += nwarps) {
       const int mb = k / (j + 1), ma = k - mb * (j + 1);
@@ -316,10 +385,10 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
   }
   __syncthreads();
   const int elem_i = valid ? t.elem_of_type[type[i]] : 0;
-  const double *beta_i = betaj + (size_t)elem_i * t.ntriples;
+  const double *beta_i = betaj + (size_t)elem_i * kMaxTriples;
   const double2 *U = sU + lane;
 
-  for (;;) {
+  for (;;) { // strips (j, ma) from a queue sorted by cost, most expensive first
     int s = 0;
     if (lane == 0) s = atomicAdd(&s_next, 1);
     s = __shfl_sync(0xffffffffu, s, 0);
@@ -329,37 +398,16 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
 #pragma unroll
     for (int mb = 0; mb < kMaxCol; mb++) { yr[mb] = 0.0; yi[mb] = 0.0; }
     for (int tr = t.tri_begin[J]; tr < t.tri_begin[J + 1]; tr++) {
-      const int j1 = t.triple[tr].j1, j2 = t.triple[tr].j2;
-      const double *cgb = cg + t.triple[tr].cgoff; // cgarray(j1,j2,J,m1,m2) at m1*(j2+1)+m2
+      if (t.triple[tr].j1 > twojmax) continue; // blocks of the 2J = 8 table that a smaller twojmax does not have
       const double bj = beta_i[tr];
-      const int u1b = t.uf_block[j1], u2b = t.uf_block[j2];
-      const int ma1lo = max(0, (2 * ma - J - j2 + j1) / 2), ma1hi = min(j1, (2 * ma - J + j2 + j1) / 2);
-#pragma unroll
-      for (int mb = 0; mb < kMaxCol; mb++) {
-        if (2 * mb <= J && !(2 * mb == J && ma > mb)) { // compute_zi :228-270 for one (ma, mb)
-          const int mb1lo = max(0, (2 * mb - J - j2 + j1) / 2), mb1hi = min(j1, (2 * mb - J + j2 + j1) / 2);
-          double zr = 0.0, zi = 0.0;
-          for (int ma1 = ma1lo; ma1 <= ma1hi; ma1++) {
-            const int ma2 = (2 * ma - J - (2 * ma1 - j1) + j2) / 2;
-            const int mb2lo = (2 * mb - J - (2 * mb1lo - j1) + j2) / 2;
-            const double2 *p1 = U + (size_t)(u1b + ma1 * (j1 + 1) + mb1lo) * 32;
-            const double2 *p2 = U + (size_t)(u2b + ma2 * (j2 + 1) + mb2lo) * 32;
-            const double *pc = cgb + mb1lo * (j2 + 1) + mb2lo;
-            double sr = 0.0, si = 0.0;
-            for (int mb1 = mb1lo; mb1 <= mb1hi; mb1++) {
-              const double2 a = *p1, b = *p2;
-              const double c = __ldg(pc);
-              sr += c * (a.x * b.x - a.y * b.y);
-              si += c * (a.x * b.y + a.y * b.x);
-              p1 += 32; p2 -= 32; pc += j2;
-            }
-            const double ca = __ldg(cgb + ma1 * (j2 + 1) + ma2);
-            zr += sr * ca;
-            zi += si * ca;
-          }
-          yr[mb] += bj * zr;
-          yi[mb] += bj * zi;
-        }
+      // even J, ma below the diagonal of the middle column: that output has weight 0 in the contraction, leave it out
+      switch (J / 2 + 1 - ((J % 2 == 0 && ma > J / 2) ? 1 : 0)) {
+        case 0: break;
+        case 1: z_block<1>(U, t, tr, J, ma, bj, yr, yi); break;
+        case 2: z_block<2>(U, t, tr, J, ma, bj, yr, yi); break;
+        case 3: z_block<3>(U, t, tr, J, ma, bj, yr, yi); break;
+        case 4: z_block<4>(U, t, tr, J, ma, bj, yr, yi); break;
+        default: z_block<5>(U, t, tr, J, ma, bj, yr, yi); break;
       }
     }
     if (valid) {
@@ -378,6 +426,7 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
 
 // -------------------------------------------------------------------------------- snap_deidrj
 constexpr int kDeThreads = 128;
+constexpr int kDeStageAtoms = 12; // Y rows staged per CTA (155 double2 each at 2J = 8)
 
 // one level of the dU recursion for column mb, in place, all three directions (compute_duarray :786-838)
 __device__ __forceinline__ void du_level(double2 (&u)[kMaxJ + 1], double2 (&du)[3][kMaxJ + 1], int j, int mb, const double *__restrict__ s_rootpq,
@@ -417,8 +466,22 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
   __shared__ double s_rootpq[kRootDim * kRootDim];
   const SnapTab &t = *tab;
   for (int k = threadIdx.x; k < kRootDim * kRootDim; k += blockDim.x) s_rootpq[k] = t.rootpq[k];
+  // Pairs are sorted by their central atom, so the CTA's 128 pairs belong to a short run of consecutive atoms (7 at 18
+  // in-cutoff neighbors): their Y rows (atom-major, 2.4 KB each) are staged in shared memory with one contiguous copy,
+  // so the contraction reads Y at LDS latency.  (Reading Y from global at its point of use left the kernel
+  // latency-bound at 8 warps/SM: 2.5 long-scoreboard stalls per issue, 42 % FP64 pipe.)  Atoms beyond the staged
+  // run (very short rows) fall back to global loads.
+  double2 *s_y = reinterpret_cast<double2 *>(dyn) + (size_t)kMaxJ * 4 * blockDim.x;
+  const int p0 = blockIdx.x * blockDim.x;
+  const int i_first = pair_i[p0], i_last = pair_i[min(p0 + (int)blockDim.x, npairs) - 1];
+  const int n_staged = min(i_last - i_first + 1, kDeStageAtoms);
+  {
+    const double2 *src = ylist + (size_t)i_first * t.nuh;
+    const int n = n_staged * t.nuh;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s_y[k] = src[k];
+  }
   __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = p0 + threadIdx.x;
   if (p >= npairs) return;
   double2 *boot = reinterpret_cast<double2 *>(dyn) + threadIdx.x;
   const int bs = blockDim.x;
@@ -457,7 +520,7 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
   db_r[1] += r0inv;
   const double sfac = sfac_of(t, r, rcut) * wj, dsfac = dsfac_of(t, r, rcut) * wj;
 
-  const double2 *Y = ylist + (size_t)i * t.nuh;
+  const double2 *Y = (i - i_first < n_staged) ? s_y + (size_t)(i - i_first) * t.nuh : ylist + (size_t)i * t.nuh;
   double S0 = 0.0, S[3] = {0.0, 0.0, 0.0};
   double2 u[kMaxJ + 1], du[3][kMaxJ + 1];
   u[0] = make_double2(1.0, 0.0);
@@ -512,7 +575,7 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
 
 size_t ui_smem(const SnapTab &h) { return ((size_t)h.nuh * 32 + (size_t)kMaxJ * 32 * h.ncol) * sizeof(double2); }
 size_t yi_smem(const SnapTab &h) { return (size_t)h.nuf * 32 * sizeof(double2); }
-size_t de_smem() { return (size_t)kMaxJ * 4 * kDeThreads * sizeof(double2); }
+size_t de_smem(const SnapTab &h) { return ((size_t)kMaxJ * 4 * kDeThreads + (size_t)kDeStageAtoms * h.nuh) * sizeof(double2); }
 
 } // namespace
 
@@ -543,32 +606,41 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
   h.cutsq = rcutmax * rcutmax;
   for (int ty = 0; ty < p->ntypes; ty++) h.elem_of_type[ty] = p->elem_of_type[ty];
 
-  // index lists (build_indexlist, sna_impl.hpp:86-132, diagonalstyle 3): idxj = the ncoeff bispectrum components,
-  // idxj_full = every (j1 >= j2, j) block of Z
+  // index lists (build_indexlist, sna_impl.hpp:86-132, diagonalstyle 3): idxj = the ncoeff bispectrum components of THIS
+  // twojmax; the Z blocks (idxj_full) are always the twojmax = 8 list of snap_triples.inc (sorted by j), of which a
+  // smaller twojmax uses the blocks with j1 <= twojmax
   struct T3 { int j1, j2, j; };
-  std::vector<T3> idxj, full;
+  std::vector<T3> idxj;
   for (int j1 = 0; j1 <= J2; j1++)
     for (int j2 = 0; j2 <= j1; j2++)
-      for (int j = abs(j1 - j2); j <= imin(J2, j1 + j2); j += 2) {
+      for (int j = abs(j1 - j2); j <= imin(J2, j1 + j2); j += 2)
         if (j >= j1) idxj.push_back({j1, j2, j});
-        full.push_back({j1, j2, j});
-      }
   s->ncoeff = (int)idxj.size();
   if (s->ncoeff != p->ncoeffall - 1) { // :315-318
     set_error("emd_snap_create: coefficient count %d does not match twojmax %d (expected %d + 1)", p->ncoeffall, J2, s->ncoeff);
     delete s; return 1;
   }
-  std::stable_sort(full.begin(), full.end(), [](const T3 &a, const T3 &b) { return a.j < b.j; });
-  h.ntriples = (int)full.size();
-  std::vector<double> cg;
-  for (int tI = 0; tI < h.ntriples; tI++) {
-    const T3 &q = full[tI];
-    h.triple[tI].j1 = (short)q.j1; h.triple[tI].j2 = (short)q.j2; h.triple[tI].j = (short)q.j; h.triple[tI].cgoff = (int)cg.size();
-    for (int m1 = 0; m1 <= q.j1; m1++)
-      for (int m2 = 0; m2 <= q.j2; m2++) cg.push_back(clebsch_gordan(q.j1, q.j2, q.j, m1, m2));
+  static const struct { int idx, j1, j2, j, cgoff; } kTri[] = {
+#define X(IDX, TJ1, TJ2, TJ, CGOFF) {IDX, TJ1, TJ2, TJ, CGOFF},
+#include "snap_triples.inc"
+#undef X
+  };
+  static_assert(sizeof kTri / sizeof kTri[0] == kMaxTriples, "snap_triples.inc must list the 125 blocks of twojmax = 8");
+  std::vector<T3> full;
+  h.ntriples = kMaxTriples;
+  std::vector<double> cg(kNumCg, 0.0);
+  for (int tI = 0; tI < kMaxTriples; tI++) {
+    const int j1 = kTri[tI].j1, j2 = kTri[tI].j2, j = kTri[tI].j;
+    full.push_back({j1, j2, j});
+    h.triple[tI].j1 = (short)j1; h.triple[tI].j2 = (short)j2; h.triple[tI].j = (short)j; h.triple[tI].cgoff = kTri[tI].cgoff;
+    if (kTri[tI].idx != tI || kTri[tI].cgoff + (j1 + 1) * (j2 + 1) > kNumCg || (tI > 0 && full[tI - 1].j > j)) {
+      set_error("emd_snap_create: snap_triples.inc is inconsistent"); delete s; return 1;
+    }
+    for (int m1 = 0; m1 <= j1; m1++)
+      for (int m2 = 0; m2 <= j2; m2++) cg[kTri[tI].cgoff + m1 * (j2 + 1) + m2] = clebsch_gordan(j1, j2, j, m1, m2);
   }
-  h.ncg = (int)cg.size();
-  for (int j = 0, tI = 0; j <= J2 + 1; j++) {
+  h.ncg = kNumCg;
+  for (int j = 0, tI = 0; j <= kMaxJ + 1; j++) {
     while (tI < h.ntriples && full[tI].j < j) tI++;
     h.tri_begin[j] = tI;
   }
@@ -602,6 +674,7 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
       long cost = 0;
       for (int tI = h.tri_begin[j]; tI < h.tri_begin[j + 1]; tI++) {
         const int j1 = full[tI].j1, j2 = full[tI].j2;
+        if (j1 > J2) continue;
         const long na = imin(j1, (2 * ma - j + j2 + j1) / 2) - imax(0, (2 * ma - j - j2 + j1) / 2) + 1;
         for (int mb = 0; 2 * mb <= j; mb++) {
           const long nb = imin(j1, (2 * mb - j + j2 + j1) / 2) - imax(0, (2 * mb - j - j2 + j1) / 2) + 1;
@@ -616,8 +689,11 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
 
   EMD_CUDA(cudaMalloc((void **)&s->d_tab, sizeof(SnapTab)));
   EMD_CUDA(cudaMemcpy(s->d_tab, &h, sizeof(SnapTab), cudaMemcpyHostToDevice));
-  EMD_CUDA(cudaMalloc((void **)&s->d_cg, sizeof(double) * cg.size()));
-  EMD_CUDA(cudaMemcpy(s->d_cg, cg.data(), sizeof(double) * cg.size(), cudaMemcpyHostToDevice));
+  {
+    std::vector<double> padded(kNumCg + 2 * kCgPad, 0.0);
+    std::copy(cg.begin(), cg.end(), padded.begin() + kCgPad);
+    EMD_CUDA(cudaMemcpyToSymbol(c_cg, padded.data(), sizeof(double) * padded.size())); // the same twojmax = 8 table for every emd_snap
+  }
   EMD_CUDA(cudaMalloc((void **)&s->d_betaj, sizeof(double) * betaj.size()));
   EMD_CUDA(cudaMemcpy(s->d_betaj, betaj.data(), sizeof(double) * betaj.size(), cudaMemcpyHostToDevice));
   int dev = 0;
@@ -626,7 +702,7 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
   if (yi_smem(h) > (size_t)s->max_smem_optin) { set_error("emd_snap_create: U_tot batch does not fit in shared memory"); delete s; return 1; }
   EMD_CUDA(cudaFuncSetAttribute(snap_ui_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ui_smem(h)));
   EMD_CUDA(cudaFuncSetAttribute(snap_yi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yi_smem(h)));
-  EMD_CUDA(cudaFuncSetAttribute(snap_deidrj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)de_smem()));
+  EMD_CUDA(cudaFuncSetAttribute(snap_deidrj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)de_smem(h)));
   *out = s;
   return 0;
 }
@@ -634,7 +710,6 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
 void emd_snap_destroy(emd_snap *s) {
   if (!s) return;
   if (s->d_tab) cudaFree(s->d_tab);
-  if (s->d_cg) cudaFree(s->d_cg);
   if (s->d_betaj) cudaFree(s->d_betaj);
   s->ulist.release(); s->ylist.release(); s->cnt.release(); s->pair_i.release(); s->pair_j.release(); s->queue.release();
   delete s;
@@ -689,9 +764,9 @@ int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const i
   double2 *ulist = s->ulist.as<double2>(), *ylist = s->ylist.as<double2>();
   const int nbatch = grid_for(n_local, 32);
   EMD_LAUNCH(ctx, snap_ui_kernel, nbatch, 32 * h.ncol, ui_smem(h), s->d_tab, d_x, d_type, n_local, cnt, pair_j, ulist, s->ucap);
-  EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h), s->d_tab, s->d_cg, s->d_betaj, d_type, n_local, ulist, s->ucap, ylist);
+  EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h), s->d_tab, s->d_betaj, d_type, n_local, ulist, s->ucap, ylist);
   if (npairs > 0)
-    EMD_LAUNCH(ctx, snap_deidrj_kernel, grid_for(npairs, kDeThreads), kDeThreads, de_smem(), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
+    EMD_LAUNCH(ctx, snap_deidrj_kernel, grid_for(npairs, kDeThreads), kDeThreads, de_smem(h), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
                ylist, d_f);
   return 0;
 }
