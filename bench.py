@@ -104,6 +104,24 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """the C++ layer prints the reference's own banner lines (e.g. `CommSerial`, src/comm_types/comm_serial.cpp:42) on
+    stdout; bench.py's stdout must hold exactly one JSON line, so they are sent to stderr while an App is created"""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 # ------------------------------------------------------------------------------------- SNAP
 SNAP_DIR = REPO / "input" / "snap"
 
@@ -128,7 +146,8 @@ def snap_section(device, steps=10):
            "workload": "SNAP W (in.snap.W: sc 3.1803, 2J=8, rcut 4.73442 + skin 1.0, re-neighbor every step, newton on), region 50x50x100 = 250000 atoms, full CSR list"}
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
-        app = emd.App(["-il", str(snap_deck(td, (50, 50, 100), steps)), "--neigh-type", "CSR", "--comm-type", "SERIAL"], device=device)
+        with stdout_to_stderr():
+            app = emd.App(["-il", str(snap_deck(td, (50, 50, 100), steps)), "--neigh-type", "CSR", "--comm-type", "SERIAL"], device=device)
         n = app.get("N")
         app.advance(3)
         ms = C.c_float()
@@ -270,7 +289,8 @@ def main():
     half = 1 if args.iteration == "NEIGH_HALF" else 0
     argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", args.iteration, "--comm-type", "MPI" if world > 1 else "SERIAL",
             "--region", *map(str, region)]
-    app = emd.App(argv, device=local_rank)
+    with stdout_to_stderr():
+        app = emd.App(argv, device=local_rank)
     ctx = app.ctx
     n_atoms = app.get("N")  # global atom count
 

@@ -115,6 +115,8 @@ _SIGS = {
     "emd_comm_halo_phase": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _D3, _D3, _D3,
                                       C.c_double, C.POINTER(C.c_int)]),
     "emd_comm_halo_update_phase": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _D3]),
+    "emd_comm_halo_resolve": (C.c_int, [_P, _P * 6, C.c_int * 6, C.c_int, _D3, _P, _P]),
+    "emd_comm_halo_refresh": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "emd_comm_force_fold_phase": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
     "emd_comm_decompose": (C.c_int, [C.c_int, C.c_int, _D3, C.POINTER(Decomp)]),
     "emd_comm_wrap_dims": (C.c_int, [_P, _P, C.c_int, _D3, C.c_int * 3]),

@@ -49,18 +49,20 @@ void CommSerial::exchange_halo() {
     N_ghost += count;
   }
   system->N_ghost = N_ghost;
+  // resolve every ghost to its owned root atom + total shift for the single-kernel refresh
+  if (ghost_root.extent() < (size_t)N_ghost) {
+    if (!ghost_root.alloc((size_t)N_ghost + N_ghost / 8 + 1) || !ghost_shift.alloc(3 * ((size_t)N_ghost + N_ghost / 8 + 1))) fail("alloc ghost_root");
+  }
+  const int *lists[6];
+  int counts[6];
+  for (int p = 0; p < 6; p++) { lists[p] = pack_indicies[p].ptr; counts[p] = num_ghost[p]; }
+  if (emd_comm_halo_resolve(system->ctx, lists, counts, N_local, L, ghost_root.ptr, ghost_shift.ptr)) fail("halo_resolve");
 }
 
-// src/comm_types/comm_serial.cpp:99-110
+// src/comm_types/comm_serial.cpp:99-110: the six phase copies collapse into one kernel (see emd_comm_halo_resolve)
 void CommSerial::update_halo() {
-  T_INT N_ghost = 0;
-  const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
-  for (int phase = 0; phase < 6; phase++) {
-    if (emd_comm_halo_update_phase(system->ctx, phase, system->x, system->v, system->q, system->id, system->type,
-                                   pack_indicies[phase].ptr, num_ghost[phase], system->N_local + N_ghost, L))
-      fail("halo_update_phase");
-    N_ghost += num_ghost[phase];
-  }
+  if (emd_comm_halo_refresh(system->ctx, system->x, system->N_local, system->N_ghost, ghost_root.ptr, ghost_shift.ptr))
+    fail("halo_refresh");
 }
 
 // src/comm_types/comm_serial.cpp:112-127

@@ -16,6 +16,8 @@ class CommSerial : public Comm {
   T_INT num_ghost[6];
   T_INT ghost_offsets[6];
   DeviceArray<T_INT> pack_indicies[6]; // source index of every ghost, per phase (replayed by update_halo)
+  DeviceArray<T_INT> ghost_root;       // owned root atom of every ghost   } resolved once per exchange_halo, so that
+  DeviceArray<T_FLOAT> ghost_shift;    // its total periodic shift [.][3]   } update_halo is a single kernel
 
 public:
   CommSerial(System *s, T_X_FLOAT comm_depth_);

@@ -71,9 +71,62 @@ __global__ void __launch_bounds__(256) force_fold_kernel(double *f, const int *_
   f[3 * i + 2] += f[3 * g + 2];
 }
 
+// ---- fused per-step refresh --------------------------------------------------------------------------------
+// A ghost made in phase p copies its source shifted by -/+L in dimension p/2; the source may itself be a ghost of an
+// earlier dimension (comm_serial.cpp:62-66), which is why the reference refreshes phase by phase.  Following that chain
+// ONCE per ghost build gives every ghost its owned root atom and its total shift (at most one shift per dimension: an
+// odd phase never re-scans the ghosts of its even twin), after which the whole refresh is one kernel with no
+// dependencies instead of six dependent launches: x[ghost] = x[root] + shift, bit-identical to the phase-wise copy.
+struct HaloLists { const int *pack[6]; int begin[7]; };
+
+__global__ void __launch_bounds__(256) halo_resolve_kernel(HaloLists h, int n_local, int n_ghost, double Lx, double Ly, double Lz,
+                                                           int *__restrict__ root, double *__restrict__ shift) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_ghost) return;
+  const double L[3] = {Lx, Ly, Lz};
+  double s[3] = {0.0, 0.0, 0.0};
+  int i = n_local + k;
+  while (i >= n_local) {
+    int p = 0;
+#pragma unroll
+    for (int q = 1; q < 6; q++) p += (i >= h.begin[q]);
+    s[p / 2] += (p % 2 == 0) ? -L[p / 2] : L[p / 2];
+    i = h.pack[p][i - h.begin[p]];
+  }
+  root[k] = i;
+  shift[3 * (size_t)k] = s[0]; shift[3 * (size_t)k + 1] = s[1]; shift[3 * (size_t)k + 2] = s[2];
+}
+
+__global__ void __launch_bounds__(256) halo_refresh_kernel(double *__restrict__ x, int n_local, long long n3, const int *__restrict__ root,
+                                                           const double *__restrict__ shift) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n3) return;
+  const long long k = e / 3;
+  const int d = (int)(e - 3 * k);
+  x[3 * (size_t)n_local + e] = x[3 * (size_t)root[k] + d] + shift[e];
+}
+
 } // namespace
 
 extern "C" {
+
+int emd_comm_halo_resolve(emd_ctx *ctx, const int *const d_pack_indicies[6], const int counts[6], int n_local, const double domain[3],
+                          int *d_root, double *d_shift) {
+  HaloLists h;
+  int n_ghost = 0;
+  for (int p = 0; p < 6; p++) { h.pack[p] = d_pack_indicies[p]; h.begin[p] = n_local + n_ghost; n_ghost += counts[p]; }
+  h.begin[6] = n_local + n_ghost;
+  if (n_ghost <= 0) return 0;
+  EMD_LAUNCH(ctx, halo_resolve_kernel, grid_for(n_ghost, 256), 256, 0, h, n_local, n_ghost, domain[0], domain[1], domain[2], d_root, d_shift);
+  return 0;
+}
+
+int emd_comm_halo_refresh(emd_ctx *ctx, double *d_x, int n_local, int n_ghost, const int *d_root, const double *d_shift) {
+  if (n_ghost <= 0) return 0;
+  const long long n3 = 3LL * n_ghost;
+  EMD_LAUNCH(ctx, halo_refresh_kernel, grid_for(n3, 256), 256, 0, d_x, n_local, n3, d_root, d_shift);
+  return 0;
+}
 
 int emd_comm_wrap(emd_ctx *ctx, double *d_x, int n_local, const double domain[3]) {
   if (n_local <= 0) return 0;

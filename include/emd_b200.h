@@ -224,6 +224,14 @@ int emd_comm_halo_phase(emd_ctx *ctx, int phase, double *d_x, double *d_v, doubl
 int emd_comm_halo_update_phase(emd_ctx *ctx, int phase, double *d_x, double *d_v, double *d_q,
                                int *d_id, int *d_type, const int *d_pack_indicies, int count,
                                int ghost_begin, const double domain[3]);
+/* update_halo (comm_serial.cpp:99-110) as ONE kernel.  emd_comm_halo_resolve follows, once per ghost build, every ghost's
+ * chain of sources through the six pack lists (counts[p] ghosts per phase, stored behind n_local in phase order) down to
+ * its owned root atom and total periodic shift (d_root int[n_ghost], d_shift double[n_ghost][3]); emd_comm_halo_refresh
+ * then rewrites all ghost positions, x[ghost] = x[root] + shift: the same values as the six dependent phase copies
+ * (positions only: the other ghost fields do not change between ghost builds). */
+int emd_comm_halo_resolve(emd_ctx *ctx, const int *const d_pack_indicies[6], const int counts[6], int n_local,
+                          const double domain[3], int *d_root, double *d_shift);
+int emd_comm_halo_refresh(emd_ctx *ctx, double *d_x, int n_local, int n_ghost, const int *d_root, const double *d_shift);
 /* one phase of update_force (comm_serial.cpp:112-127, TagHaloForceSelf comm_serial.h:199-213) */
 int emd_comm_force_fold_phase(emd_ctx *ctx, double *d_f, const int *d_pack_indicies, int count,
                               int ghost_begin);
