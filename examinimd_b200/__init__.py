@@ -132,6 +132,8 @@ _SIGS = {
     "emd_net_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, _P]),
     "emd_net_destroy": (None, [_P]),
     "emd_net_sendrecv": (C.c_int, [_P, _P, C.c_ulonglong, C.c_int, _P, C.c_ulonglong, C.c_int]),
+    "emd_net_group_begin": (C.c_int, [_P]),
+    "emd_net_group_end": (C.c_int, [_P]),
     "emd_net_exchange_count": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "emd_net_allreduce": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "emd_net_scan_int": (C.c_int, [_P, C.POINTER(C.c_int)]),

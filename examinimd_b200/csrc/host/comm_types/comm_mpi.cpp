@@ -146,32 +146,41 @@ void CommMPI::exchange_halo() {
   system->N_ghost = N_ghost;
   // the per-step refresh ships 24 B per atom in either direction: make sure both buffers hold the largest phase
   size_t most = 0;
-  for (int p = 0; p < 6; p++) most = std::max(most, (size_t)std::max(proc_num_send[p], proc_num_recv[p]));
+  for (int d = 0; d < 3; d++)
+    most = std::max(most, (size_t)std::max(proc_num_send[2 * d] + proc_num_send[2 * d + 1], proc_num_recv[2 * d] + proc_num_recv[2 * d + 1]));
   ensure_bytes(pack_buffer, most * kParticleBytes);
   ensure_bytes(unpack_buffer, most * kParticleBytes);
 }
 
-// src/comm_types/comm_mpi.cpp:382-423: no host synchronisation anywhere in here
+// src/comm_types/comm_mpi.cpp:382-423: no host synchronisation anywhere in here.  The two phases of a dimension do not
+// depend on each other (phase 2d+1 never replays ghosts received in phase 2d, :306), so a decomposed dimension packs
+// both directions, ships them as ONE NCCL group and unpacks both: three exchanges per step instead of six.
 void CommMPI::update_halo() {
   emd_ctx *ctx = system->ctx;
   const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
+  T_INT ghost_begin[6];
   T_INT N_ghost = 0;
-  for (int phase = 0; phase < 6; phase++) {
-    const T_INT ghost_begin = system->N_local + N_ghost;
-    if (decomposed(phase)) {
-      if (emd_comm_halo_update_pack(ctx, phase, &dec, L, system->x, pack_indicies[phase].ptr, proc_num_send[phase], (double *)pack_buffer.ptr))
+  for (int phase = 0; phase < 6; phase++) { ghost_begin[phase] = system->N_local + N_ghost; N_ghost += proc_num_recv[phase]; }
+  for (int dim = 0; dim < 3; dim++) {
+    const int pa = 2 * dim, pb = 2 * dim + 1;
+    if (decomposed(pa)) {
+      double *send_a = (double *)pack_buffer.ptr, *send_b = send_a + 3 * (size_t)proc_num_send[pa];
+      // a refresh message is exactly the ghost rows of x (3 doubles per ghost, in ghost order): receive in place, no unpack
+      double *recv_a = system->x + 3 * (size_t)ghost_begin[pa], *recv_b = system->x + 3 * (size_t)ghost_begin[pb];
+      if (emd_comm_halo_update_pack(ctx, pa, &dec, L, system->x, pack_indicies[pa].ptr, proc_num_send[pa], send_a) ||
+          emd_comm_halo_update_pack(ctx, pb, &dec, L, system->x, pack_indicies[pb].ptr, proc_num_send[pb], send_b))
         fail("halo_update_pack");
-      if (emd_net_sendrecv(net, pack_buffer.ptr, (size_t)proc_num_send[phase] * 24, dec.neighbor_send[phase], unpack_buffer.ptr,
-                           (size_t)proc_num_recv[phase] * 24, dec.neighbor_recv[phase]))
+      if (emd_net_group_begin(net) ||
+          emd_net_sendrecv(net, send_a, (size_t)proc_num_send[pa] * 24, dec.neighbor_send[pa], recv_a, (size_t)proc_num_recv[pa] * 24, dec.neighbor_recv[pa]) ||
+          emd_net_sendrecv(net, send_b, (size_t)proc_num_send[pb] * 24, dec.neighbor_send[pb], recv_b, (size_t)proc_num_recv[pb] * 24, dec.neighbor_recv[pb]) ||
+          emd_net_group_end(net))
         fail("sendrecv");
-      if (emd_comm_halo_update_unpack(ctx, system->x, ghost_begin, proc_num_recv[phase], (const double *)unpack_buffer.ptr))
-        fail("halo_update_unpack");
     } else {
-      if (emd_comm_halo_update_phase(ctx, phase, system->x, system->v, system->q, system->id, system->type, pack_indicies[phase].ptr,
-                                     proc_num_send[phase], ghost_begin, L))
-        fail("halo_update_phase");
+      for (int phase = pa; phase <= pb; phase++)
+        if (emd_comm_halo_update_phase(ctx, phase, system->x, system->v, system->q, system->id, system->type, pack_indicies[phase].ptr,
+                                       proc_num_send[phase], ghost_begin[phase], L))
+          fail("halo_update_phase");
     }
-    N_ghost += proc_num_recv[phase];
   }
 }
 

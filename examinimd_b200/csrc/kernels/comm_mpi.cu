@@ -258,6 +258,7 @@ struct emd_net {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   int *d_small = nullptr; // 64 ints / 32 doubles of device staging for counts and scalar reductions
+  bool in_group = false;  // between emd_net_group_begin / _end: message pairs join one NCCL group
 };
 
 extern "C" {
@@ -430,9 +431,25 @@ int emd_net_sendrecv(emd_net *n, const void *d_send, unsigned long long send_byt
                      unsigned long long recv_bytes, int peer_recv) {
   if (!n) { set_error("emd_net_sendrecv: no transport"); return 1; }
   if (send_bytes == 0 && recv_bytes == 0) return 0;
-  EMD_NCCL(g_nccl.GroupStart());
+  if (!n->in_group) EMD_NCCL(g_nccl.GroupStart());
   if (recv_bytes) EMD_NCCL(g_nccl.Recv(d_recv, recv_bytes, ncclChar, peer_recv, n->comm, n->ctx->stream));
   if (send_bytes) EMD_NCCL(g_nccl.Send(d_send, send_bytes, ncclChar, peer_send, n->comm, n->ctx->stream));
+  if (!n->in_group) { EMD_NCCL(g_nccl.GroupEnd()); n->ctx->launches++; }
+  return 0;
+}
+
+// Several message pairs as ONE NCCL group = one fused send/recv kernel: the +d and -d phases of a dimension are
+// independent of each other (an odd phase never scans the ghosts of its even twin, comm_mpi.cpp:306), so the per-step
+// refresh needs three exchanges, not six.
+int emd_net_group_begin(emd_net *n) {
+  if (!n || n->in_group) { set_error("emd_net_group_begin: no transport or nested group"); return 1; }
+  EMD_NCCL(g_nccl.GroupStart());
+  n->in_group = true;
+  return 0;
+}
+int emd_net_group_end(emd_net *n) {
+  if (!n || !n->in_group) { set_error("emd_net_group_end: no open group"); return 1; }
+  n->in_group = false;
   EMD_NCCL(g_nccl.GroupEnd());
   n->ctx->launches++;
   return 0;

@@ -286,6 +286,9 @@ void emd_net_destroy(emd_net *n);
  * stream-ordered, no host synchronisation; either side may be 0 bytes */
 int emd_net_sendrecv(emd_net *n, const void *d_send, unsigned long long send_bytes, int peer_send, void *d_recv,
                      unsigned long long recv_bytes, int peer_recv);
+/* message pairs issued between begin and end travel as one NCCL group (one fused send/recv kernel on the stream) */
+int emd_net_group_begin(emd_net *n);
+int emd_net_group_end(emd_net *n);
 /* the count handshake of a phase (comm_mpi.cpp:235-238, 325-328); synchronises */
 int emd_net_exchange_count(emd_net *n, int send_count, int peer_send, int peer_recv, int *h_recv_count);
 /* MPI_Allreduce(IN_PLACE) / MPI_Scan on HOST scalars (comm_mpi.cpp:150-191): is_double 0 int / 1 double, op 0 sum / 1 max */
