@@ -31,6 +31,8 @@
 // (ghost forces are needed there) and for tiles that do not fit.
 #include "common.cuh"
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <cmath>
 #include <algorithm>
 
@@ -57,6 +59,12 @@ struct TileArgs {
   double wx, wy, wz; // bin widths
   unsigned short *ell; // [ntiles][maxrow/8][stride][8]: 8 entries of one atom = one 16-byte word
   int *nell;           // [ntiles][stride]
+  // the same adjacency re-ordered for the force kernel (tiles_schedule_kernel): every warp's rows are laid
+  // out in COLUMNS that a half-warp can read from shared memory without bank conflicts.  Entries with bit 15
+  // set are padding (the slot in the low bits is one another lane of the half-warp reads in that column).
+  unsigned short *ell_s; // [ntiles][maxrow_s/8][stride][8]
+  int *nell_s;           // [ntiles][stride]: columns of the thread's warp, multiple of 8
+  int maxrow_s;          // column capacity, multiple of 8
   // per-tile staging tables written once per build (tiles_tables_kernel), so that the per-step
   // force kernel needs no cell arithmetic: global index of every staged slot, and for every
   // dense atom slot its staged slot / global index
@@ -258,6 +266,320 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_tables_kernel(TileArgs a
   }
 }
 
+// ------------------------------------------------------- bank-conflict-free column schedule
+// The force kernel reads x[j] of 32 different neighbors per warp instruction from shared memory
+// (LDS.64, served per half-warp: 16 lanes x 8 bytes = one wavefront if the 16 words lie in 16
+// different bank pairs or are the same word).  In list order the 16 rows of a half-warp hit
+// ~2.5 words per bank pair (ncu: 57 % of the kernel's shared-memory wavefronts were conflicts
+// and the LSU pipe, not FP64, bounded it).  Rows are therefore re-ordered once per build:
+// column q of a half-warp holds, for every lane, an entry whose bank (slot mod 16: the AoS
+// stride 3 is odd, so x, y and z all map slot -> bank pair bijectively) is different from
+// every other lane's, or the SAME slot as another lane's (broadcast).  A lane with no such
+// entry left idles in that column (a flagged copy of a slot another lane reads).
+//
+// Greedy, lane after lane (lane 0 of the half-warp picks first): join a slot already taken in
+// this column if it is the head of one of my buckets (atoms of one cell share most neighbors),
+// else take, among my non-empty buckets whose bank is free, one that holds more than its share
+// of what I have left (the bottleneck banks drain first), searching from bank (q + lane) mod 16.
+// The lane-serial dependency is a systolic pipeline: at step t lane l works on column t - l and
+// reads the state its predecessors left for that column in a shared-memory ring, so a warp
+// schedules its two half-warps in (columns + 16) steps.  Measured on the 2 M-atom liquid
+// (tools/sim_lds_conflicts.py models the same algorithm): 1.93 wavefronts per LDS.64 instead of
+// 5.0, for 1 % more columns than the longest row of the warp.
+constexpr int kSchedWarps = 2;
+constexpr int kSchedMaxRow = 248;        // bucket positions and prefix sums are bytes
+constexpr unsigned kNoSlot = 0xffffu;    // head of an empty bucket
+constexpr unsigned kFreeBank = 0xfffeu;  // bank not taken in this column
+
+__device__ __forceinline__ unsigned nib_of_bytes(unsigned x) { // byte i non-zero (0xff) -> bit i
+  return ((x & 0x08040201u) * 0x01010101u) >> 24;
+}
+__device__ __forceinline__ unsigned half_eq_mask(const uint4 &h0, const uint4 &h1, const uint4 &t0, const uint4 &t1) {
+  // bit b set iff 16-bit element b of h equals element b of t
+  const unsigned e0 = __vcmpeq2(h0.x, t0.x), e1 = __vcmpeq2(h0.y, t0.y), e2 = __vcmpeq2(h0.z, t0.z), e3 = __vcmpeq2(h0.w, t0.w);
+  const unsigned e4 = __vcmpeq2(h1.x, t1.x), e5 = __vcmpeq2(h1.y, t1.y), e6 = __vcmpeq2(h1.z, t1.z), e7 = __vcmpeq2(h1.w, t1.w);
+  return nib_of_bytes(__byte_perm(e0, e1, 0x6420)) | (nib_of_bytes(__byte_perm(e2, e3, 0x6420)) << 4) |
+         (nib_of_bytes(__byte_perm(e4, e5, 0x6420)) << 8) | (nib_of_bytes(__byte_perm(e6, e7, 0x6420)) << 12);
+}
+__device__ __forceinline__ unsigned bytes_gt_mask(const uint4 &c, unsigned th) { // bit b set iff byte b of c > th
+  const unsigned t4 = th * 0x01010101u;
+  return nib_of_bytes(__vcmpgtu4(c.x, t4)) | (nib_of_bytes(__vcmpgtu4(c.y, t4)) << 4) | (nib_of_bytes(__vcmpgtu4(c.z, t4)) << 8) |
+         (nib_of_bytes(__vcmpgtu4(c.w, t4)) << 12);
+}
+
+size_t sched_warp_smem(int maxrow, int maxrow_s) {
+  return (size_t)32 * maxrow * 2 + (size_t)32 * maxrow_s * 2 + 32 * 16 * 2 /*hs*/ + 32 * 16 /*cnt*/ + 32 * 16 /*hp*/ + 2 * 32 * 16 * 2 /*ring*/ +
+         2 * 32 * 2 /*ring masks*/ + 128;
+}
+
+// MODE: SCHED_FULL = the conflict-free column schedule above; SCHED_ROT = every lane re-orders its own row so that at
+// column q it reads bank (q + lane) mod 16 whenever it still has an entry there (no negotiation between lanes: conflicts
+// remain where a bucket ran dry, 3.2 wavefronts per LDS.64 instead of 5.0 / 1.93, at a tenth of the scheduling cost);
+// SCHED_NONE = list order (rows longer than kSchedMaxRow), only the flagged padding.
+enum { SCHED_FULL = 0, SCHED_NONE = 1, SCHED_ROT = 2 };
+template <int MODE>
+__global__ void __launch_bounds__(32 * kSchedWarps) tiles_schedule_kernel(TileArgs a, int ntiles, unsigned warp_smem) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wrows = a.stride >> 5;
+  const long long gw = (long long)blockIdx.x * kSchedWarps + warp;
+  if (gw >= (long long)ntiles * wrows) return; // whole warps leave; no block-wide barrier below
+  const int tile = (int)(gw / wrows), ts = (int)(gw % wrows) * 32 + lane;
+  unsigned char *base = dyn + (size_t)warp * warp_smem;
+  unsigned short *out = reinterpret_cast<unsigned short *>(base);                 // [lane][maxrow_s]
+  unsigned short *srow = out + 32 * a.maxrow_s;                                    // [pos][lane], bank-sorted
+  unsigned short *hs = srow + 32 * a.maxrow;                                       // [lane][16] slot at the head of every bucket
+  unsigned short *ring = hs + 32 * 16;                                             // [half][32 columns][16] slot taken per bank
+  unsigned short *rmask = ring + 2 * 32 * 16;                                      // [half][32] taken banks
+  unsigned char *cnt = reinterpret_cast<unsigned char *>(rmask + 2 * 32);          // [lane][16]
+  unsigned char *hp = cnt + 32 * 16;                                               // [lane][16] position of the bucket head in srow
+
+  const int n = a.nell[(size_t)tile * a.stride + ts];
+  const unsigned own = a.int_slot[(size_t)tile * a.stride + ts];
+  const uint4 *row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)tile * (a.maxrow >> 3)) * a.stride + ts;
+  { // every column starts as padding
+    const unsigned pad2 = (0x8000u | own) * 0x00010001u;
+    uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)lane * a.maxrow_s);
+    for (int c = 0; c < (a.maxrow_s >> 3); c++) o[c] = make_uint4(pad2, pad2, pad2, pad2);
+  }
+  int last = 0;      // columns this lane really uses
+  bool ovf = false;
+  int need = 0;
+  if (MODE == SCHED_NONE) {
+    if (n > a.maxrow_s) { ovf = true; need = n; }
+    else {
+      for (int c = 0; c * 8 < n; c++) {
+        const uint4 w = row[(size_t)c * a.stride];
+        const unsigned e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (c * 8 + k < n) out[(size_t)lane * a.maxrow_s + c * 8 + k] = (unsigned short)((e[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+      }
+      last = n;
+    }
+  } else {
+    // ---- counting sort of the row by bank (stable: buckets stay in ascending slot order)
+    unsigned long long c_lo = 0, c_hi = 0; // bucket sizes, one byte per bank
+    for (int c = 0; c * 8 < n; c++) {
+      const uint4 w = row[(size_t)c * a.stride];
+      const unsigned e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (c * 8 + k < n) {
+          const unsigned b = (e[k >> 1] >> (16 * (k & 1))) & 15u;
+          if (b < 8) c_lo += 1ull << (8 * b); else c_hi += 1ull << (8 * (b - 8));
+        }
+    }
+    const unsigned long long M = 0x0101010101010101ull;
+    const unsigned long long inc_lo = c_lo * M; // byte k = c_lo[0] + ... + c_lo[k]  (n <= 248: no carries)
+    const unsigned long long tot_lo = inc_lo >> 56;
+    const unsigned long long inc_hi = c_hi * M + tot_lo * M;
+    const unsigned long long st_lo = inc_lo << 8, st_hi = (inc_hi << 8) | tot_lo; // first position of every bucket
+    unsigned long long p_lo = st_lo, p_hi = st_hi;
+    for (int c = 0; c * 8 < n; c++) {
+      const uint4 w = row[(size_t)c * a.stride];
+      const unsigned e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (c * 8 + k < n) {
+          const unsigned s = (e[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+          const unsigned b = s & 15u;
+          unsigned pos;
+          if (b < 8) { pos = (unsigned)(p_lo >> (8 * b)) & 0xffu; p_lo += 1ull << (8 * b); }
+          else { pos = (unsigned)(p_hi >> (8 * (b - 8))) & 0xffu; p_hi += 1ull << (8 * (b - 8)); }
+          srow[pos * 32 + lane] = (unsigned short)s;
+        }
+    }
+    unsigned N = 0; // non-empty buckets
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const unsigned cb = (unsigned)((b < 8 ? c_lo >> (8 * b) : c_hi >> (8 * (b - 8))) & 0xffu);
+      const unsigned sb = (unsigned)((b < 8 ? st_lo >> (8 * b) : st_hi >> (8 * (b - 8))) & 0xffu);
+      cnt[lane * 16 + b] = (unsigned char)cb;
+      hp[lane * 16 + b] = (unsigned char)sb;
+      hs[lane * 16 + b] = cb ? srow[sb * 32 + lane] : (unsigned short)kNoSlot;
+      if (cb) N |= 1u << b;
+    }
+    int rem = n;
+    const int half = lane >> 4, hl = lane & 15;
+    unsigned short *rg = ring + half * 32 * 16;
+    unsigned short *rm = rmask + half * 32;
+    unsigned big = 0;   // banks holding more than th entries
+    int th = -1;
+    __syncwarp();
+    for (int t = 0;; t++) {
+      if (!__any_sync(0xffffffffu, rem > 0)) break;
+      const int q = t - hl;
+      if (q >= 0) {
+        unsigned short *tq = rg + (q & 31) * 16;
+        if (hl == 0) { // first lane of the half-warp opens the column
+          const unsigned f2 = kFreeBank * 0x00010001u;
+          reinterpret_cast<uint4 *>(tq)[0] = make_uint4(f2, f2, f2, f2);
+          reinterpret_cast<uint4 *>(tq)[1] = make_uint4(f2, f2, f2, f2);
+          rm[q & 31] = 0;
+        }
+        if (rem > 0 && q >= a.maxrow_s) { ovf = true; need = q + rem; rem = 0; }
+        if (q < a.maxrow_s) {
+          const unsigned tm = rm[q & 31];
+          int b = -1;
+          bool join = false;
+          if (rem > 0) {
+            if (tm) {
+              const uint4 t0 = reinterpret_cast<const uint4 *>(tq)[0], t1 = reinterpret_cast<const uint4 *>(tq)[1];
+              const uint4 h0 = reinterpret_cast<const uint4 *>(hs + lane * 16)[0], h1 = reinterpret_cast<const uint4 *>(hs + lane * 16)[1];
+              const unsigned jm = half_eq_mask(h0, h1, t0, t1);
+              if (jm) { b = __ffs(jm) - 1; join = true; }
+            }
+            if (!join) {
+              const unsigned m = N & ~tm;
+              if (m) {
+                const int th_now = (rem + 15) >> 4;
+                if (th_now != th) { th = th_now; big = bytes_gt_mask(reinterpret_cast<const uint4 *>(cnt + lane * 16)[0], (unsigned)th); }
+                const unsigned mb = m & big;
+                const unsigned sel = mb ? mb : m;
+                const unsigned r = (unsigned)(q + hl) & 15u;
+                const unsigned rot = ((sel >> r) | (sel << (16 - r))) & 0xffffu;
+                b = (int)((__ffs(rot) - 1 + r) & 15u);
+              }
+            }
+          }
+          if (b >= 0) {
+            const unsigned s = hs[lane * 16 + b];
+            out[(size_t)lane * a.maxrow_s + q] = (unsigned short)s;
+            const unsigned c = (unsigned)cnt[lane * 16 + b] - 1u, p = (unsigned)hp[lane * 16 + b] + 1u;
+            cnt[lane * 16 + b] = (unsigned char)c;
+            hp[lane * 16 + b] = (unsigned char)p;
+            hs[lane * 16 + b] = c ? srow[p * 32 + lane] : (unsigned short)kNoSlot;
+            if (!c) N &= ~(1u << b);
+            if ((int)c <= th) big &= ~(1u << b);
+            rem--;
+            last = q + 1;
+            if (!join) { tq[b] = (unsigned short)s; rm[q & 31] = (unsigned short)(tm | (1u << b)); }
+          } else if (tm) {
+            // idle: read what another lane of the half-warp reads in this column (no extra wavefront)
+            out[(size_t)lane * a.maxrow_s + q] = (unsigned short)(0x8000u | tq[__ffs(tm) - 1]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  const int cols = __reduce_max_sync(0xffffffffu, last);
+  if (__any_sync(0xffffffffu, ovf)) {
+    if (ovf) { atomicOr(&a.flags[0], 8); atomicMax(&a.flags[1], need); }
+    return;
+  }
+  const int c8 = (cols + 7) & ~7;
+  __syncwarp();
+  uint4 *dst = reinterpret_cast<uint4 *>(a.ell_s) + ((size_t)tile * (a.maxrow_s >> 3)) * a.stride + ts;
+  const uint4 *o = reinterpret_cast<const uint4 *>(out + (size_t)lane * a.maxrow_s);
+  for (int c = 0; c < (c8 >> 3); c++) dst[(size_t)c * a.stride] = o[c];
+  a.nell_s[(size_t)tile * a.stride + ts] = c8;
+}
+
+// The default re-ordering (SCHED_ROT), lean version: no negotiation between lanes, so no per-column state.  Per lane: the
+// bank-sorted row ([pos][lane]) and one word per bucket ([bank][lane]: head position | entries left << 8) in shared memory,
+// both laid out so that a warp access never has a bank conflict; 8 columns are emitted as one coalesced 16-byte word.
+constexpr int kRotWarps = 4;
+size_t rot_warp_smem(int maxrow) { return (size_t)32 * maxrow * sizeof(unsigned short) + 16 * 32 * sizeof(unsigned); }
+
+__global__ void __launch_bounds__(32 * kRotWarps) tiles_rotate_kernel(TileArgs a, int ntiles, unsigned warp_smem) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wrows = a.stride >> 5;
+  const long long gw = (long long)blockIdx.x * kRotWarps + warp;
+  if (gw >= (long long)ntiles * wrows) return;
+  const int tile = (int)(gw / wrows), ts = (int)(gw % wrows) * 32 + lane;
+  unsigned *state = reinterpret_cast<unsigned *>(dyn + (size_t)warp * warp_smem) + lane;       // state[bank * 32]
+  unsigned short *srow = reinterpret_cast<unsigned short *>(dyn + (size_t)warp * warp_smem + 16 * 32 * sizeof(unsigned)) + lane; // srow[pos * 32]
+  const int n = a.nell[(size_t)tile * a.stride + ts];
+  const unsigned own = a.int_slot[(size_t)tile * a.stride + ts];
+  const uint4 *row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)tile * (a.maxrow >> 3)) * a.stride + ts;
+  const int nmax = __reduce_max_sync(0xffffffffu, n);
+  if (nmax > a.maxrow_s) {
+    if (lane == 0) { atomicOr(&a.flags[0], 8); atomicMax(&a.flags[1], nmax); }
+    return;
+  }
+  // counting sort by bank (stable): sizes -> starts -> scatter
+#pragma unroll
+  for (int b = 0; b < 16; b++) state[b * 32] = 0;
+  for (int c = 0; c * 8 < n; c++) {
+    const uint4 w = row[(size_t)c * a.stride];
+    const unsigned e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (c * 8 + k < n) state[((e[k >> 1] >> (16 * (k & 1))) & 15u) * 32] += 1;
+  }
+  unsigned N = 0;
+  {
+    unsigned run = 0;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const unsigned cb = state[b * 32];
+      state[b * 32] = run | (cb << 8);
+      if (cb) N |= 1u << b;
+      run += cb;
+    }
+  }
+  for (int c = 0; c * 8 < n; c++) {
+    const uint4 w = row[(size_t)c * a.stride];
+    const unsigned e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (c * 8 + k < n) {
+        const unsigned s = (e[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+        const unsigned st = state[(s & 15u) * 32];
+        srow[(st & 0xffu) * 32] = (unsigned short)s;
+        state[(s & 15u) * 32] = st + 1;
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < 16; b++) { // heads back to the bucket starts
+    const unsigned st = state[b * 32];
+    state[b * 32] = st - (st >> 8);
+  }
+  const int hl = lane & 15;
+  const unsigned pad = 0x8000u | own;
+  unsigned big = 0;
+  int th = -1;
+  const int c8 = (nmax + 7) & ~7;
+  uint4 *dst = reinterpret_cast<uint4 *>(a.ell_s) + ((size_t)tile * (a.maxrow_s >> 3)) * a.stride + ts;
+  for (int q0 = 0; q0 < c8; q0 += 8) {
+    unsigned wv[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int q = q0 + k;
+      unsigned s = pad;
+      if (q < n) {
+        const unsigned pref = (unsigned)(q + hl) & 15u;
+        unsigned b = pref;
+        if (!((N >> pref) & 1u)) { // my bucket for this column's bank ran dry: take from one that holds more than its share
+          const int th_now = (n - q + 15) >> 4;
+          if (th_now != th) {
+            th = th_now;
+            big = 0;
+#pragma unroll
+            for (int bb = 0; bb < 16; bb++) if ((int)(state[bb * 32] >> 8) > th) big |= 1u << bb;
+          }
+          const unsigned mb = N & big;
+          const unsigned sel = mb ? mb : N;
+          const unsigned rot = ((sel >> pref) | (sel << (16 - pref))) & 0xffffu;
+          b = (unsigned)(__ffs(rot) - 1 + pref) & 15u;
+        }
+        const unsigned st = state[b * 32];
+        s = srow[(st & 0xffu) * 32];
+        const unsigned left = (st >> 8) - 1u;
+        state[b * 32] = ((st + 1u) & 0xffu) | (left << 8);
+        if (!left) N &= ~(1u << b);
+        if ((int)left <= th) big &= ~(1u << b);
+      }
+      wv[k >> 1] |= s << (16 * (k & 1));
+    }
+    dst[(size_t)(q0 >> 3) * a.stride] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+  }
+  a.nell_s[(size_t)tile * a.stride + ts] = c8;
+}
+
 // ------------------------------------------------------------ exact lists from the ELL superset
 enum { EMIT_COUNT = 0, EMIT_CSR = 1, EMIT_2D = 2 };
 
@@ -293,22 +615,33 @@ __global__ void __launch_bounds__(512) tiles_emit_kernel(TileArgs a, EmitArgs e)
   const double x_i = sx[own], y_i = sy[own], z_i = sz[own];
   const size_t base = (MODE == EMIT_CSR) ? (size_t)e.row_map[i] : (size_t)i * e.maxneighs;
   int count = 0;
-  for (int q = 0; q < n; q++) {
-    const int s = a.ell[ell_index(a, t.tile, q, ts)];
-    const int j = sj[s];
-    const double x_j = sx[s], y_j = sy[s], z_j = sz[s];
-    if (HALF) { // neighbor_csr.h:290-291 (j != i by construction)
-      const bool skip = (j < a.n_local || e.newton) &&
-                        !((x_j > x_i) || ((x_j == x_i) && ((y_j > y_i) || ((y_j == y_i) && (z_j > z_i)))));
-      if (skip) continue;
+  // one 16-byte word = 8 entries of the row; the next word is requested before the current one is used
+  const uint4 *row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)t.tile * (a.maxrow >> 3)) * a.stride + ts;
+  const int nchunk = (n + 7) >> 3;
+  uint4 cur = nchunk > 0 ? row[0] : make_uint4(0, 0, 0, 0);
+  for (int c = 0; c < nchunk; c++) {
+    const uint4 nxt = (c + 1 < nchunk) ? row[(size_t)(c + 1) * a.stride] : make_uint4(0, 0, 0, 0);
+    const unsigned w4[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (c * 8 + k >= n) break;
+      const int s = (int)((w4[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+      const int j = sj[s];
+      const double x_j = sx[s], y_j = sy[s], z_j = sz[s];
+      if (HALF) { // neighbor_csr.h:290-291 (j != i by construction)
+        const bool skip = (j < a.n_local || e.newton) &&
+                          !((x_j > x_i) || ((x_j == x_i) && ((y_j > y_i) || ((y_j == y_i) && (z_j > z_i)))));
+        if (skip) continue;
+      }
+      const double dx = x_i - x_j, dy = y_i - y_j, dz = z_i - z_j;
+      const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      if (rsq <= e.cutsq) { // neighbor_csr.h:206,299
+        if (MODE == EMIT_CSR) e.entries[base + count] = j;
+        if (MODE == EMIT_2D && count < e.maxneighs) e.entries[base + count] = j; // neighbor_2d.h:207-208
+        count++;
+      }
     }
-    const double dx = x_i - x_j, dy = y_i - y_j, dz = z_i - z_j;
-    const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    if (rsq <= e.cutsq) { // neighbor_csr.h:206,299
-      if (MODE == EMIT_CSR) e.entries[base + count] = j;
-      if (MODE == EMIT_2D && count < e.maxneighs) e.entries[base + count] = j; // neighbor_2d.h:207-208
-      count++;
-    }
+    cur = nxt;
   }
   if (MODE == EMIT_COUNT) e.counts[i] = count;
   if (MODE == EMIT_2D) { e.counts[i] = count; atomicMax(e.max_count, count); }
@@ -321,32 +654,32 @@ struct LJTab {
   int ntypes;
 };
 
-// 1/a to <= 1 ulp: MUFU.RCP64H seed + two Newton steps (the library division adds range fix-ups
-// that rsq in (0, cutsq) never needs)
+// 1/a to <= 1 ulp: MUFU.RCP64H seed y0 (~2^-20) and one cubic step y0 (1 + e + e^2), e = 1 - a y0: three
+// DFMA (error e^3 ~ 2^-60) instead of the four of two Newton steps; the library division adds range
+// fix-ups that rsq in (0, cutsq) never needs
 __device__ __forceinline__ double fast_rcp(double a) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double e = fma(-a, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-a, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double e = fma(-a, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
 }
 
 // Four pairs (one ELL word) at a time, branch-free and written stage by stage so that the four
 // ~20-instruction FP64 dependency chains are interleaved by the scheduler.
 template <bool ONETYPE, bool ENERGY>
-__device__ __forceinline__ void lj_quad(const double *__restrict__ sp, const int *__restrict__ st, const ushort4 w, int left,
+__device__ __forceinline__ void lj_quad(const double *__restrict__ sp, const int *__restrict__ st, const unsigned w01, const unsigned w23,
                                         double x_i, double y_i, double z_i, int type_i, const LJOne &one, const LJTab *__restrict__ tab,
                                         double &fx, double &fy, double &fz, double &pe) {
-  const int sl[4] = {w.x, w.y, w.z, w.w};
+  const unsigned raw[4] = {w01 & 0xffffu, w01 >> 16, w23 & 0xffffu, w23 >> 16};
   double dx[4], dy[4], dz[4], rsq[4], lj1[4], lj2[4], cutsq[4];
 #pragma unroll
   for (int u = 0; u < 4; u++) {
-    const double *p = sp + 3 * sl[u];
+    const unsigned sl = raw[u] & 0x7fffu;
+    const double *p = sp + 3 * sl;
     dx[u] = x_i - p[0]; dy[u] = y_i - p[1]; dz[u] = z_i - p[2];
     if (ONETYPE) { lj1[u] = one.lj1; lj2[u] = one.lj2; cutsq[u] = one.cutsq; }
-    else { const int tij = type_i * tab->ntypes + st[sl[u]]; lj1[u] = tab->lj1[tij]; lj2[u] = tab->lj2[tij]; cutsq[u] = tab->cutsq[tij]; }
+    else { const int tij = type_i * tab->ntypes + st[sl]; lj1[u] = tab->lj1[tij]; lj2[u] = tab->lj2[tij]; cutsq[u] = tab->cutsq[tij]; }
   }
 #pragma unroll
   for (int u = 0; u < 4; u++) rsq[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
@@ -354,8 +687,10 @@ __device__ __forceinline__ void lj_quad(const double *__restrict__ sp, const int
   double r2inv[4];
 #pragma unroll
   for (int u = 0; u < 4; u++) {
-    in[u] = (u < left) && rsq[u] < cutsq[u]; // force_lj_neigh_impl.h:189 (strict)
-    r2inv[u] = fast_rcp(rsq[u]); // padded entries (rsq = 0) give inf/NaN below, discarded by the select on in[u]
+    // force_lj_neigh_impl.h:189 (strict).  rsq and cutsq are non-negative, so the IEEE order is the order of the bit
+    // patterns: the test runs on the integer pipe and leaves the FP64 pipe to the arithmetic.  Bit 15 marks padding.
+    in[u] = !(raw[u] & 0x8000u) && __double_as_longlong(rsq[u]) < __double_as_longlong(cutsq[u]);
+    r2inv[u] = fast_rcp(rsq[u]); // a padding entry that is the atom itself (rsq = 0) gives inf/NaN below, discarded by the select
   }
 #pragma unroll
   for (int u = 0; u < 4; u++) {
@@ -377,6 +712,16 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+// The ELL words of a row are read once per step, one 16-byte word per 8 pairs.  The register budget (80 at two 384-thread
+// CTAs per SM) makes the compiler place the load of word c+1 at the END of iteration c, next to its first use (as a plain
+// load AND as volatile asm), and 26 % of the kernel's stall samples were warps waiting for it (profiles/, round 1).  A
+// prefetch holds no register: word c+2 is requested into L1 at the top of iteration c, so the late load hits L1.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -432,7 +777,7 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
   if (tile < ntiles) {
     i_cur = a.int_glob[(size_t)tile * a.stride + ts];
     own_cur = a.int_slot[(size_t)tile * a.stride + ts];
-    n_cur = a.nell[(size_t)tile * a.stride + ts];
+    n_cur = a.nell_s[(size_t)tile * a.stride + ts];
   }
   double pe = 0.0;
   int buf = 0;
@@ -445,7 +790,7 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
     if (tile + G < ntiles) {
       i_nxt = a.int_glob[(size_t)(tile + G) * a.stride + ts];
       own_nxt = a.int_slot[(size_t)(tile + G) * a.stride + ts];
-      n_nxt = a.nell[(size_t)(tile + G) * a.stride + ts];
+      n_nxt = a.nell_s[(size_t)(tile + G) * a.stride + ts];
     }
     const double *sp = sp0 + (size_t)buf * 3 * a.cap;
     const int *st = st0 + (size_t)buf * a.cap;
@@ -453,17 +798,19 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
       const double x_i = sp[3 * own_cur], y_i = sp[3 * own_cur + 1], z_i = sp[3 * own_cur + 2];
       const int type_i = ONETYPE ? 0 : st[own_cur];
       double fx = 0.0, fy = 0.0, fz = 0.0;
-      // one 16-byte word = 8 neighbors; the next word is requested before the current one is used
-      const uint4 *row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)tile * (a.maxrow >> 3)) * a.stride + ts;
-      const int nchunk = (n_cur + 7) >> 3;
-      uint4 cur = nchunk > 0 ? row[0] : make_uint4(0, 0, 0, 0);
+      // one 16-byte word = 8 columns of the warp's schedule (n_cur is the same multiple of 8 in every lane of the warp);
+      // the next word is requested before the current one is used
+      const uint4 *row = reinterpret_cast<const uint4 *>(a.ell_s) + ((size_t)tile * (a.maxrow_s >> 3)) * a.stride + ts;
+      const int nchunk = n_cur >> 3;
+      uint4 cur = make_uint4(0, 0, 0, 0);
+      if (nchunk > 0) cur = ldg_nc_v4(row);
+      if (nchunk > 1) prefetch_l1(row + a.stride);
       for (int c = 0; c < nchunk; c++) {
-        const uint4 nxt = (c + 1 < nchunk) ? row[(size_t)(c + 1) * a.stride] : make_uint4(0, 0, 0, 0);
-        const int left = n_cur - 8 * c; // the filter pads the last word with in-bounds slots
-        const ushort4 lo = make_ushort4(cur.x & 0xffff, cur.x >> 16, cur.y & 0xffff, cur.y >> 16);
-        const ushort4 hi = make_ushort4(cur.z & 0xffff, cur.z >> 16, cur.w & 0xffff, cur.w >> 16);
-        lj_quad<ONETYPE, ENERGY>(sp, st, lo, left, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
-        lj_quad<ONETYPE, ENERGY>(sp, st, hi, left - 4, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+        if (c + 2 < nchunk) prefetch_l1(row + (size_t)(c + 2) * a.stride);
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (c + 1 < nchunk) nxt = ldg_nc_v4(row + (size_t)(c + 1) * a.stride);
+        lj_quad<ONETYPE, ENERGY>(sp, st, cur.x, cur.y, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+        lj_quad<ONETYPE, ENERGY>(sp, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
         cur = nxt;
       }
       if (!ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
@@ -497,6 +844,8 @@ struct emd_tiles {
   bool valid = false;
   unsigned short *d_ell = nullptr; size_t ell_cap = 0;
   int *d_nell = nullptr; size_t nell_cap = 0;
+  unsigned short *d_ell_s = nullptr; size_t ell_s_cap = 0;
+  int *d_nell_s = nullptr; size_t nell_s_cap = 0;
   int *d_stg_j = nullptr; size_t stg_j_cap = 0;
   int *d_stg_n = nullptr; size_t stg_n_cap = 0;
   unsigned short *d_int_slot = nullptr; size_t int_slot_cap = 0;
@@ -550,6 +899,8 @@ void emd_tiles_destroy(emd_tiles *t) {
   if (!t) return;
   if (t->d_ell) cudaFree(t->d_ell);
   if (t->d_nell) cudaFree(t->d_nell);
+  if (t->d_ell_s) cudaFree(t->d_ell_s);
+  if (t->d_nell_s) cudaFree(t->d_nell_s);
   if (t->d_stg_j) cudaFree(t->d_stg_j);
   if (t->d_stg_n) cudaFree(t->d_stg_n);
   if (t->d_int_slot) cudaFree(t->d_int_slot);
@@ -569,6 +920,18 @@ int emd_tiles_info(const emd_tiles *t, int *tile_dims, int *ntiles, int *stride,
   if (stride) *stride = t->a.stride;
   if (maxrow) *maxrow = t->a.maxrow;
   if (cap) *cap = t->a.cap;
+  return 0;
+}
+
+int emd_tiles_lists(const emd_tiles *t, const unsigned short **d_ell, const int **d_nell, int *maxrow_s, const unsigned short **d_ell_s,
+                    const int **d_nell_s, const unsigned short **d_int_slot) {
+  if (!t || !t->valid) { set_error("emd_tiles_lists: tiles not built"); return 1; }
+  if (d_ell) *d_ell = t->a.ell;
+  if (d_nell) *d_nell = t->a.nell;
+  if (maxrow_s) *maxrow_s = t->a.maxrow_s;
+  if (d_ell_s) *d_ell_s = t->a.ell_s;
+  if (d_nell_s) *d_nell_s = t->a.nell_s;
+  if (d_int_slot) *d_int_slot = t->a.int_slot;
   return 0;
 }
 
@@ -646,8 +1009,41 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
       if (ensure_bytes((void **)&t->d_int_glob, &t->int_glob_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
       a.stg_j = t->d_stg_j; a.stg_n = t->d_stg_n; a.int_slot = t->d_int_slot; a.int_glob = t->d_int_glob;
       EMD_LAUNCH(ctx, tiles_tables_kernel, t->ntiles, kFilterThreads, 0, a);
-      t->valid = true;
-      return 0;
+      // the force kernel's copy of the adjacency: bank-conflict-free columns (tiles_schedule_kernel)
+      if (ensure_bytes((void **)&t->d_nell_s, &t->nell_s_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
+      a.nell_s = t->d_nell_s;
+      // EMD_TILES_SCHED = full | rot | none (measurement switch; default below)
+      int mode = SCHED_ROT;
+      if (const char *e = getenv("EMD_TILES_SCHED")) mode = !strcmp(e, "full") ? SCHED_FULL : !strcmp(e, "none") ? SCHED_NONE : SCHED_ROT;
+      if (a.maxrow > kSchedMaxRow) mode = SCHED_NONE;
+      int maxrow_s = a.maxrow + 8;
+      const long long warps = (long long)t->ntiles * (a.stride / 32);
+      const int sgrid = (int)((warps + kSchedWarps - 1) / kSchedWarps);
+      for (int sa = 0; sa < 4; sa++) {
+        a.maxrow_s = maxrow_s;
+        if (ensure_bytes((void **)&t->d_ell_s, &t->ell_s_cap, (size_t)t->ntiles * a.maxrow_s * a.stride * sizeof(unsigned short))) return 1;
+        a.ell_s = t->d_ell_s;
+        const size_t wsm = sched_warp_smem(a.maxrow, a.maxrow_s), ssm = wsm * kSchedWarps;
+        if (ssm > (size_t)t->max_smem_optin) return 3;
+        EMD_CUDA(cudaMemsetAsync(t->d_flags, 0, 4 * sizeof(int), ctx->stream));
+#define EMD_SCHED(M)                                                                                                        \
+  do {                                                                                                                     \
+    if (set_smem(tiles_schedule_kernel<M>, ssm)) return 1;                                                                 \
+    EMD_LAUNCH(ctx, tiles_schedule_kernel<M>, sgrid, 32 * kSchedWarps, ssm, a, t->ntiles, (unsigned)wsm);                  \
+  } while (0)
+        if (mode == SCHED_ROT) {
+          const size_t rwsm = rot_warp_smem(a.maxrow), rsm = rwsm * kRotWarps;
+          if (set_smem(tiles_rotate_kernel, rsm)) return 1;
+          EMD_LAUNCH(ctx, tiles_rotate_kernel, (int)((warps + kRotWarps - 1) / kRotWarps), 32 * kRotWarps, rsm, a, t->ntiles, (unsigned)rwsm);
+        } else if (mode == SCHED_FULL) EMD_SCHED(SCHED_FULL);
+        else EMD_SCHED(SCHED_NONE);
+#undef EMD_SCHED
+        EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        EMD_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (!(ctx->h_pinned[0] & 8)) { t->valid = true; return 0; }
+        maxrow_s = (ctx->h_pinned[1] + ctx->h_pinned[1] / 8 + 15) / 8 * 8;
+      }
+      return 3;
     }
     if (bits & 2) { (void)need_int; return 3; } // a tile holds more atoms than threads: density far from the estimate
     if (bits & 1) {

@@ -148,6 +148,13 @@ void emd_tiles_destroy(emd_tiles *t);
 int emd_tiles_valid(const emd_tiles *t);
 void emd_tiles_invalidate(emd_tiles *t);
 int emd_tiles_info(const emd_tiles *t, int *tile_dims3, int *ntiles, int *stride, int *maxrow, int *cap);
+/* Device pointers of the two copies of the tile adjacency (inspection / tests): the list-order rows the
+ * CSR/2D lists are emitted from (ell: [ntiles][maxrow/8][stride][8] uint16 staged-slot numbers, nell:
+ * [ntiles][stride] row lengths) and the force kernel's copy, re-ordered into shared-memory
+ * bank-conflict-free columns (ell_s, nell_s, capacity maxrow_s; bit 15 of an entry marks padding);
+ * int_slot: [ntiles][stride] staged slot of the row's own atom.  Any pointer argument may be NULL. */
+int emd_tiles_lists(const emd_tiles *t, const unsigned short **d_ell, const int **d_nell, int *maxrow_s,
+                    const unsigned short **d_ell_s, const int **d_nell_s, const unsigned short **d_int_slot);
 int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_local, int n_all,
                           const emd_bin_geom *geom, const int *d_bincount, const int *d_binoffsets,
                           const int *d_permute, double neigh_cut);

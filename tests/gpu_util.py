@@ -104,6 +104,27 @@ class Tiles:
         emd.check(emd.lib().emd_tiles_info(self.h, d, C.byref(nt), C.byref(st), C.byref(mr), C.byref(cap)))
         return {"dims": tuple(d), "ntiles": nt.value, "stride": st.value, "maxrow": mr.value, "cap": cap.value}
 
+    def lists(self):
+        """host copies of both adjacency layouts as [ntiles][words][stride][8] uint16 arrays (+ row lengths, own slots)"""
+        inf = self.info()
+        ell, nell, ell_s, nell_s, islot = P(), P(), P(), P(), P()
+        mrs = C.c_int()
+        emd.check(emd.lib().emd_tiles_lists(self.h, C.byref(ell), C.byref(nell), C.byref(mrs), C.byref(ell_s), C.byref(nell_s), C.byref(islot)))
+        nt, st = inf["ntiles"], inf["stride"]
+
+        def grab(p, count, dtype):
+            h = np.empty(count, dtype=dtype)
+            emd.check(emd.lib().emd_memcpy_d2h(self.ctx.handle, h.ctypes.data_as(P), p, h.nbytes), "emd_memcpy_d2h")
+            return h
+
+        out = {"maxrow": inf["maxrow"], "maxrow_s": mrs.value, "stride": st, "ntiles": nt}
+        out["ell"] = grab(ell, nt * inf["maxrow"] * st, np.uint16).reshape(nt, inf["maxrow"] // 8, st, 8)
+        out["nell"] = grab(nell, nt * st, np.int32).reshape(nt, st)
+        out["ell_s"] = grab(ell_s, nt * mrs.value * st, np.uint16).reshape(nt, mrs.value // 8, st, 8)
+        out["nell_s"] = grab(nell_s, nt * st, np.int32).reshape(nt, st)
+        out["int_slot"] = grab(islot, nt * st, np.uint16).reshape(nt, st)
+        return out
+
     def csr(self, half, newton):
         L = emd.lib()
         rm = torch.empty(self.n_local + 1, dtype=torch.int32, device="cuda")

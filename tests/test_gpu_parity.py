@@ -254,6 +254,50 @@ def test_tiles_lj_force_and_energy(emd, gu, ctx, iteration):
     t.close(); md.close()
 
 
+@pytest.mark.parametrize("mode", ["full", "rot", "none"])
+@pytest.mark.parametrize("state", ["lattice", "liquid"])
+def test_tiles_schedule_is_a_conflict_free_permutation(emd, gu, ctx, state, mode, monkeypatch):
+    """the force kernel's copy of the tile adjacency (tiles_schedule_kernel) holds, row by row, exactly the entries of the
+    list-order copy; within a column no two lanes of a half-warp read different slots of the same shared-memory bank;
+    and the padding costs only a few per cent of columns"""
+    monkeypatch.setenv("EMD_TILES_SCHED", mode)  # read by emd_neigh_tiles_build
+    md = OracleMD.from_deck(DECK, "CSR", "NEIGH_FULL", region=(10, 10, 10)) if state == "lattice" else rebuilt(liquid(iteration="NEIGH_FULL"))
+    t, _ = _tiles_for(gu, ctx, md)
+    assert t.ok, t.info()
+    L = t.lists()
+    nt, st = L["ntiles"], L["stride"]
+    rows = L["ell"].transpose(0, 2, 1, 3).reshape(nt, st, -1)        # [tile][thread][q]
+    rows_s = L["ell_s"].transpose(0, 2, 1, 3).reshape(nt, st, -1)
+    cols_total, longest_total, conflicts, pad_conflicts, pairs = 0, 0, 0, 0, 0
+    for tile in range(nt):
+        for w0 in range(0, st, 32):
+            n = L["nell"][tile, w0:w0 + 32]
+            c8 = L["nell_s"][tile, w0:w0 + 32]
+            assert (c8 == c8[0]).all() and c8[0] % 8 == 0 and c8[0] <= L["maxrow_s"]
+            assert c8[0] >= n.max() and (n.max() == 0) == (c8[0] == 0)
+            blk = rows_s[tile, w0:w0 + 32, : c8[0]].astype(np.int64)
+            for l in range(32):
+                real = blk[l][blk[l] < 0x8000]
+                np.testing.assert_array_equal(np.sort(real), np.sort(rows[tile, w0 + l, : n[l]].astype(np.int64)))
+            for h in (slice(0, 16), slice(16, 32)):
+                for q in range(c8[0]):
+                    col = blk[h, q]
+                    u = np.unique(col[col < 0x8000])            # slots whose pairs are evaluated
+                    conflicts += u.size - np.unique(u % 16).size
+                    u = np.unique(col & 0x7fff)                  # with the padding lanes' reads
+                    pad_conflicts += u.size - np.unique(u % 16).size
+            cols_total += int(c8[0]); longest_total += int(n.max()); pairs += int(n.sum())
+    assert pairs > 0
+    print(f"schedule {mode}/{state}: {conflicts / (2 * cols_total):.3f} extra wavefronts per half-warp column, "
+          f"{pad_conflicts / (2 * cols_total):.3f} with padding reads, {cols_total / max(longest_total, 1):.3f} x longest-row columns")
+    if mode == "full":
+        assert conflicts == 0, conflicts
+        assert cols_total <= 1.12 * longest_total + 8 * nt * (st // 32), (cols_total, longest_total)
+    else:
+        assert cols_total <= longest_total + 8 * nt * (st // 32)
+    t.close(); md.close()
+
+
 def test_tiles_two_types_and_ragged(emd, gu, ctx):
     import torch
     rng = np.random.default_rng(3)
