@@ -251,6 +251,12 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # stdout carries exactly one JSON line: everything native code prints on fd 1 while the job runs (the C++ layer's
+    # banner lines, NCCL's version line at communicator creation) goes to stderr; the line is written to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import examinimd_b200 as emd
@@ -431,7 +437,8 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(20)
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if dist:
         dist.destroy_process_group()
 

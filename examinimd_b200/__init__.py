@@ -104,6 +104,12 @@ _SIGS = {
     "emd_neigh_tiles_fill_csr": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "emd_neigh_tiles_fill_2d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "emd_force_lj_compute_tiles": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
+    "emd_force_lj_compute_tiles_part": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "emd_tiles_halo_split": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "emd_ctx_side_mark": (C.c_int, [_P]),
+    "emd_ctx_side_begin": (C.c_int, [_P]),
+    "emd_ctx_side_end": (C.c_int, [_P]),
+    "emd_ctx_side_join": (C.c_int, [_P]),
     "emd_snap_create": (C.c_int, [C.POINTER(_P), C.POINTER(SnapParams)]),
     "emd_snap_destroy": (None, [_P]),
     "emd_snap_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),

@@ -153,6 +153,9 @@ void ExaMiniMD::thermo(T_FLOAT *T, T_FLOAT *PE, T_FLOAT *KE) {
 
 void ExaMiniMD::step_once(int step, PhaseTimers *tm) {
   const T_F_FLOAT neigh_cutoff = input->force_cutoff + input->neighbor_skin;
+  static const bool overlap_halo = !(getenv("EMD_NO_OVERLAP") && atoi(getenv("EMD_NO_OVERLAP")));
+  static const bool comm_first = !(getenv("EMD_OVERLAP_ORDER") && atoi(getenv("EMD_OVERLAP_ORDER")) == 0);
+  bool split = false;
   if (tm) tm->begin();
   integrator->initial_integrate();
   if (tm) tm->end(PhaseTimers::OTHER);
@@ -168,13 +171,33 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm) {
     if (neighbor) neighbor->create_neigh_list(system, binning, force->half_neigh, false);
     if (tm) tm->end(PhaseTimers::NEIGH);
   } else {
+    // decomposed run: the share of the force that reads no ghost atom starts now, on the side stream, and overlaps the
+    // halo exchange (the reference's blocking sequence update_halo -> compute, examinimd.cpp:226-235, otherwise)
+    split = overlap_halo && comm->num_processes() > 1 && force->can_split(system, neighbor);
+    // the exchange's kernels are enqueued first (they find the SMs free); the side stream forks from the point before them
+    if (split && emd_ctx_side_mark(system->ctx)) comm->error(emd_last_error());
+    if (split && !comm_first) {
+      if (emd_ctx_side_begin(system->ctx)) comm->error(emd_last_error());
+      force->compute_part(system, binning, neighbor, 1);
+      if (emd_ctx_side_end(system->ctx)) comm->error(emd_last_error());
+    }
     comm->update_halo();
+    if (split && comm_first) {
+      if (emd_ctx_side_begin(system->ctx)) comm->error(emd_last_error());
+      force->compute_part(system, binning, neighbor, 1);
+      if (emd_ctx_side_end(system->ctx)) comm->error(emd_last_error());
+    }
     if (tm) tm->end(PhaseTimers::COMM);
   }
 
-  if (!force->zeroes_forces())
-    emd_memset_zero(system->ctx, system->f, sizeof(T_F_FLOAT) * 3 * (size_t)system->N_max);
-  force->compute(system, binning, neighbor);
+  if (split) {
+    force->compute_part(system, binning, neighbor, 2);
+    if (emd_ctx_side_join(system->ctx)) comm->error(emd_last_error());
+  } else {
+    if (!force->zeroes_forces())
+      emd_memset_zero(system->ctx, system->f, sizeof(T_F_FLOAT) * 3 * (size_t)system->N_max);
+    force->compute(system, binning, neighbor);
+  }
   if (tm) tm->end(PhaseTimers::FORCE);
 
   if (input->comm_newton) {

@@ -16,6 +16,11 @@ public:
   // true when compute() zeroes/overwrites f itself, so the driver may skip deep_copy(f,0)
   // (src/examinimd.cpp:232); a foreign Force plugin simply inherits `false`
   virtual bool zeroes_forces() const { return false; }
+  // Optional split of compute() for decomposed runs (not in the reference): part 1 = the share that reads no ghost atom
+  // (the driver runs it on the context's side stream while Comm::update_halo is in flight), part 2 = the rest; the two
+  // parts together equal compute().  A module that cannot split inherits `false` and the driver calls compute().
+  virtual bool can_split(System *system, Neighbor *neigh) { return false; }
+  virtual void compute_part(System *system, Binning *binning, Neighbor *neigh, int part) {}
   virtual const char *name() { return "ForceNone"; }
 };
 

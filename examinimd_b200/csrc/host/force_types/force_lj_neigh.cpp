@@ -49,6 +49,21 @@ void ForceLJNeigh::compute(System *system, Binning *, Neighbor *neighbor) {
     fail("compute");
 }
 
+// compute() in two launches for a decomposed run (force.h): the tile lists know which tiles read ghost atoms
+bool ForceLJNeigh::can_split(System *, Neighbor *neighbor) {
+  emd_tiles *t = neighbor->tiles();
+  int n_free = 0, n_halo = 0;
+  if (!t || comm_newton || emd_tiles_halo_split(t, &n_free, &n_halo)) return false;
+  return n_free > 0 && n_halo > 0;
+}
+
+void ForceLJNeigh::compute_part(System *system, Binning *, Neighbor *neighbor, int part) {
+  static const int reserve = getenv("EMD_OVERLAP_RESERVE") ? atoi(getenv("EMD_OVERLAP_RESERVE")) : 16;
+  // part 1 shares the SMs with the halo exchange's pack and transport kernels: leave them CTA slots
+  if (emd_force_lj_compute_tiles_part(system->ctx, neighbor->tiles(), system->x, system->type, system->f, part, part == 1 ? reserve : 0))
+    fail("compute_part (tiles)");
+}
+
 // src/force_types/force_lj_neigh_impl.h:128-156
 T_F_FLOAT ForceLJNeigh::compute_energy(System *system, Binning *, Neighbor *neighbor) {
   double pe = 0.0;

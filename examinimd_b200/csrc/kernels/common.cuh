@@ -53,6 +53,9 @@ struct emd_ctx {
   bool own_stream = false;
   unsigned long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t side_stream = nullptr, main_stream = nullptr; // emd_ctx_side_*: main_stream != nullptr while the side stream is current
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool fork_marked = false;
   int num_sms = 148;
   // scratch
   emd::Scratch s_a, s_b, s_c, s_scan; // general-purpose device scratch

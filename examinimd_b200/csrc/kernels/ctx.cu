@@ -146,6 +146,9 @@ void emd_ctx_destroy(emd_ctx *c) {
   c->s_a.release(); c->s_b.release(); c->s_c.release(); c->s_scan.release();
   if (c->d_lj_tables) cudaFree(c->d_lj_tables);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -155,6 +158,44 @@ void emd_ctx_destroy(emd_ctx *c) {
 void *emd_ctx_stream(emd_ctx *c) { return (void *)c->stream; }
 int emd_ctx_sync(emd_ctx *c) { EMD_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
 unsigned long long emd_ctx_launch_count(emd_ctx *c) { return c->launches; }
+static int side_init(emd_ctx *c) {
+  if (c->side_stream) return 0;
+  int lo = 0, hi = 0;
+  EMD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi)); // lo = least priority: the exchange on the module stream goes first
+  EMD_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
+  EMD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  EMD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  return 0;
+}
+int emd_ctx_side_mark(emd_ctx *c) {
+  if (c->main_stream) { set_error("emd_ctx_side_mark: already on the side stream"); return 1; }
+  if (side_init(c)) return 1;
+  EMD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  c->fork_marked = true;
+  return 0;
+}
+int emd_ctx_side_begin(emd_ctx *c) {
+  if (c->main_stream) { set_error("emd_ctx_side_begin: already on the side stream"); return 1; }
+  if (side_init(c)) return 1;
+  if (!c->fork_marked) EMD_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  c->fork_marked = false;
+  EMD_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+  c->main_stream = c->stream;
+  c->stream = c->side_stream;
+  return 0;
+}
+int emd_ctx_side_end(emd_ctx *c) {
+  if (!c->main_stream) { set_error("emd_ctx_side_end: not on the side stream"); return 1; }
+  EMD_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
+  c->stream = c->main_stream;
+  c->main_stream = nullptr;
+  return 0;
+}
+int emd_ctx_side_join(emd_ctx *c) {
+  if (c->main_stream || !c->side_stream) { set_error("emd_ctx_side_join: no side work"); return 1; }
+  EMD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  return 0;
+}
 int emd_ctx_tic(emd_ctx *c) { EMD_CUDA(cudaEventRecord(c->ev0, c->stream)); return 0; }
 int emd_ctx_toc(emd_ctx *c, float *h_ms) {
   EMD_CUDA(cudaEventRecord(c->ev1, c->stream));

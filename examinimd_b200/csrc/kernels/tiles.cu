@@ -72,6 +72,10 @@ struct TileArgs {
   int *stg_n;                // [ntiles]  staged atoms
   unsigned short *int_slot;  // [ntiles][stride]
   int *int_glob;             // [ntiles][stride]  (>= n_local or 0x7fffffff: no row)
+  // tiles whose staged cells hold only owned atoms come first in `order` (their forces do not depend on the halo, so a
+  // decomposed run computes them while the halo exchange is in flight); has_ghost[tile] is the classification
+  int *order;          // [ntiles] tile numbers, halo-independent tiles first (stable)
+  int *has_ghost;      // [ntiles]
   int *flags;          // [0] overflow bits (1 staged, 2 interior, 4 row)  [1] max row  [2] max staged  [3] max interior
 };
 
@@ -247,10 +251,17 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_tables_kernel(TileArgs a
   if (t.total > a.cap || t.n_int > a.stride) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   if (threadIdx.x == 0) a.stg_n[t.tile] = t.total;
+  int ghost = 0;
   for (int c = warp; c < t.ncs; c += nwarps) {
     const int base = s_start[c], n = s_start[c + 1] - base, goff = s_goff[c];
-    for (int k = lane; k < n; k += 32) a.stg_j[(size_t)t.tile * a.cap + base + k] = a.permute[goff + k];
+    for (int k = lane; k < n; k += 32) {
+      const int j = a.permute[goff + k];
+      a.stg_j[(size_t)t.tile * a.cap + base + k] = j;
+      ghost |= (j >= a.n_local);
+    }
   }
+  ghost = __syncthreads_or(ghost);
+  if (threadIdx.x == 0) a.has_ghost[t.tile] = ghost ? 1 : 0;
   for (int k = t.n_int + threadIdx.x; k < a.stride; k += blockDim.x) {
     a.int_slot[(size_t)t.tile * a.stride + k] = 0;
     a.int_glob[(size_t)t.tile * a.stride + k] = 0x7fffffff;
@@ -264,6 +275,31 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_tables_kernel(TileArgs a
       a.int_glob[(size_t)t.tile * a.stride + s_ibase[ci] + k] = a.permute[s_goff[c] + k];
     }
   }
+}
+
+// order[]: halo-independent tiles first, then the others, each group in tile order.  One block: every thread owns a
+// contiguous chunk of tiles; flags[2] receives the number of halo-independent tiles.
+__global__ void __launch_bounds__(1024) tiles_order_kernel(TileArgs a, int ntiles) {
+  __shared__ int s_cnt[1024];
+  const int chunk = (ntiles + 1023) / 1024;
+  const int b = min(ntiles, (int)threadIdx.x * chunk), e = min(ntiles, b + chunk);
+  int mine = 0;
+  for (int k = b; k < e; k++) mine += a.has_ghost[k] ? 0 : 1;
+  s_cnt[threadIdx.x] = mine;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) { // inclusive scan
+    const int v = threadIdx.x >= o ? s_cnt[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_cnt[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const int total_free = s_cnt[1023];
+  int free_before = s_cnt[threadIdx.x] - mine;
+  for (int k = b; k < e; k++) {
+    if (a.has_ghost[k]) a.order[total_free + (k - free_before)] = k;
+    else a.order[free_before++] = k;
+  }
+  if (threadIdx.x == 0) a.flags[2] = total_free;
 }
 
 // ------------------------------------------------------- bank-conflict-free column schedule
@@ -732,8 +768,9 @@ constexpr int kStagePerThread = 8; // cap <= kForceThreads * kStagePerThread
 // tile n+1 are copied global->shared with cp.async (LDGSTS) into the second buffer while tile n
 // is computed, and the staging indices of tile n+2 are prefetched into registers, so no global
 // latency is exposed between tiles.
+// The CTA walks the tiles a.order[first + blockIdx.x], [first + blockIdx.x + gridDim.x], ... below first + ntiles.
 template <bool ONETYPE, bool ENERGY>
-__global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int ntiles, LJOne one, const LJTab *__restrict__ tab,
+__global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, LJOne one, const LJTab *__restrict__ tab,
                                                                    double *__restrict__ f, double *__restrict__ pe_partial) {
   __shared__ double s_red[kForceThreads / 32];
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -743,8 +780,9 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
   const int G = gridDim.x;
   int jreg[kStagePerThread];
 
+  auto tile_at = [&](int pos) { return pos < ntiles ? a.order[first + pos] : -1; }; // pos-th tile of this launch's range
   auto load_j = [&](int tile) { // staging indices of `tile` into registers (coalesced)
-    if (tile < ntiles) {
+    if (tile >= 0) {
       const int n = a.stg_n[tile];
       const int *src = a.stg_j + (size_t)tile * a.cap;
 #pragma unroll
@@ -768,29 +806,31 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
     }
   };
 
-  int tile = blockIdx.x;
+  int pos = blockIdx.x;
+  int tile = tile_at(pos), tile_nxt = tile_at(pos + G);
   load_j(tile);
   issue_copies(0);
-  load_j(tile + G);
+  load_j(tile_nxt);
   // per-thread row descriptors of the current tile
   int i_cur = 0x7fffffff, own_cur = 0, n_cur = 0;
-  if (tile < ntiles) {
+  if (tile >= 0) {
     i_cur = a.int_glob[(size_t)tile * a.stride + ts];
     own_cur = a.int_slot[(size_t)tile * a.stride + ts];
     n_cur = a.nell_s[(size_t)tile * a.stride + ts];
   }
   double pe = 0.0;
   int buf = 0;
-  for (; tile < ntiles; tile += G, buf ^= 1) {
+  for (; pos < ntiles; pos += G, buf ^= 1) {
     cp_async_wait_all();
     __syncthreads(); // buffer `buf` is complete; every thread is done with buffer `buf^1`
-    issue_copies(buf ^ 1);  // tile + G
-    load_j(tile + 2 * G);
+    issue_copies(buf ^ 1);  // tile_nxt
+    const int tile_nn = tile_at(pos + 2 * G);
+    load_j(tile_nn);
     int i_nxt = 0x7fffffff, own_nxt = 0, n_nxt = 0;
-    if (tile + G < ntiles) {
-      i_nxt = a.int_glob[(size_t)(tile + G) * a.stride + ts];
-      own_nxt = a.int_slot[(size_t)(tile + G) * a.stride + ts];
-      n_nxt = a.nell_s[(size_t)(tile + G) * a.stride + ts];
+    if (tile_nxt >= 0) {
+      i_nxt = a.int_glob[(size_t)tile_nxt * a.stride + ts];
+      own_nxt = a.int_slot[(size_t)tile_nxt * a.stride + ts];
+      n_nxt = a.nell_s[(size_t)tile_nxt * a.stride + ts];
     }
     const double *sp = sp0 + (size_t)buf * 3 * a.cap;
     const int *st = st0 + (size_t)buf * a.cap;
@@ -816,6 +856,7 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
       if (!ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
     }
     i_cur = i_nxt; own_cur = own_nxt; n_cur = n_nxt;
+    tile = tile_nxt; tile_nxt = tile_nn;
   }
   cp_async_wait_all();
   if (ENERGY) {
@@ -850,6 +891,9 @@ struct emd_tiles {
   int *d_stg_n = nullptr; size_t stg_n_cap = 0;
   unsigned short *d_int_slot = nullptr; size_t int_slot_cap = 0;
   int *d_int_glob = nullptr; size_t int_glob_cap = 0;
+  int *d_order = nullptr; size_t order_cap = 0;
+  int *d_has_ghost = nullptr; size_t has_ghost_cap = 0;
+  int n_free_tiles = 0;  // tiles that do not read the halo (first in d_order)
   int *d_flags = nullptr;
   int num_sms = 148;
   LJTab *d_tab = nullptr;
@@ -905,6 +949,8 @@ void emd_tiles_destroy(emd_tiles *t) {
   if (t->d_stg_n) cudaFree(t->d_stg_n);
   if (t->d_int_slot) cudaFree(t->d_int_slot);
   if (t->d_int_glob) cudaFree(t->d_int_glob);
+  if (t->d_order) cudaFree(t->d_order);
+  if (t->d_has_ghost) cudaFree(t->d_has_ghost);
   if (t->d_flags) cudaFree(t->d_flags);
   if (t->d_tab) cudaFree(t->d_tab);
   delete t;
@@ -1007,7 +1053,10 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
       if (ensure_bytes((void **)&t->d_stg_n, &t->stg_n_cap, (size_t)t->ntiles * sizeof(int))) return 1;
       if (ensure_bytes((void **)&t->d_int_slot, &t->int_slot_cap, (size_t)t->ntiles * a.stride * sizeof(unsigned short))) return 1;
       if (ensure_bytes((void **)&t->d_int_glob, &t->int_glob_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
+      if (ensure_bytes((void **)&t->d_order, &t->order_cap, (size_t)t->ntiles * sizeof(int))) return 1;
+      if (ensure_bytes((void **)&t->d_has_ghost, &t->has_ghost_cap, (size_t)t->ntiles * sizeof(int))) return 1;
       a.stg_j = t->d_stg_j; a.stg_n = t->d_stg_n; a.int_slot = t->d_int_slot; a.int_glob = t->d_int_glob;
+      a.order = t->d_order; a.has_ghost = t->d_has_ghost;
       EMD_LAUNCH(ctx, tiles_tables_kernel, t->ntiles, kFilterThreads, 0, a);
       // the force kernel's copy of the adjacency: bank-conflict-free columns (tiles_schedule_kernel)
       if (ensure_bytes((void **)&t->d_nell_s, &t->nell_s_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
@@ -1026,6 +1075,7 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
         const size_t wsm = sched_warp_smem(a.maxrow, a.maxrow_s), ssm = wsm * kSchedWarps;
         if (ssm > (size_t)t->max_smem_optin) return 3;
         EMD_CUDA(cudaMemsetAsync(t->d_flags, 0, 4 * sizeof(int), ctx->stream));
+        EMD_LAUNCH(ctx, tiles_order_kernel, 1, 1024, 0, a, t->ntiles); // writes flags[2]
 #define EMD_SCHED(M)                                                                                                        \
   do {                                                                                                                     \
     if (set_smem(tiles_schedule_kernel<M>, ssm)) return 1;                                                                 \
@@ -1040,7 +1090,7 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
 #undef EMD_SCHED
         EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         EMD_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (!(ctx->h_pinned[0] & 8)) { t->valid = true; return 0; }
+        if (!(ctx->h_pinned[0] & 8)) { t->n_free_tiles = ctx->h_pinned[2]; t->valid = true; return 0; }
         maxrow_s = (ctx->h_pinned[1] + ctx->h_pinned[1] / 8 + 15) / 8 * 8;
       }
       return 3;
@@ -1112,9 +1162,14 @@ int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half, int newton, in
 // ForceLJNeigh::compute / compute_energy on the tile lists.  d_x/d_type are the CURRENT arrays
 // (atoms keep their indices between rebuilds; the binning arrays captured at build time must
 // still be alive).  With h_pe != NULL only the energy is computed (forces untouched).
-int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe) {
+// part: 0 = every tile; 1 = only the tiles that do not read the halo (their forces are final before the halo exchange of
+// this step has landed); 2 = the rest.  reserve_ctas > 0 leaves that many CTA slots of the persistent grid free, so that
+// the pack and NCCL kernels of a concurrent halo exchange find room on the SMs.
+static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe, int part,
+                           int reserve_ctas) {
   if (!t || !t->valid) { set_error("emd_force_lj_compute_tiles: tiles not built"); return 1; }
   if (ctx->lj.ntypes == 0) { set_error("emd_force_lj_compute_tiles: parameters not set"); return 1; }
+  if (part < 0 || part > 2 || (h_pe && part != 0)) { set_error("emd_force_lj_compute_tiles: bad part"); return 1; }
   TileArgs a = t->a;
   a.x = d_x; a.type = d_type;
   const bool one = ctx->lj.ntypes == 1;
@@ -1128,21 +1183,40 @@ int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, co
   }
   const size_t smem = force_smem(a.cap, !one);
   if (smem > (size_t)t->max_smem_optin) { set_error("emd_force_lj_compute_tiles: tile does not fit in shared memory"); return 1; }
-  const int grid = std::min(t->ntiles, 2 * t->num_sms);
+  const int first = part == 2 ? t->n_free_tiles : 0;
+  const int count = part == 0 ? t->ntiles : part == 1 ? t->n_free_tiles : t->ntiles - t->n_free_tiles;
+  if (count <= 0) return 0;
+  const int grid = std::max(1, std::min(count, 2 * t->num_sms - std::max(0, reserve_ctas)));
   double *partial = nullptr;
   if (h_pe) {
     if (ctx->s_c.ensure(sizeof(double) * ((size_t)grid + 8))) return 1;
     partial = ctx->s_c.as<double>() + 8;
   }
-#define EMD_LJ_TILES(ONE, EN)                                                                                          \
-  do {                                                                                                                 \
-    if (set_smem(lj_tiles_kernel<ONE, EN>, smem)) return 1;                                                            \
-    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN>), grid, kForceThreads, smem, a, t->ntiles, p1, t->d_tab, d_f, partial);  \
+#define EMD_LJ_TILES(ONE, EN)                                                                                              \
+  do {                                                                                                                     \
+    if (set_smem(lj_tiles_kernel<ONE, EN>, smem)) return 1;                                                                \
+    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN>), grid, kForceThreads, smem, a, first, count, p1, t->d_tab, d_f, partial);   \
   } while (0)
   if (h_pe) { if (one) EMD_LJ_TILES(true, true); else EMD_LJ_TILES(false, true); }
   else { if (one) EMD_LJ_TILES(true, false); else EMD_LJ_TILES(false, false); }
 #undef EMD_LJ_TILES
   if (h_pe) return device_sum_partials(ctx, partial, grid, h_pe);
+  return 0;
+}
+
+int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe) {
+  return lj_tiles_launch(ctx, t, d_x, d_type, d_f, h_pe, 0, 0);
+}
+
+int emd_force_lj_compute_tiles_part(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, int part,
+                                    int reserve_ctas) {
+  return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, part, reserve_ctas);
+}
+
+int emd_tiles_halo_split(const emd_tiles *t, int *n_free, int *n_halo) {
+  if (!t || !t->valid) { set_error("emd_tiles_halo_split: tiles not built"); return 1; }
+  if (n_free) *n_free = t->n_free_tiles;
+  if (n_halo) *n_halo = t->ntiles - t->n_free_tiles;
   return 0;
 }
 

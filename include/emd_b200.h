@@ -48,6 +48,14 @@ int emd_memcpy_h2d(emd_ctx *ctx, void *d_dst, const void *h_src, unsigned long l
 int emd_memcpy_d2h(emd_ctx *ctx, void *h_dst, const void *d_src, unsigned long long bytes);
 int emd_memcpy_d2d(emd_ctx *ctx, void *d_dst, const void *d_src, unsigned long long bytes);
 int emd_memset_zero(emd_ctx *ctx, void *d_dst, unsigned long long bytes); /* Kokkos::deep_copy(view,0) */
+/* A second, lower-priority stream for work that may overlap the module stream (the driver computes the halo-independent
+ * part of the force on it while CommMPI::update_halo runs on the module stream).  side_begin: the side stream waits for
+ * everything queued so far (or up to the last side_mark) and becomes the stream every entry point launches on; side_end: back to the module stream;
+ * side_join: the module stream waits for the side work. */
+int emd_ctx_side_mark(emd_ctx *ctx);  /* optional: fix the fork point now; the next side_begin waits for THIS point only */
+int emd_ctx_side_begin(emd_ctx *ctx);
+int emd_ctx_side_end(emd_ctx *ctx);
+int emd_ctx_side_join(emd_ctx *ctx);
 
 /* ---- binning: BinningKKSort::create_binning, src/binning_types/binning_kksort.cpp:71-140 */
 typedef struct {
@@ -170,6 +178,13 @@ int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half_neigh, int comm
  * Valid for full lists and for half lists with newton off (same forces on owned atoms). */
 int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type,
                                double *d_f, double *h_pe);
+/* The same force in two launches, for a decomposed run (CommMPI): part 1 = the tiles whose staged cells hold only owned
+ * atoms (no dependence on this step's halo exchange, src/comm_types/comm_mpi.cpp:382-423), part 2 = the tiles that read
+ * ghosts; part 0 = all.  The two parts write disjoint rows of d_f.  reserve_ctas leaves CTA slots of the persistent grid
+ * free for the exchange's pack / transport kernels.  emd_tiles_halo_split reports the two tile counts. */
+int emd_force_lj_compute_tiles_part(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type,
+                                    double *d_f, int part, int reserve_ctas);
+int emd_tiles_halo_split(const emd_tiles *t, int *n_free_tiles, int *n_halo_tiles);
 
 /* ---- SNAP force: ForceSNAP<> + SNA, src/force_types/force_snap_neigh_impl.h, sna_impl.hpp ------- */
 /* What init_coeff/read_files (force_snap_neigh_impl.h:227-336, 340-587) leave behind, as plain values.

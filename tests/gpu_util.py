@@ -153,6 +153,15 @@ class Tiles:
                                                        C.byref(pe) if energy else None), "force_tiles")
         return pe.value
 
+    def force_part(self, x_dev, type_dev, f_dev, part, reserve=0):
+        emd.check(emd.lib().emd_force_lj_compute_tiles_part(self.ctx.handle, self.h, ptr(x_dev), ptr(type_dev), ptr(f_dev), part, reserve),
+                  "force_tiles_part")
+
+    def halo_split(self):
+        a, b = C.c_int(), C.c_int()
+        emd.check(emd.lib().emd_tiles_halo_split(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def close(self):
         if self.h:
             emd.lib().emd_tiles_destroy(self.h)

@@ -298,6 +298,36 @@ def test_tiles_schedule_is_a_conflict_free_permutation(emd, gu, ctx, state, mode
     t.close(); md.close()
 
 
+def test_tiles_force_in_two_parts(emd, gu, ctx):
+    """the halo-independent tiles and the tiles that read ghosts partition the force: part 1 + part 2 write exactly the rows
+    of the single launch, bit for bit, and part 1 really does not depend on the ghost coordinates"""
+    import torch
+    md = OracleMD.from_deck(DECK, "CSR", "NEIGH_FULL", region=(16, 16, 16))
+    md.step(3)
+    rebuilt(md)
+    n = md.geti("N_local")
+    t, x = _tiles_for(gu, ctx, md)
+    assert t.ok
+    n_free, n_halo = t.halo_split()
+    assert n_free > 0 and n_halo > 0 and n_free + n_halo == t.info()["ntiles"]
+    _set_lj(emd, ctx, md)
+    typ = gu.dev(md.arr("type"))
+    f0 = torch.full((x.shape[0], 3), 7.0, dtype=torch.float64, device="cuda")
+    t.force(x, typ, f0)
+    f1 = torch.full_like(f0, 7.0)
+    xg = x.clone()
+    xg[n:] = float("nan")                      # part 1 must not read a single ghost coordinate
+    t.force_part(xg, typ, f1, 1, reserve=16)
+    ctx.sync()
+    touched1 = (f1[:n] != 7.0).any(dim=1)
+    assert bool(touched1.any()) and not bool(touched1.all())
+    assert not bool(torch.isnan(f1).any())
+    t.force_part(x, typ, f1, 2)
+    ctx.sync()
+    assert torch.equal(f0, f1)
+    t.close(); md.close()
+
+
 def test_tiles_two_types_and_ragged(emd, gu, ctx):
     import torch
     rng = np.random.default_rng(3)
