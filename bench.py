@@ -361,7 +361,16 @@ def main():
     achieved = force_bytes / (force_ms * 1e-3) / 1e9
     b_lj = 208 + 100 * g + 52 * (g - 1) + 4 * nbar
     value_per_gpu = value / world
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM bytes of one launch of this kernel on this workload from the committed `ncu --set full` capture (profiles/)
+    traffic, traffic_src = None, None
+    tj = REPO / "profiles" / "r01_lj_tiles_traffic.json"
+    if tiles and world == 1 and not args.region and tj.exists():
+        tr = json.loads(tj.read_text())
+        traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": force_bytes,
+                "limiter": "FP64 pipe + LSU, not HBM: 17 FP64 instructions per pair, every pair evaluated from both sides (ncu: FP64 pipe 48 % active, "
+                           "DRAM 17 % of peak); the HBM fraction is reported because BASELINE.json's metric asks for it",
                 "kernel": "lj_tiles_kernel" if tiles else "lj_force_kernel<half> + zero_rows_kernel", "kernel_ms": force_ms, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_atom": force_bytes / n_local, "nbar": nbar, "g": g,
                 "whole_step": {"B_LJ_bytes_per_atom_step": b_lj, "achieved_gbs": b_lj * value_per_gpu / 1e9,

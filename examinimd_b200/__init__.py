@@ -110,6 +110,7 @@ _SIGS = {
     "emd_ctx_side_begin": (C.c_int, [_P]),
     "emd_ctx_side_end": (C.c_int, [_P]),
     "emd_ctx_side_join": (C.c_int, [_P]),
+    "emd_ctx_side_sms": (C.c_int, [_P]),
     "emd_snap_create": (C.c_int, [C.POINTER(_P), C.POINTER(SnapParams)]),
     "emd_snap_destroy": (None, [_P]),
     "emd_snap_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),

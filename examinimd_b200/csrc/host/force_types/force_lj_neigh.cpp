@@ -58,8 +58,8 @@ bool ForceLJNeigh::can_split(System *, Neighbor *neighbor) {
 }
 
 void ForceLJNeigh::compute_part(System *system, Binning *, Neighbor *neighbor, int part) {
-  static const int reserve = getenv("EMD_OVERLAP_RESERVE") ? atoi(getenv("EMD_OVERLAP_RESERVE")) : 16;
-  // part 1 shares the SMs with the halo exchange's pack and transport kernels: leave them CTA slots
+  static const int reserve = getenv("EMD_OVERLAP_RESERVE") ? atoi(getenv("EMD_OVERLAP_RESERVE")) : 0;
+  // part 1 runs on the side stream's SM partition (ctx.cu); EMD_OVERLAP_RESERVE additionally leaves CTA slots free
   if (emd_force_lj_compute_tiles_part(system->ctx, neighbor->tiles(), system->x, system->type, system->f, part, part == 1 ? reserve : 0))
     fail("compute_part (tiles)");
 }

@@ -56,6 +56,7 @@ struct emd_ctx {
   cudaStream_t side_stream = nullptr, main_stream = nullptr; // emd_ctx_side_*: main_stream != nullptr while the side stream is current
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fork_marked = false;
+  int side_sms = 0; // SMs of the side stream's green context (0: it shares the whole device)
   int num_sms = 148;
   // scratch
   emd::Scratch s_a, s_b, s_c, s_scan; // general-purpose device scratch

@@ -1,5 +1,9 @@
 // ctx.cu -- context lifetime, error string, memory helpers, exclusive scan.
 #include "common.cuh"
+#include <cuda.h>
+#include <dlfcn.h>
+#include <cstdlib>
+#include <cstdio>
 #include <cstdarg>
 
 namespace emd {
@@ -158,15 +162,63 @@ void emd_ctx_destroy(emd_ctx *c) {
 void *emd_ctx_stream(emd_ctx *c) { return (void *)c->stream; }
 int emd_ctx_sync(emd_ctx *c) { EMD_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
 unsigned long long emd_ctx_launch_count(emd_ctx *c) { return c->launches; }
+// The side stream lives in a GREEN CONTEXT that owns all but a few SMs (driver API, CUDA >= 12.4, resolved at run time so the
+// library has no link-time dependency on libcuda): the persistent force kernel launched on it fills ITS SMs, and the pack and
+// NCCL kernels of the halo exchange, on the module stream, always find the remaining SMs empty.  Measured on 2 B200s: with a
+// plain low-priority stream the exchange kernels queue behind the persistent CTAs (stream priority does not preempt) and the
+// overlap hides a quarter of the exchange; with 20 SMs set aside the 2-GPU step is 5.6 % shorter than without overlap
+// (gpurun r01p).  EMD_OVERLAP_SMS = SMs left to the exchange (default 20; 0 = plain stream).
+static cudaStream_t partition_stream(emd_ctx *c, int comm_sms, int priority, int *sms_out) {
+  void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return nullptr;
+  typedef CUresult (*f_devget)(CUdevice *, int);
+  typedef CUresult (*f_getres)(CUdevice, CUdevResource *, CUdevResourceType);
+  typedef CUresult (*f_split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+  typedef CUresult (*f_desc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+  typedef CUresult (*f_gcreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*f_gstream)(CUstream *, CUgreenCtx, unsigned int, int);
+  f_devget devget = (f_devget)dlsym(h, "cuDeviceGet");
+  f_getres getres = (f_getres)dlsym(h, "cuDeviceGetDevResource");
+  f_split split = (f_split)dlsym(h, "cuDevSmResourceSplitByCount");
+  f_desc gendesc = (f_desc)dlsym(h, "cuDevResourceGenerateDesc");
+  f_gcreate gcreate = (f_gcreate)dlsym(h, "cuGreenCtxCreate");
+  f_gstream gstream = (f_gstream)dlsym(h, "cuGreenCtxStreamCreate");
+  if (!devget || !getres || !split || !gendesc || !gcreate || !gstream) return nullptr;
+  CUdevice dev;
+  CUdevResource sm, grp, rem;
+  if (devget(&dev, c->device) != CUDA_SUCCESS || getres(dev, &sm, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return nullptr;
+  const int total = (int)sm.sm.smCount;
+  if (comm_sms <= 0 || comm_sms >= total) return nullptr;
+  unsigned int ngroups = 1;
+  if (split(&grp, &ngroups, &sm, &rem, 0, (unsigned)(total - comm_sms)) != CUDA_SUCCESS || ngroups != 1) return nullptr;
+  if ((int)grp.sm.smCount >= total) return nullptr; // the granularity left nothing for the exchange
+  CUdevResourceDesc desc;
+  CUgreenCtx g;
+  CUstream st;
+  if (gendesc(&desc, &grp, 1) != CUDA_SUCCESS || gcreate(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return nullptr;
+  if (gstream(&st, g, CU_STREAM_NON_BLOCKING, priority) != CUDA_SUCCESS) return nullptr;
+  *sms_out = (int)grp.sm.smCount;
+  return (cudaStream_t)st; // the green context lives as long as the process
+}
+
 static int side_init(emd_ctx *c) {
   if (c->side_stream) return 0;
   int lo = 0, hi = 0;
   EMD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi)); // lo = least priority: the exchange on the module stream goes first
-  EMD_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
+  const char *e = getenv("EMD_OVERLAP_SMS");
+  const int comm_sms = e ? atoi(e) : 20;
+  c->side_sms = 0;
+  c->side_stream = partition_stream(c, comm_sms, lo, &c->side_sms);
+  if (!c->side_stream) {
+    c->side_sms = 0;
+    EMD_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
+  }
+  if (getenv("EMD_VERBOSE")) fprintf(stderr, "emd: side stream on %d SMs (%s)\n", c->side_sms ? c->side_sms : c->num_sms, c->side_sms ? "green context" : "shared");
   EMD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   EMD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   return 0;
 }
+int emd_ctx_side_sms(const emd_ctx *c) { return (c->main_stream && c->side_sms) ? c->side_sms : c->num_sms; }
 int emd_ctx_side_mark(emd_ctx *c) {
   if (c->main_stream) { set_error("emd_ctx_side_mark: already on the side stream"); return 1; }
   if (side_init(c)) return 1;

@@ -1186,7 +1186,7 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
   const int first = part == 2 ? t->n_free_tiles : 0;
   const int count = part == 0 ? t->ntiles : part == 1 ? t->n_free_tiles : t->ntiles - t->n_free_tiles;
   if (count <= 0) return 0;
-  const int grid = std::max(1, std::min(count, 2 * t->num_sms - std::max(0, reserve_ctas)));
+  const int grid = std::max(1, std::min(count, 2 * emd_ctx_side_sms(ctx) - std::max(0, reserve_ctas)));
   double *partial = nullptr;
   if (h_pe) {
     if (ctx->s_c.ensure(sizeof(double) * ((size_t)grid + 8))) return 1;

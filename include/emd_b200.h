@@ -56,6 +56,7 @@ int emd_ctx_side_mark(emd_ctx *ctx);  /* optional: fix the fork point now; the n
 int emd_ctx_side_begin(emd_ctx *ctx);
 int emd_ctx_side_end(emd_ctx *ctx);
 int emd_ctx_side_join(emd_ctx *ctx);
+int emd_ctx_side_sms(const emd_ctx *ctx); /* SMs available to the current stream (side stream: its partition) */
 
 /* ---- binning: BinningKKSort::create_binning, src/binning_types/binning_kksort.cpp:71-140 */
 typedef struct {
