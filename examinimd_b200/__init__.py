@@ -118,6 +118,7 @@ _SIGS = {
     "emd_snap_device_ptr": (_P, [_P, C.c_char_p]),
     "emd_force_snap_compute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NeighList)]),
     "emd_nve_initial_integrate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double]),
+    "emd_nve_final_initial_integrate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double]),
     "emd_nve_final_integrate": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double]),
     "emd_comm_wrap": (C.c_int, [_P, _P, C.c_int, _D3]),
     "emd_comm_halo_phase": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _D3, _D3, _D3,

@@ -41,7 +41,7 @@ int emd_app_advance(emd_app *a, int nsteps) {
 
 int emd_app_advance_timed(emd_app *a, int nsteps, double *h_seconds4) {
   PhaseTimers tm(a->md->system->ctx);
-  for (int k = 0; k < nsteps; k++) a->md->step_once(++a->md->current_step, &tm);
+  for (int k = 0; k < nsteps; k++) a->md->step_once(++a->md->current_step, &tm, k + 1 < nsteps);
   tm.flush();
   h_seconds4[0] = tm.seconds[PhaseTimers::FORCE]; h_seconds4[1] = tm.seconds[PhaseTimers::NEIGH];
   h_seconds4[2] = tm.seconds[PhaseTimers::COMM]; h_seconds4[3] = tm.seconds[PhaseTimers::OTHER];

@@ -151,13 +151,15 @@ void ExaMiniMD::thermo(T_FLOAT *T, T_FLOAT *PE, T_FLOAT *KE) {
   *KE = kine.compute(system) / system->N;
 }
 
-void ExaMiniMD::step_once(int step, PhaseTimers *tm) {
+void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
   const T_F_FLOAT neigh_cutoff = input->force_cutoff + input->neighbor_skin;
   static const bool overlap_halo = !(getenv("EMD_NO_OVERLAP") && atoi(getenv("EMD_NO_OVERLAP")));
   static const bool comm_first = !(getenv("EMD_OVERLAP_ORDER") && atoi(getenv("EMD_OVERLAP_ORDER")) == 0);
   bool split = false;
+  static const bool fuse_nve = !(getenv("EMD_NO_FUSED_NVE") && atoi(getenv("EMD_NO_FUSED_NVE")));
   if (tm) tm->begin();
-  integrator->initial_integrate();
+  if (!initial_done) integrator->initial_integrate();
+  initial_done = false;
   if (tm) tm->end(PhaseTimers::OTHER);
 
   if (step % input->comm_exchange_rate == 0 && step > 0) {
@@ -205,12 +207,13 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm) {
     if (tm) tm->end(PhaseTimers::COMM);
   }
 
-  integrator->final_integrate();
+  if (fuse_next && fuse_nve) { integrator->final_initial_integrate(); initial_done = true; }
+  else integrator->final_integrate();
   if (tm) tm->end(PhaseTimers::OTHER);
 }
 
 void ExaMiniMD::advance(int nsteps) {
-  for (int k = 0; k < nsteps; k++) step_once(++current_step, nullptr);
+  for (int k = 0; k < nsteps; k++) step_once(++current_step, nullptr, k + 1 < nsteps);
 }
 
 void ExaMiniMD::run(int nsteps) {
@@ -221,7 +224,9 @@ void ExaMiniMD::run(int nsteps) {
 
   for (int s = 1; s <= nsteps; s++) {
     const int step = ++current_step;
-    step_once(step, &tm);
+    // thermo output, dumps and the correctness check read x, v, f between two steps: no fusion across them
+    const bool observed = (input->thermo_rate > 0 && step % input->thermo_rate == 0) || input->dumpbinaryflag || input->correctnessflag;
+    step_once(step, &tm, s < nsteps && !observed);
 
     if (input->thermo_rate > 0 && step % input->thermo_rate == 0) {
       T_FLOAT T, PE, KE;

@@ -51,7 +51,10 @@ public:
   void run(int nsteps);
 
   // one timestep of the loop body of run() (examinimd.cpp:192-250), without output
-  void step_once(int step, PhaseTimers *timers);
+  // fuse_next: the next step follows with nothing observing the state in between, so this step ends with
+  // Integrator::final_initial_integrate() and the next one skips its initial_integrate()
+  void step_once(int step, PhaseTimers *timers, bool fuse_next = false);
+  bool initial_done = false; // the pending step's initial_integrate has already been applied
   // advance `nsteps` steps continuing the global step counter (rebuild cadence preserved)
   void advance(int nsteps);
   void thermo(T_FLOAT *T, T_FLOAT *PE, T_FLOAT *KE);

@@ -11,6 +11,9 @@ public:
   virtual ~Integrator() {}
   virtual void initial_integrate() {}
   virtual void final_integrate() {}
+  // final_integrate() immediately followed by the next step's initial_integrate() (not in the reference; the driver calls
+  // it when nothing observes the state between two steps).  Default: the two calls.
+  virtual void final_initial_integrate() { final_integrate(); initial_integrate(); }
   virtual const char *name() { return "IntegratorNone"; }
 };
 

@@ -24,4 +24,12 @@ void IntegratorNVE::final_integrate() {
   }
 }
 
+void IntegratorNVE::final_initial_integrate() {
+  if (emd_nve_final_initial_integrate(system->ctx, system->x, system->v, system->f, system->type, system->mass, system->N_local,
+                                      dtf, dtv)) {
+    fprintf(stderr, "IntegratorNVE::final_initial_integrate: %s\n", emd_last_error());
+    exit(1);
+  }
+}
+
 const char *IntegratorNVE::name() { return "IntegratorNVE"; }

@@ -10,6 +10,7 @@ public:
   IntegratorNVE(System *s);
   void initial_integrate();
   void final_integrate();
+  void final_initial_integrate();
   const char *name();
 };
 #endif

@@ -35,9 +35,34 @@ __global__ void __launch_bounds__(256) nve_final_kernel(double *__restrict__ v, 
   v[e] = __dadd_rn(v[e], __dmul_rn(dtfm, f[e]));        // :107-109
 }
 
+// final_integrate of step n and initial_integrate of step n+1 in one pass (124 B/atom instead of 76 + 124): the same
+// operations in the same order on the same values, so x and v are bit-identical to the two separate kernels.
+__global__ void __launch_bounds__(256) nve_final_initial_kernel(double *__restrict__ x, double *__restrict__ v,
+                                                                const double *__restrict__ f, const int *__restrict__ type,
+                                                                const double *__restrict__ mass, long long n3, double dtf,
+                                                                double dtv) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n3) return;
+  const int i = (int)(e / 3);
+  const double dtfm = dtf / mass[type[i]];
+  const double kick = __dmul_rn(dtfm, f[e]);
+  const double v1 = __dadd_rn(v[e], kick);              // final_integrate, integrator_nve.cpp:107-109
+  const double v2 = __dadd_rn(v1, kick);                // initial_integrate of the next step, :68-70 (f unchanged in between)
+  v[e] = v2;
+  x[e] = __dadd_rn(x[e], __dmul_rn(dtv, v2));           // :71-73
+}
+
 } // namespace
 
 extern "C" {
+
+int emd_nve_final_initial_integrate(emd_ctx *ctx, double *d_x, double *d_v, const double *d_f, const int *d_type,
+                                    const double *d_mass, int n_local, double dtf, double dtv) {
+  if (n_local <= 0) return 0;
+  const long long n3 = 3LL * n_local;
+  EMD_LAUNCH(ctx, nve_final_initial_kernel, grid_for(n3, 256), 256, 0, d_x, d_v, d_f, d_type, d_mass, n3, dtf, dtv);
+  return 0;
+}
 
 int emd_nve_initial_integrate(emd_ctx *ctx, double *d_x, double *d_v, const double *d_f, const int *d_type,
                               const double *d_mass, int n_local, double dtf, double dtv) {

@@ -219,23 +219,37 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_filter_kernel(TileArgs a
       const int own = s_start[c_i] + k;
       const float4 p = in_cell ? sf[own] : make_float4(0.f, 0.f, 0.f, 0.f);
       const int tslot = s_ibase[ci] + k;
+      // Accepted slots are shifted into a 64-bit accumulator from the top (after four of them the first sits in the low 16
+      // bits) and leave as whole 16-byte words: one store per 8 entries instead of eight 2-byte stores with their index math.
       int q = 0;
+      unsigned long long acc = 0ull, lo = 0ull;
+      uint4 *const wrow = reinterpret_cast<uint4 *>(a.ell) + ((size_t)t.tile * (a.maxrow >> 3)) * a.stride + tslot;
       for (int sc = 0; sc < 27; sc++) {
         const int c = c_i + ((sc / 9 - 1) * t.syn + ((sc / 3) % 3 - 1)) * t.szn + (sc % 3 - 1);
         const int e = s_start[c + 1];
+#pragma unroll 4
         for (int s = s_start[c]; s < e; s++) {
           const float4 pj = sf[s]; // same address in every lane: broadcast
           const float dx = p.x - pj.x, dy = p.y - pj.y, dz = p.z - pj.z;
           const float r2 = dx * dx + dy * dy + dz * dz;
           if (active && r2 <= cutf2 && s != own) {
-            if (q < a.maxrow) a.ell[ell_index(a, t.tile, q, tslot)] = (unsigned short)s;
+            acc = (acc >> 16) | ((unsigned long long)s << 48);
             q++;
+            if ((q & 3) == 0) {
+              if (q & 4) lo = acc;
+              else if (q <= a.maxrow) wrow[(size_t)((q >> 3) - 1) * a.stride] = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)acc, (unsigned)(acc >> 32));
+            }
           }
         }
       }
       if (in_cell) {
-        // pad the last 8-entry word with an in-bounds slot: the force kernel loads whole words
-        for (int qp = q; qp < min((q + 7) & ~7, a.maxrow); qp++) a.ell[ell_index(a, t.tile, qp, tslot)] = (unsigned short)own;
+        const int rem = q & 7;
+        if (rem && q < a.maxrow) { // the last, partial word (entries beyond the row length are never read)
+          unsigned long long hi = 0ull;
+          if (rem < 4) lo = acc >> (16 * (4 - rem));
+          else if (rem > 4) hi = acc >> (16 * (8 - rem));
+          wrow[(size_t)(q >> 3) * a.stride] = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+        }
         a.nell[(size_t)t.tile * a.stride + tslot] = min(q, a.maxrow);
         if (q > a.maxrow) { atomicOr(&a.flags[0], 4); atomicMax(&a.flags[1], q); }
       }
@@ -530,7 +544,7 @@ __global__ void __launch_bounds__(32 * kRotWarps) tiles_rotate_kernel(TileArgs a
   unsigned short *srow = reinterpret_cast<unsigned short *>(dyn + (size_t)warp * warp_smem + 16 * 32 * sizeof(unsigned)) + lane; // srow[pos * 32]
   const int n = a.nell[(size_t)tile * a.stride + ts];
   const unsigned own = a.int_slot[(size_t)tile * a.stride + ts];
-  const uint4 *row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)tile * (a.maxrow >> 3)) * a.stride + ts;
+  const uint4 *__restrict__ row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)tile * (a.maxrow >> 3)) * a.stride + ts;
   const int nmax = __reduce_max_sync(0xffffffffu, n);
   if (nmax > a.maxrow_s) {
     if (lane == 0) { atomicOr(&a.flags[0], 8); atomicMax(&a.flags[1], nmax); }
@@ -539,8 +553,11 @@ __global__ void __launch_bounds__(32 * kRotWarps) tiles_rotate_kernel(TileArgs a
   // counting sort by bank (stable): sizes -> starts -> scatter
 #pragma unroll
   for (int b = 0; b < 16; b++) state[b * 32] = 0;
+  // (both passes request word c+1 before they work on word c: the row comes from DRAM)
+  uint4 wnext = n > 0 ? __ldg(row) : make_uint4(0, 0, 0, 0);
   for (int c = 0; c * 8 < n; c++) {
-    const uint4 w = row[(size_t)c * a.stride];
+    const uint4 w = wnext;
+    if ((c + 1) * 8 < n) wnext = __ldg(row + (size_t)(c + 1) * a.stride);
     const unsigned e[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int k = 0; k < 8; k++)
@@ -557,8 +574,10 @@ __global__ void __launch_bounds__(32 * kRotWarps) tiles_rotate_kernel(TileArgs a
       run += cb;
     }
   }
+  wnext = n > 0 ? __ldg(row) : make_uint4(0, 0, 0, 0);
   for (int c = 0; c * 8 < n; c++) {
-    const uint4 w = row[(size_t)c * a.stride];
+    const uint4 w = wnext;
+    if ((c + 1) * 8 < n) wnext = __ldg(row + (size_t)(c + 1) * a.stride);
     const unsigned e[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int k = 0; k < 8; k++)

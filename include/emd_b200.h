@@ -228,6 +228,10 @@ int emd_nve_initial_integrate(emd_ctx *ctx, double *d_x, double *d_v, const doub
                               double dtf, double dtv);
 int emd_nve_final_integrate(emd_ctx *ctx, double *d_v, const double *d_f, const int *d_type,
                             const double *d_mass, int n_local, double dtf);
+/* final_integrate of one step followed by initial_integrate of the next (nothing between the two reads or writes x, v
+ * or f when no thermo output / dump sits between the steps): one pass over the atoms, bit-identical results. */
+int emd_nve_final_initial_integrate(emd_ctx *ctx, double *d_x, double *d_v, const double *d_f, const int *d_type,
+                                    const double *d_mass, int n_local, double dtf, double dtv);
 
 /* ---- single-process periodic comm: CommSerial, src/comm_types/comm_serial.{h,cpp} ------- */
 /* exchange (comm_serial.cpp:47-54, TagExchangeSelf comm_serial.h:94-107) */
