@@ -764,6 +764,10 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -788,13 +792,19 @@ constexpr int kStagePerThread = 8; // cap <= kForceThreads * kStagePerThread
 // is computed, and the staging indices of tile n+2 are prefetched into registers, so no global
 // latency is exposed between tiles.
 // The CTA walks the tiles a.order[first + blockIdx.x], [first + blockIdx.x + gridDim.x], ... below first + ntiles.
-template <bool ONETYPE, bool ENERGY>
+// RING: the ELL words travel global -> shared with cp.async into one 16-byte slot per thread (no register is held while
+// the copy is in flight, so -- unlike a register prefetch, which ptxas sinks to the end of the loop body at this register
+// budget -- the request really is issued a whole 8-pair iteration before its use); word 0 of the next tile's row is
+// requested during the last iteration of the current one.  Needs two CTAs to still fit on an SM with the extra 6 KB.
+// An experiment that did not pay (see lj_tiles_launch): kept behind EMD_TILES_RING=1.
+template <bool ONETYPE, bool ENERGY, bool RING>
 __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, LJOne one, const LJTab *__restrict__ tab,
-                                                                   double *__restrict__ f, double *__restrict__ pe_partial) {
+                                                                   double *__restrict__ f, double *__restrict__ pe_partial, unsigned ring_offset) {
   __shared__ double s_red[kForceThreads / 32];
   extern __shared__ __align__(16) unsigned char dyn[];
   double *const sp0 = reinterpret_cast<double *>(dyn); // 2 x [cap][3]: x,y,z of a staged atom adjacent (one address computation per pair)
   int *const st0 = reinterpret_cast<int *>(sp0 + 6 * (size_t)a.cap); // 2 x [cap] types (multi-type systems only)
+  uint4 *const ering = reinterpret_cast<uint4 *>(dyn + ring_offset) + threadIdx.x; // RING: this thread's slot
   const int ts = threadIdx.x;
   const int G = gridDim.x;
   int jreg[kStagePerThread];
@@ -837,6 +847,8 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
     own_cur = a.int_slot[(size_t)tile * a.stride + ts];
     n_cur = a.nell_s[(size_t)tile * a.stride + ts];
   }
+  auto row_of_tile = [&](int tl) { return reinterpret_cast<const uint4 *>(a.ell_s) + ((size_t)tl * (a.maxrow_s >> 3)) * a.stride + ts; };
+  if (RING && tile >= 0 && i_cur < a.n_local && n_cur > 0) cp_async16(ering, row_of_tile(tile)); // word 0 of the first row
   double pe = 0.0;
   int buf = 0;
   for (; pos < ntiles; pos += G, buf ^= 1) {
@@ -859,21 +871,36 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
       double fx = 0.0, fy = 0.0, fz = 0.0;
       // one 16-byte word = 8 columns of the warp's schedule (n_cur is the same multiple of 8 in every lane of the warp);
       // the next word is requested before the current one is used
-      const uint4 *row = reinterpret_cast<const uint4 *>(a.ell_s) + ((size_t)tile * (a.maxrow_s >> 3)) * a.stride + ts;
+      const uint4 *row = row_of_tile(tile);
       const int nchunk = n_cur >> 3;
-      uint4 cur = make_uint4(0, 0, 0, 0);
-      if (nchunk > 0) cur = ldg_nc_v4(row);
-      if (nchunk > 1) prefetch_l1(row + a.stride);
-      for (int c = 0; c < nchunk; c++) {
-        if (c + 2 < nchunk) prefetch_l1(row + (size_t)(c + 2) * a.stride);
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (c + 1 < nchunk) nxt = ldg_nc_v4(row + (size_t)(c + 1) * a.stride);
-        lj_quad<ONETYPE, ENERGY>(sp, st, cur.x, cur.y, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
-        lj_quad<ONETYPE, ENERGY>(sp, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
-        cur = nxt;
+      if (RING) {
+        // word 0 arrived with the tile's coordinates (wait + barrier above); the row of the next tile, if this thread has one
+        const uint4 *row_nxt = (tile_nxt >= 0 && i_nxt < a.n_local && n_nxt > 0) ? row_of_tile(tile_nxt) : nullptr;
+        for (int c = 0; c < nchunk; c++) {
+          if (c > 0) cp_async_wait_all(); // the word requested one iteration ago (and, long since, the next tile's coordinates)
+          const uint4 cur = *ering;
+          const uint4 *nextp = (c + 1 < nchunk) ? row + (size_t)(c + 1) * a.stride : row_nxt;
+          if (nextp) cp_async16(ering, nextp); // same thread: the read above precedes the asynchronous write
+          lj_quad<ONETYPE, ENERGY>(sp, st, cur.x, cur.y, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+          lj_quad<ONETYPE, ENERGY>(sp, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+        }
+      } else {
+        uint4 cur = make_uint4(0, 0, 0, 0);
+        if (nchunk > 0) cur = ldg_nc_v4(row);
+        if (nchunk > 1) prefetch_l1(row + a.stride);
+        for (int c = 0; c < nchunk; c++) {
+          if (c + 2 < nchunk) prefetch_l1(row + (size_t)(c + 2) * a.stride);
+          uint4 nxt = make_uint4(0, 0, 0, 0);
+          if (c + 1 < nchunk) nxt = ldg_nc_v4(row + (size_t)(c + 1) * a.stride);
+          lj_quad<ONETYPE, ENERGY>(sp, st, cur.x, cur.y, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+          lj_quad<ONETYPE, ENERGY>(sp, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+          cur = nxt;
+        }
       }
       if (!ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
     }
+    if (RING && !(i_cur < a.n_local && n_cur > 0) && tile_nxt >= 0 && i_nxt < a.n_local && n_nxt > 0)
+      cp_async16(ering, row_of_tile(tile_nxt)); // no row here, one in the next tile: its word 0
     i_cur = i_nxt; own_cur = own_nxt; n_cur = n_nxt;
     tile = tile_nxt; tile_nxt = tile_nn;
   }
@@ -919,6 +946,7 @@ struct emd_tiles {
   double neigh_cut = 0.0;
   float cutf2 = 0.f;
   int max_smem_optin = 0;
+  int max_smem_sm = 0;
 };
 
 namespace {
@@ -954,6 +982,7 @@ int emd_tiles_create(emd_tiles **out) {
   EMD_CUDA(cudaGetDevice(&dev));
   EMD_CUDA(cudaDeviceGetAttribute(&t->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   EMD_CUDA(cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  EMD_CUDA(cudaDeviceGetAttribute(&t->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
   *out = t;
   return 0;
 }
@@ -1200,8 +1229,16 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
     EMD_CUDA(cudaMemcpyAsync(t->d_tab, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
     EMD_CUDA(cudaStreamSynchronize(ctx->stream)); // h is a stack object
   }
-  const size_t smem = force_smem(a.cap, !one);
-  if (smem > (size_t)t->max_smem_optin) { set_error("emd_force_lj_compute_tiles: tile does not fit in shared memory"); return 1; }
+  const size_t base_smem = force_smem(a.cap, !one);
+  if (base_smem > (size_t)t->max_smem_optin) { set_error("emd_force_lj_compute_tiles: tile does not fit in shared memory"); return 1; }
+  // the ELL ring (16 bytes per thread) only if two CTAs still fit on one SM (1 KB per CTA is reserved by the system).
+  // Measured at 2 M atoms (gpurun r01t): the ring halves the long-scoreboard stalls (18 % -> 10 % of samples) but the
+  // per-iteration cp.async wait and the extra LDS.128 cost more than that buys: 0.386 ms against 0.367 ms with the L1
+  // prefetch.  Off unless EMD_TILES_RING=1.
+  const bool ring_allowed = getenv("EMD_TILES_RING") && atoi(getenv("EMD_TILES_RING"));
+  const size_t ring_smem = base_smem + (size_t)kForceThreads * sizeof(uint4);
+  const bool ring = ring_allowed && 2 * (ring_smem + 1024) <= (size_t)t->max_smem_sm && 2 * (base_smem + 1024) <= (size_t)t->max_smem_sm;
+  const size_t smem = ring ? ring_smem : base_smem;
   const int first = part == 2 ? t->n_free_tiles : 0;
   const int count = part == 0 ? t->ntiles : part == 1 ? t->n_free_tiles : t->ntiles - t->n_free_tiles;
   if (count <= 0) return 0;
@@ -1211,13 +1248,16 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
     if (ctx->s_c.ensure(sizeof(double) * ((size_t)grid + 8))) return 1;
     partial = ctx->s_c.as<double>() + 8;
   }
-#define EMD_LJ_TILES(ONE, EN)                                                                                              \
+#define EMD_LJ_TILES(ONE, EN, RG)                                                                                          \
   do {                                                                                                                     \
-    if (set_smem(lj_tiles_kernel<ONE, EN>, smem)) return 1;                                                                \
-    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN>), grid, kForceThreads, smem, a, first, count, p1, t->d_tab, d_f, partial);   \
+    if (set_smem(lj_tiles_kernel<ONE, EN, RG>, smem)) return 1;                                                            \
+    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN, RG>), grid, kForceThreads, smem, a, first, count, p1, t->d_tab, d_f, partial, \
+               (unsigned)base_smem);                                                                                       \
   } while (0)
-  if (h_pe) { if (one) EMD_LJ_TILES(true, true); else EMD_LJ_TILES(false, true); }
-  else { if (one) EMD_LJ_TILES(true, false); else EMD_LJ_TILES(false, false); }
+#define EMD_LJ_TILES2(ONE, EN) do { if (ring) EMD_LJ_TILES(ONE, EN, true); else EMD_LJ_TILES(ONE, EN, false); } while (0)
+  if (h_pe) { if (one) EMD_LJ_TILES2(true, true); else EMD_LJ_TILES2(false, true); }
+  else { if (one) EMD_LJ_TILES2(true, false); else EMD_LJ_TILES2(false, false); }
+#undef EMD_LJ_TILES2
 #undef EMD_LJ_TILES
   if (h_pe) return device_sum_partials(ctx, partial, grid, h_pe);
   return 0;
