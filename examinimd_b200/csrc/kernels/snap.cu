@@ -333,23 +333,36 @@ __device__ __forceinline__ void z_block(const double2 *__restrict__ U, const Sna
     double sr[NMB], si[NMB];
 #pragma unroll
     for (int k = 0; k < NMB; k++) { sr[k] = 0.0; si[k] = 0.0; }
+    // ncu (profiles/r01e_snap_ncu.csv, source page) puts 20 % of the kernel's stall samples on `pc += j2` (short scoreboard:
+    // the bump waits until the indexed constant loads of the step before have read their address register) and 8 % on the
+    // first use of `a`.  One address register per unrolled step (pcs[r], bumped once per group of NMB steps) and a one-step
+    // look-ahead for `a` (the element after the last one of a row is read and never used; sU carries a pad for the very
+    // last row) bought only 1.5 % (10.83 -> 10.67 ms at 250 000 atoms, gpurun r01v): the stall moves, the 4 warps per
+    // scheduler that 146 KB of U_tot and 128 registers allow cannot hide it.
+    double2 a_next = *r1;
     for (int mb1 = lo1; mb1 <= hi1; mb1 += NMB) {
+      const double *pcs[NMB];
+#pragma unroll
+      for (int r = 0; r < NMB; r++) pcs[r] = pc + r * j2;
 #pragma unroll
       for (int r = 0; r < NMB; r++) {
         if (mb1 + r <= hi1) {
-          const double2 a = *r1;
+          const double2 a = a_next;
+          r1 += 32;
+          a_next = *r1;
 #pragma unroll
           for (int k = 0; k < NMB; k++) {
             const double2 wk = w[(k - r + NMB) % NMB];
-            const double c = pc[k];
+            const double c = pcs[r][k];
             sr[k] += c * (a.x * wk.x - a.y * wk.y);
             si[k] += c * (a.x * wk.y + a.y * wk.x);
           }
           // the slot of output NMB-1 is free now: it receives the element output 0 needs at the next step
           w[(NMB - 1 - r + NMB) % NMB] = (nb2 >= 0 && nb2 <= j2) ? *r2n : make_double2(0.0, 0.0);
-          r1 += 32; r2n -= 32; nb2--; pc += j2;
+          r2n -= 32; nb2--;
         }
       }
+      pc += NMB * j2;
     }
 #pragma unroll
     for (int k = 0; k < NMB; k++) { zr[k] += cga * sr[k]; zi[k] += cga * si[k]; }
@@ -574,7 +587,7 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
 }
 
 size_t ui_smem(const SnapTab &h) { return ((size_t)h.nuh * 32 + (size_t)kMaxJ * 32 * h.ncol) * sizeof(double2); }
-size_t yi_smem(const SnapTab &h) { return (size_t)h.nuf * 32 * sizeof(double2); }
+size_t yi_smem(const SnapTab &h) { return ((size_t)h.nuf + 8) * 32 * sizeof(double2); } // + pad: z_block prefetches one element past a row
 size_t de_smem(const SnapTab &h) { return ((size_t)kMaxJ * 4 * kDeThreads + (size_t)kDeStageAtoms * h.nuh) * sizeof(double2); }
 
 } // namespace

@@ -61,6 +61,23 @@ def test_100_steps_vs_oracle(emd, neigh, iteration):
     app.close(); md.close()
 
 
+def test_fused_integrator_is_bit_identical(emd):
+    """advance(n) folds final_integrate of a step and initial_integrate of the next into one kernel
+    (Integrator::final_initial_integrate); advance(1) n times never does: x, v, f must agree bit for bit, across a
+    re-neighboring, and the launch count must show the fusion"""
+    argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--comm-type", "SERIAL", "--region", "12", "12", "12"]
+    a, b = emd.App(argv), emd.App(argv)
+    la, lb = a.launches(), b.launches()
+    a.advance(45)
+    for _ in range(45):
+        b.advance(1)
+    sa, sb = a.download(), b.download()
+    for k in ("id", "x", "v", "f"):
+        np.testing.assert_array_equal(sa[k], sb[k])
+    assert (b.launches() - lb) - (a.launches() - la) == 44  # one kernel less per fused step boundary
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("no_tiles", ["0", "1"])
 def test_binary_dump_and_correctness_flags(emd, tmp_path, no_tiles):
     """the ExaMiniMD executable with the reference's own record/replay flags (README.md:99-107); once on the
