@@ -192,13 +192,19 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
     if (tm) tm->end(PhaseTimers::COMM);
   }
 
+  bool kicked = false; // the force launch already applied final_integrate + the next initial_integrate
   if (split) {
     force->compute_part(system, binning, neighbor, 2);
     if (emd_ctx_side_join(system->ctx)) comm->error(emd_last_error());
   } else {
-    if (!force->zeroes_forces())
-      emd_memset_zero(system->ctx, system->f, sizeof(T_F_FLOAT) * 3 * (size_t)system->N_max);
-    force->compute(system, binning, neighbor);
+    T_V_FLOAT dtf = 0.0, dtv = 0.0;
+    if (fuse_next && fuse_nve && !input->comm_newton && integrator->step_factors(&dtf, &dtv))
+      kicked = force->compute_with_nve(system, binning, neighbor, dtf, dtv);
+    if (!kicked) {
+      if (!force->zeroes_forces())
+        emd_memset_zero(system->ctx, system->f, sizeof(T_F_FLOAT) * 3 * (size_t)system->N_max);
+      force->compute(system, binning, neighbor);
+    }
   }
   if (tm) tm->end(PhaseTimers::FORCE);
 
@@ -207,7 +213,8 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
     if (tm) tm->end(PhaseTimers::COMM);
   }
 
-  if (fuse_next && fuse_nve) { integrator->final_initial_integrate(); initial_done = true; }
+  if (kicked) initial_done = true;
+  else if (fuse_next && fuse_nve) { integrator->final_initial_integrate(); initial_done = true; }
   else integrator->final_integrate();
   if (tm) tm->end(PhaseTimers::OTHER);
 }

@@ -19,6 +19,10 @@ public:
   // Optional split of compute() for decomposed runs (not in the reference): part 1 = the share that reads no ghost atom
   // (the driver runs it on the context's side stream while Comm::update_halo is in flight), part 2 = the rest; the two
   // parts together equal compute().  A module that cannot split inherits `false` and the driver calls compute().
+  // Optional: compute() and, in the same pass over the atoms, Integrator::final_integrate of this step + initial_integrate of
+  // the next with the given factors (v += dtf/m f twice, x += dtv v); the module publishes the new positions itself.  The
+  // driver offers it between two unobserved steps; a module that cannot do it returns false and nothing has happened.
+  virtual bool compute_with_nve(System *system, Binning *binning, Neighbor *neigh, T_V_FLOAT dtf, T_V_FLOAT dtv) { return false; }
   virtual bool can_split(System *system, Neighbor *neigh) { return false; }
   virtual void compute_part(System *system, Binning *binning, Neighbor *neigh, int part) {}
   virtual const char *name() { return "ForceNone"; }

@@ -49,6 +49,20 @@ void ForceLJNeigh::compute(System *system, Binning *, Neighbor *neighbor) {
     fail("compute");
 }
 
+// compute() + final_integrate + next initial_integrate in one launch (force.h): tile path only; the kernel reads the old
+// positions of every staged atom, so the advanced positions go to the System's second position array, published here
+bool ForceLJNeigh::compute_with_nve(System *system, Binning *, Neighbor *neighbor, T_V_FLOAT dtf, T_V_FLOAT dtv) {
+  static const bool off = getenv("EMD_NO_FUSED_FORCE_NVE") && atoi(getenv("EMD_NO_FUSED_FORCE_NVE"));
+  emd_tiles *t = neighbor->tiles();
+  if (off || !t || comm_newton || !system->x_alt) return false;
+  const int rc = emd_force_lj_compute_tiles_nve(system->ctx, t, system->x, system->type, system->f, system->v, system->x_alt, system->mass,
+                                                dtf, dtv);
+  if (rc == 3) return false; // an owned atom without a row: separate kernels
+  if (rc) fail("compute_with_nve (tiles)");
+  system->swap_x();
+  return true;
+}
+
 // compute() in two launches for a decomposed run (force.h): the tile lists know which tiles read ghost atoms
 bool ForceLJNeigh::can_split(System *, Neighbor *neighbor) {
   emd_tiles *t = neighbor->tiles();

@@ -31,6 +31,7 @@ public:
   void compute(System *system, Binning *binning, Neighbor *neighbor);
   T_F_FLOAT compute_energy(System *system, Binning *binning, Neighbor *neighbor);
   bool zeroes_forces() const { return true; }
+  bool compute_with_nve(System *system, Binning *binning, Neighbor *neighbor, T_V_FLOAT dtf, T_V_FLOAT dtv);
   bool can_split(System *system, Neighbor *neighbor);
   void compute_part(System *system, Binning *binning, Neighbor *neighbor, int part);
   const char *name();

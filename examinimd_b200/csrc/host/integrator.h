@@ -14,6 +14,9 @@ public:
   // final_integrate() immediately followed by the next step's initial_integrate() (not in the reference; the driver calls
   // it when nothing observes the state between two steps).  Default: the two calls.
   virtual void final_initial_integrate() { final_integrate(); initial_integrate(); }
+  // the two factors of a plain velocity-Verlet step (v += dtf/m f, x += dtv v), for Force::compute_with_nve; an integrator
+  // that is not of that form returns false
+  virtual bool step_factors(T_V_FLOAT *dtf, T_V_FLOAT *dtv) { return false; }
   virtual const char *name() { return "IntegratorNone"; }
 };
 

@@ -12,6 +12,7 @@ public:
   void initial_integrate() override;        // emd_nve_initial_integrate:       v += dtf/m f ; x += dtv v
   void final_integrate() override;          // emd_nve_final_integrate:         v += dtf/m f
   void final_initial_integrate() override;  // emd_nve_final_initial_integrate: both, one pass over the atoms
+  bool step_factors(T_V_FLOAT *dtf_, T_V_FLOAT *dtv_) override { *dtf_ = dtf; *dtv_ = dtv; return true; }
   const char *name() override;
 
 private:

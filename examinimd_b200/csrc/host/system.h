@@ -56,6 +56,7 @@ public:
   // sort destination buffers (same capacity as the primary ones) and the swap that publishes them
   t_x x_alt; t_v v_alt; t_f f_alt; t_type type_alt; t_id id_alt; t_q q_alt;
   void swap_sorted();
+  void swap_x() { t_x t = x; x = x_alt; x_alt = t; } // a kernel wrote the advanced positions of the owned atoms to x_alt
 
   // host <-> device staging of atoms [0,n)
   void upload(const HostAtoms &h, T_INT n, bool with_f);

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_tables_kernel(TileArgs a
   if (t.total > a.cap || t.n_int > a.stride) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   if (threadIdx.x == 0) a.stg_n[t.tile] = t.total;
-  int ghost = 0;
+  int ghost = 0, owned_rows = 0;
   for (int c = warp; c < t.ncs; c += nwarps) {
     const int base = s_start[c], n = s_start[c + 1] - base, goff = s_goff[c];
     for (int k = lane; k < n; k += 32) {
@@ -285,10 +285,17 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_tables_kernel(TileArgs a
     if (n == 0) continue;
     const int c = staged_of_interior(t, a, ci);
     for (int k = lane; k < n; k += 32) {
+      const int ig = a.permute[s_goff[c] + k];
       a.int_slot[(size_t)t.tile * a.stride + s_ibase[ci] + k] = (unsigned short)(s_start[c] + k);
-      a.int_glob[(size_t)t.tile * a.stride + s_ibase[ci] + k] = a.permute[s_goff[c] + k];
+      a.int_glob[(size_t)t.tile * a.stride + s_ibase[ci] + k] = ig;
+      owned_rows += (ig < a.n_local);
     }
   }
+  // flags[4]: owned atoms that have a row (= n_local unless an owned atom sits outside the interior bins, which the
+  // reference leaves without neighbors, neighbor_csr.h:184; the fused force + integrator launch requires equality)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) owned_rows += __shfl_down_sync(0xffffffffu, owned_rows, o);
+  if (lane == 0 && owned_rows) atomicAdd(&a.flags[4], owned_rows);
 }
 
 // order[]: halo-independent tiles first, then the others, each group in tile order.  One block: every thread owns a
@@ -797,9 +804,16 @@ constexpr int kStagePerThread = 8; // cap <= kForceThreads * kStagePerThread
 // budget -- the request really is issued a whole 8-pair iteration before its use); word 0 of the next tile's row is
 // requested during the last iteration of the current one.  Needs two CTAs to still fit on an SM with the extra 6 KB.
 // An experiment that did not pay (see lj_tiles_launch): kept behind EMD_TILES_RING=1.
-template <bool ONETYPE, bool ENERGY, bool RING>
+// FUSE: the epilogue also applies IntegratorNVE::final_integrate of this step and initial_integrate of the next one to the
+// atom whose force was just accumulated (src/integrator_nve.cpp:47-74, 87-112: same operations, same order, so v and x are
+// bit-identical to the separate kernels): v is updated in place, the new position goes to a SECOND position array because
+// other CTAs still stage the old coordinates (the host swaps the two arrays after the launch).
+struct NveFuse { double *v; double *x_new; const double *mass; double dtf, dtv; };
+
+template <bool ONETYPE, bool ENERGY, bool RING, bool FUSE>
 __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, LJOne one, const LJTab *__restrict__ tab,
-                                                                   double *__restrict__ f, double *__restrict__ pe_partial, unsigned ring_offset) {
+                                                                   double *__restrict__ f, double *__restrict__ pe_partial, unsigned ring_offset,
+                                                                   NveFuse nve) {
   __shared__ double s_red[kForceThreads / 32];
   extern __shared__ __align__(16) unsigned char dyn[];
   double *const sp0 = reinterpret_cast<double *>(dyn); // 2 x [cap][3]: x,y,z of a staged atom adjacent (one address computation per pair)
@@ -898,6 +912,19 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
         }
       }
       if (!ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
+      if (FUSE) {
+        const double dtfm = nve.dtf / nve.mass[ONETYPE ? a.type[i_cur] : type_i]; // integrator_nve.cpp:67,106
+        double *vp = nve.v + 3 * (size_t)i_cur, *xp = nve.x_new + 3 * (size_t)i_cur;
+        const double fi[3] = {fx, fy, fz}, xi[3] = {x_i, y_i, z_i};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          const double kick = __dmul_rn(dtfm, fi[d]);
+          const double v1 = __dadd_rn(vp[d], kick);            // final_integrate :107-109
+          const double v2 = __dadd_rn(v1, kick);               // initial_integrate of the next step :68-70
+          vp[d] = v2;
+          xp[d] = __dadd_rn(xi[d], __dmul_rn(nve.dtv, v2));    // :71-73
+        }
+      }
     }
     if (RING && !(i_cur < a.n_local && n_cur > 0) && tile_nxt >= 0 && i_nxt < a.n_local && n_nxt > 0)
       cp_async16(ering, row_of_tile(tile_nxt)); // no row here, one in the next tile: its word 0
@@ -940,6 +967,7 @@ struct emd_tiles {
   int *d_order = nullptr; size_t order_cap = 0;
   int *d_has_ghost = nullptr; size_t has_ghost_cap = 0;
   int n_free_tiles = 0;  // tiles that do not read the halo (first in d_order)
+  bool all_owned_have_rows = false; // every owned atom is listed (precondition of the fused force + integrator launch)
   int *d_flags = nullptr;
   int num_sms = 148;
   LJTab *d_tab = nullptr;
@@ -976,7 +1004,7 @@ int emd_tiles_create(emd_tiles **out) {
   if (!out) { set_error("emd_tiles_create: out == NULL"); return 1; }
   emd_tiles *t = new emd_tiles();
   memset(&t->a, 0, sizeof t->a);
-  EMD_CUDA(cudaMalloc((void **)&t->d_flags, 4 * sizeof(int)));
+  EMD_CUDA(cudaMalloc((void **)&t->d_flags, 8 * sizeof(int)));
   EMD_CUDA(cudaMalloc((void **)&t->d_tab, sizeof(LJTab)));
   int dev = 0;
   EMD_CUDA(cudaGetDevice(&dev));
@@ -1105,6 +1133,7 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
       if (ensure_bytes((void **)&t->d_has_ghost, &t->has_ghost_cap, (size_t)t->ntiles * sizeof(int))) return 1;
       a.stg_j = t->d_stg_j; a.stg_n = t->d_stg_n; a.int_slot = t->d_int_slot; a.int_glob = t->d_int_glob;
       a.order = t->d_order; a.has_ghost = t->d_has_ghost;
+      EMD_CUDA(cudaMemsetAsync(t->d_flags + 4, 0, 4 * sizeof(int), ctx->stream));
       EMD_LAUNCH(ctx, tiles_tables_kernel, t->ntiles, kFilterThreads, 0, a);
       // the force kernel's copy of the adjacency: bank-conflict-free columns (tiles_schedule_kernel)
       if (ensure_bytes((void **)&t->d_nell_s, &t->nell_s_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
@@ -1136,9 +1165,14 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
         } else if (mode == SCHED_FULL) EMD_SCHED(SCHED_FULL);
         else EMD_SCHED(SCHED_NONE);
 #undef EMD_SCHED
-        EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         EMD_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (!(ctx->h_pinned[0] & 8)) { t->n_free_tiles = ctx->h_pinned[2]; t->valid = true; return 0; }
+        if (!(ctx->h_pinned[0] & 8)) {
+          t->n_free_tiles = ctx->h_pinned[2];
+          t->all_owned_have_rows = ctx->h_pinned[4] == n_local;
+          t->valid = true;
+          return 0;
+        }
         maxrow_s = (ctx->h_pinned[1] + ctx->h_pinned[1] / 8 + 15) / 8 * 8;
       }
       return 3;
@@ -1214,10 +1248,12 @@ int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half, int newton, in
 // this step has landed); 2 = the rest.  reserve_ctas > 0 leaves that many CTA slots of the persistent grid free, so that
 // the pack and NCCL kernels of a concurrent halo exchange find room on the SMs.
 static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe, int part,
-                           int reserve_ctas) {
+                           int reserve_ctas, const NveFuse *fuse = nullptr) {
   if (!t || !t->valid) { set_error("emd_force_lj_compute_tiles: tiles not built"); return 1; }
   if (ctx->lj.ntypes == 0) { set_error("emd_force_lj_compute_tiles: parameters not set"); return 1; }
   if (part < 0 || part > 2 || (h_pe && part != 0)) { set_error("emd_force_lj_compute_tiles: bad part"); return 1; }
+  if (fuse && (h_pe || part != 0)) { set_error("emd_force_lj_compute_tiles: the fused integrator needs the whole force in one launch"); return 1; }
+  const NveFuse nve = fuse ? *fuse : NveFuse{nullptr, nullptr, nullptr, 0.0, 0.0};
   TileArgs a = t->a;
   a.x = d_x; a.type = d_type;
   const bool one = ctx->lj.ntypes == 1;
@@ -1237,7 +1273,7 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
   // prefetch.  Off unless EMD_TILES_RING=1.
   const bool ring_allowed = getenv("EMD_TILES_RING") && atoi(getenv("EMD_TILES_RING"));
   const size_t ring_smem = base_smem + (size_t)kForceThreads * sizeof(uint4);
-  const bool ring = ring_allowed && 2 * (ring_smem + 1024) <= (size_t)t->max_smem_sm && 2 * (base_smem + 1024) <= (size_t)t->max_smem_sm;
+  const bool ring = !fuse && ring_allowed && 2 * (ring_smem + 1024) <= (size_t)t->max_smem_sm && 2 * (base_smem + 1024) <= (size_t)t->max_smem_sm;
   const size_t smem = ring ? ring_smem : base_smem;
   const int first = part == 2 ? t->n_free_tiles : 0;
   const int count = part == 0 ? t->ntiles : part == 1 ? t->n_free_tiles : t->ntiles - t->n_free_tiles;
@@ -1248,14 +1284,15 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
     if (ctx->s_c.ensure(sizeof(double) * ((size_t)grid + 8))) return 1;
     partial = ctx->s_c.as<double>() + 8;
   }
-#define EMD_LJ_TILES(ONE, EN, RG)                                                                                          \
+#define EMD_LJ_TILES(ONE, EN, RG, FU)                                                                                      \
   do {                                                                                                                     \
-    if (set_smem(lj_tiles_kernel<ONE, EN, RG>, smem)) return 1;                                                            \
-    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN, RG>), grid, kForceThreads, smem, a, first, count, p1, t->d_tab, d_f, partial, \
-               (unsigned)base_smem);                                                                                       \
+    if (set_smem(lj_tiles_kernel<ONE, EN, RG, FU>, smem)) return 1;                                                        \
+    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN, RG, FU>), grid, kForceThreads, smem, a, first, count, p1, t->d_tab, d_f,     \
+               partial, (unsigned)base_smem, nve);                                                                         \
   } while (0)
-#define EMD_LJ_TILES2(ONE, EN) do { if (ring) EMD_LJ_TILES(ONE, EN, true); else EMD_LJ_TILES(ONE, EN, false); } while (0)
-  if (h_pe) { if (one) EMD_LJ_TILES2(true, true); else EMD_LJ_TILES2(false, true); }
+#define EMD_LJ_TILES2(ONE, EN) do { if (ring) EMD_LJ_TILES(ONE, EN, true, false); else EMD_LJ_TILES(ONE, EN, false, false); } while (0)
+  if (fuse) { if (one) EMD_LJ_TILES(true, false, false, true); else EMD_LJ_TILES(false, false, false, true); }
+  else if (h_pe) { if (one) EMD_LJ_TILES2(true, true); else EMD_LJ_TILES2(false, true); }
   else { if (one) EMD_LJ_TILES2(true, false); else EMD_LJ_TILES2(false, false); }
 #undef EMD_LJ_TILES2
 #undef EMD_LJ_TILES
@@ -1270,6 +1307,14 @@ int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, co
 int emd_force_lj_compute_tiles_part(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, int part,
                                     int reserve_ctas) {
   return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, part, reserve_ctas);
+}
+
+int emd_force_lj_compute_tiles_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *d_v,
+                                   double *d_x_new, const double *d_mass, double dtf, double dtv) {
+  if (t && t->valid && !t->all_owned_have_rows) return 3; // an owned atom has no row: its position would not be advanced
+  if (!d_v || !d_x_new || !d_mass || d_x_new == d_x) { set_error("emd_force_lj_compute_tiles_nve: v, mass and a second position array are required"); return 1; }
+  const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv};
+  return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, 0, 0, &nve);
 }
 
 int emd_tiles_halo_split(const emd_tiles *t, int *n_free, int *n_halo) {

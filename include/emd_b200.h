@@ -186,6 +186,13 @@ int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, co
 int emd_force_lj_compute_tiles_part(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type,
                                     double *d_f, int part, int reserve_ctas);
 int emd_tiles_halo_split(const emd_tiles *t, int *n_free_tiles, int *n_halo_tiles);
+/* ForceLJNeigh::compute followed, per owned atom and in the same launch, by IntegratorNVE::final_integrate of this step and
+ * initial_integrate of the next (src/integrator_nve.cpp:77-83,115-121; legal when nothing observes x, v, f between the two
+ * steps): d_f and d_v are updated as by the separate calls, the advanced positions are written to d_x_new (rows [0,n_local));
+ * d_x is left untouched -- the caller publishes d_x_new as the position array afterwards.  Bit-identical to the three calls.
+ * Returns 3 (nothing done) if an owned atom has no row in the tile lists (it sits outside the interior bins). */
+int emd_force_lj_compute_tiles_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f,
+                                   double *d_v, double *d_x_new, const double *d_mass, double dtf, double dtv);
 
 /* ---- SNAP force: ForceSNAP<> + SNA, src/force_types/force_snap_neigh_impl.h, sna_impl.hpp ------- */
 /* What init_coeff/read_files (force_snap_neigh_impl.h:227-336, 340-587) leave behind, as plain values.

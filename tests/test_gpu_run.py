@@ -62,8 +62,8 @@ def test_100_steps_vs_oracle(emd, neigh, iteration):
 
 
 def test_fused_integrator_is_bit_identical(emd):
-    """advance(n) folds final_integrate of a step and initial_integrate of the next into one kernel
-    (Integrator::final_initial_integrate); advance(1) n times never does: x, v, f must agree bit for bit, across a
+    """advance(n) folds final_integrate of a step and initial_integrate of the next into the force launch
+    (Force::compute_with_nve) or into one kernel (Integrator::final_initial_integrate); advance(1) n times never does: x, v, f must agree bit for bit, across a
     re-neighboring, and the launch count must show the fusion"""
     argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--comm-type", "SERIAL", "--region", "12", "12", "12"]
     a, b = emd.App(argv), emd.App(argv)
@@ -74,7 +74,9 @@ def test_fused_integrator_is_bit_identical(emd):
     sa, sb = a.download(), b.download()
     for k in ("id", "x", "v", "f"):
         np.testing.assert_array_equal(sa[k], sb[k])
-    assert (b.launches() - lb) - (a.launches() - la) == 44  # one kernel less per fused step boundary
+    # per fused step boundary: the two integrator kernels disappear into the force launch (88), or -- when the force module
+    # cannot take the integrator along -- become one kernel (44)
+    assert (b.launches() - lb) - (a.launches() - la) in (44, 88)
     a.close(); b.close()
 
 
