@@ -155,7 +155,8 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
   const T_F_FLOAT neigh_cutoff = input->force_cutoff + input->neighbor_skin;
   static const bool overlap_halo = !(getenv("EMD_NO_OVERLAP") && atoi(getenv("EMD_NO_OVERLAP")));
   static const bool comm_first = !(getenv("EMD_OVERLAP_ORDER") && atoi(getenv("EMD_OVERLAP_ORDER")) == 0);
-  bool split = false;
+  bool split = false, split_kick = false;
+  T_V_FLOAT nve_factors[2] = {0.0, 0.0};
   static const bool fuse_nve = !(getenv("EMD_NO_FUSED_NVE") && atoi(getenv("EMD_NO_FUSED_NVE")));
   if (tm) tm->begin();
   if (!initial_done) integrator->initial_integrate();
@@ -176,17 +177,20 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
     // decomposed run: the share of the force that reads no ghost atom starts now, on the side stream, and overlaps the
     // halo exchange (the reference's blocking sequence update_halo -> compute, examinimd.cpp:226-235, otherwise)
     split = overlap_halo && comm->num_processes() > 1 && force->can_split(system, neighbor);
+    // the split force can take the integrator kick along like the single launch (Force::compute_with_nve)
+    split_kick = split && fuse_next && fuse_nve && !input->comm_newton && integrator->step_factors(&nve_factors[0], &nve_factors[1]) &&
+                 force->can_kick(system, neighbor);
     // the exchange's kernels are enqueued first (they find the SMs free); the side stream forks from the point before them
     if (split && emd_ctx_side_mark(system->ctx)) comm->error(emd_last_error());
     if (split && !comm_first) {
       if (emd_ctx_side_begin(system->ctx)) comm->error(emd_last_error());
-      force->compute_part(system, binning, neighbor, 1);
+      force->compute_part(system, binning, neighbor, 1, split_kick ? nve_factors : nullptr);
       if (emd_ctx_side_end(system->ctx)) comm->error(emd_last_error());
     }
     comm->update_halo();
     if (split && comm_first) {
       if (emd_ctx_side_begin(system->ctx)) comm->error(emd_last_error());
-      force->compute_part(system, binning, neighbor, 1);
+      force->compute_part(system, binning, neighbor, 1, split_kick ? nve_factors : nullptr);
       if (emd_ctx_side_end(system->ctx)) comm->error(emd_last_error());
     }
     if (tm) tm->end(PhaseTimers::COMM);
@@ -194,8 +198,9 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
 
   bool kicked = false; // the force launch already applied final_integrate + the next initial_integrate
   if (split) {
-    force->compute_part(system, binning, neighbor, 2);
+    force->compute_part(system, binning, neighbor, 2, split_kick ? nve_factors : nullptr);
     if (emd_ctx_side_join(system->ctx)) comm->error(emd_last_error());
+    kicked = split_kick;
   } else {
     T_V_FLOAT dtf = 0.0, dtv = 0.0;
     if (fuse_next && fuse_nve && !input->comm_newton && integrator->step_factors(&dtf, &dtv))

@@ -24,7 +24,10 @@ public:
   // driver offers it between two unobserved steps; a module that cannot do it returns false and nothing has happened.
   virtual bool compute_with_nve(System *system, Binning *binning, Neighbor *neigh, T_V_FLOAT dtf, T_V_FLOAT dtv) { return false; }
   virtual bool can_split(System *system, Neighbor *neigh) { return false; }
-  virtual void compute_part(System *system, Binning *binning, Neighbor *neigh, int part) {}
+  // nve != nullptr: {dtf, dtv}; the part also carries the integrator kick as compute_with_nve does (only offered when
+  // can_kick() said so); part 2 then publishes the new positions
+  virtual void compute_part(System *system, Binning *binning, Neighbor *neigh, int part, const T_V_FLOAT *nve = nullptr) {}
+  virtual bool can_kick(System *system, Neighbor *neigh) { return false; }
   virtual const char *name() { return "ForceNone"; }
 };
 

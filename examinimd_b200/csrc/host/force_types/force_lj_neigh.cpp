@@ -71,9 +71,23 @@ bool ForceLJNeigh::can_split(System *, Neighbor *neighbor) {
   return n_free > 0 && n_halo > 0;
 }
 
-void ForceLJNeigh::compute_part(System *system, Binning *, Neighbor *neighbor, int part) {
+bool ForceLJNeigh::can_kick(System *system, Neighbor *neighbor) {
+  static const bool off = getenv("EMD_NO_FUSED_FORCE_NVE") && atoi(getenv("EMD_NO_FUSED_FORCE_NVE"));
+  emd_tiles *t = neighbor->tiles();
+  int lists_complete = 0;
+  return !off && t && !comm_newton && system->x_alt && !emd_tiles_complete(t, &lists_complete) && lists_complete;
+}
+
+void ForceLJNeigh::compute_part(System *system, Binning *, Neighbor *neighbor, int part, const T_V_FLOAT *nve) {
   static const int reserve = getenv("EMD_OVERLAP_RESERVE") ? atoi(getenv("EMD_OVERLAP_RESERVE")) : 0;
   // part 1 runs on the side stream's SM partition (ctx.cu); EMD_OVERLAP_RESERVE additionally leaves CTA slots free
+  if (nve) {
+    if (emd_force_lj_compute_tiles_part_nve(system->ctx, neighbor->tiles(), system->x, system->type, system->f, part, part == 1 ? reserve : 0,
+                                            system->v, system->x_alt, system->mass, nve[0], nve[1]))
+      fail("compute_part + nve (tiles)");
+    if (part == 2) system->swap_x(); // host pointers only: part 1 may still be running on the old array, which stays alive
+    return;
+  }
   if (emd_force_lj_compute_tiles_part(system->ctx, neighbor->tiles(), system->x, system->type, system->f, part, part == 1 ? reserve : 0))
     fail("compute_part (tiles)");
 }

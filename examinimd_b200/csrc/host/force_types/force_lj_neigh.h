@@ -33,7 +33,8 @@ public:
   bool zeroes_forces() const { return true; }
   bool compute_with_nve(System *system, Binning *binning, Neighbor *neighbor, T_V_FLOAT dtf, T_V_FLOAT dtv);
   bool can_split(System *system, Neighbor *neighbor);
-  void compute_part(System *system, Binning *binning, Neighbor *neighbor, int part);
+  void compute_part(System *system, Binning *binning, Neighbor *neighbor, int part, const T_V_FLOAT *nve = nullptr);
+  bool can_kick(System *system, Neighbor *neighbor);
   const char *name();
 };
 #endif

@@ -1252,7 +1252,7 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
   if (!t || !t->valid) { set_error("emd_force_lj_compute_tiles: tiles not built"); return 1; }
   if (ctx->lj.ntypes == 0) { set_error("emd_force_lj_compute_tiles: parameters not set"); return 1; }
   if (part < 0 || part > 2 || (h_pe && part != 0)) { set_error("emd_force_lj_compute_tiles: bad part"); return 1; }
-  if (fuse && (h_pe || part != 0)) { set_error("emd_force_lj_compute_tiles: the fused integrator needs the whole force in one launch"); return 1; }
+  if (fuse && h_pe) { set_error("emd_force_lj_compute_tiles: the energy launch cannot carry the integrator"); return 1; }
   const NveFuse nve = fuse ? *fuse : NveFuse{nullptr, nullptr, nullptr, 0.0, 0.0};
   TileArgs a = t->a;
   a.x = d_x; a.type = d_type;
@@ -1315,6 +1315,20 @@ int emd_force_lj_compute_tiles_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x
   if (!d_v || !d_x_new || !d_mass || d_x_new == d_x) { set_error("emd_force_lj_compute_tiles_nve: v, mass and a second position array are required"); return 1; }
   const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv};
   return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, 0, 0, &nve);
+}
+
+int emd_force_lj_compute_tiles_part_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, int part,
+                                        int reserve_ctas, double *d_v, double *d_x_new, const double *d_mass, double dtf, double dtv) {
+  if (t && t->valid && !t->all_owned_have_rows) return 3;
+  if (!d_v || !d_x_new || !d_mass || d_x_new == d_x) { set_error("emd_force_lj_compute_tiles_part_nve: v, mass and a second position array are required"); return 1; }
+  const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv};
+  return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, part, reserve_ctas, &nve);
+}
+
+int emd_tiles_complete(const emd_tiles *t, int *all_owned_have_rows) {
+  if (!t || !t->valid) { set_error("emd_tiles_complete: tiles not built"); return 1; }
+  if (all_owned_have_rows) *all_owned_have_rows = t->all_owned_have_rows ? 1 : 0;
+  return 0;
 }
 
 int emd_tiles_halo_split(const emd_tiles *t, int *n_free, int *n_halo) {

@@ -186,6 +186,8 @@ int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, co
 int emd_force_lj_compute_tiles_part(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type,
                                     double *d_f, int part, int reserve_ctas);
 int emd_tiles_halo_split(const emd_tiles *t, int *n_free_tiles, int *n_halo_tiles);
+/* 1 if every owned atom has a row in the tile lists (precondition of the *_nve launches) */
+int emd_tiles_complete(const emd_tiles *t, int *all_owned_have_rows);
 /* ForceLJNeigh::compute followed, per owned atom and in the same launch, by IntegratorNVE::final_integrate of this step and
  * initial_integrate of the next (src/integrator_nve.cpp:77-83,115-121; legal when nothing observes x, v, f between the two
  * steps): d_f and d_v are updated as by the separate calls, the advanced positions are written to d_x_new (rows [0,n_local));
@@ -193,6 +195,10 @@ int emd_tiles_halo_split(const emd_tiles *t, int *n_free_tiles, int *n_halo_tile
  * Returns 3 (nothing done) if an owned atom has no row in the tile lists (it sits outside the interior bins). */
 int emd_force_lj_compute_tiles_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f,
                                    double *d_v, double *d_x_new, const double *d_mass, double dtf, double dtv);
+/* the same for one part of a split force (emd_force_lj_compute_tiles_part): every owned atom belongs to exactly one part */
+int emd_force_lj_compute_tiles_part_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f,
+                                        int part, int reserve_ctas, double *d_v, double *d_x_new, const double *d_mass,
+                                        double dtf, double dtv);
 
 /* ---- SNAP force: ForceSNAP<> + SNA, src/force_types/force_snap_neigh_impl.h, sna_impl.hpp ------- */
 /* What init_coeff/read_files (force_snap_neigh_impl.h:227-336, 340-587) leave behind, as plain values.
