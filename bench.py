@@ -240,8 +240,8 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--region", type=int, nargs=3, default=None, help="override the lattice (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -307,13 +307,15 @@ def main():
             dist.barrier()
 
     # ---- resident throughput ------------------------------------------------------------
+    # nvidia-smi needs ~0.1 s to deliver its first sample: it is started before the warm-up so that its samples cover the
+    # timed region (both run the same steps under the same load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     app.advance(W)
     # land on a step just after a re-neighboring so K steps hold K/20 rebuilds
     rate = app.get("exchange_rate")
     app.advance((-app.get("step")) % rate)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = app.launches()
     ms = C.c_float()
     emd.check(L.emd_ctx_tic(ctx))
