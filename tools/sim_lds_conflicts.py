@@ -19,7 +19,9 @@ def main(region=(20, 20, 20), tile=(2, 2, 4), steps=25):
     bc = md.arr("bincount").reshape(nbx, nby, nbz); bo = md.arr("binoffsets").reshape(nbx, nby, nbz); pv = md.arr("permute")
     cut2 = md.getd("neigh_cutoff") ** 2
     tx, ty, tz = tile
-    res = {"A_thread_per_atom": [0, 0], "B_8lane_group": [0, 0], "C_16lane_group": [0, 0], "D_thread_per_atom_bank_rotated": [0, 0]}
+    res = {"A_thread_per_atom": [0, 0], "B_8lane_group": [0, 0], "C_16lane_group": [0, 0], "D_thread_per_atom_bank_rotated": [0, 0],
+           "E_rotate_kernel": [0, 0], "F_schedule_kernel": [0, 0]}
+    cols = {"E_rotate_kernel": [0, 0], "F_schedule_kernel": [0, 0]}  # [columns, longest row] per warp
     ntile = 0
     for bx0 in range(1, nbx - 1, tx):
         for by0 in range(1, nby - 1, ty):
@@ -84,6 +86,62 @@ def main(region=(20, 20, 20), tile=(2, 2, 4), steps=25):
                     for q in range(maxn):
                         a = np.array([r[q] if q < len(r) else -1 for r in grp] + [-1] * (32 - len(grp)))
                         res["D_thread_per_atom_bank_rotated"][0] += wavefronts([a[:16], a[16:]]); res["D_thread_per_atom_bank_rotated"][1] += (a >= 0).sum()
+                # E: kernels/tiles.cu tiles_rotate_kernel -- lane l reads bank (q + l) mod 16 at column q while that bucket lasts,
+                #    else a bucket holding more than its share of what is left (first in rotation order), else any
+                def rotate_kernel(r, hl):
+                    buckets = [list(r[r % 16 == b]) for b in range(16)]
+                    out = []
+                    for q in range(len(r)):
+                        pref = (q + hl) % 16
+                        b = pref
+                        if not buckets[pref]:
+                            th = (len(r) - q + 15) // 16
+                            ne = sorted((k for k in range(16) if buckets[k]), key=lambda k: (k - pref) % 16)
+                            big = [k for k in ne if len(buckets[k]) > th]
+                            b = big[0] if big else ne[0]
+                        out.append(buckets[b].pop(0))
+                    return np.array(out, int)
+                # F: tiles_schedule_kernel (EMD_TILES_SCHED=full) -- lane after lane: join a slot already taken in this column if
+                #    it heads one of my buckets, else the first free bank (rotation order) among my over-full buckets, else among
+                #    all my non-empty ones; no free bank: idle (padding)
+                def schedule_half(grp):
+                    bk = [[sorted(r[r % 16 == b]) for b in range(16)] for r in grp]
+                    rem = [len(r) for r in grp]
+                    columns = []
+                    q = 0
+                    while any(rem):
+                        col = [-1] * 16
+                        taken = {}
+                        for l in range(len(grp)):
+                            if not rem[l]: continue
+                            pick = next(((b, sl) for b, sl in taken.items() if bk[l][b] and bk[l][b][0] == sl), None)
+                            if pick is None:
+                                r0 = (q + l) % 16
+                                free = sorted((b for b in range(16) if bk[l][b] and b not in taken), key=lambda b: (b - r0) % 16)
+                                if free:
+                                    th = (rem[l] + 15) // 16
+                                    big = [b for b in free if len(bk[l][b]) > th]
+                                    b = big[0] if big else free[0]
+                                    pick = (b, bk[l][b][0])
+                            if pick is None: continue
+                            b, sl = pick
+                            bk[l][b].remove(sl); rem[l] -= 1; taken[b] = sl; col[l] = sl
+                        columns.append(col); q += 1
+                    return columns
+                for w0 in range(0, len(rows), 32):
+                    grp = [rotate_kernel(r, l % 16) for l, r in enumerate(rows[w0:w0 + 32])]
+                    maxn = max((len(r) for r in grp), default=0)
+                    cols["E_rotate_kernel"][0] += maxn; cols["E_rotate_kernel"][1] += maxn
+                    for q in range(maxn):
+                        a = np.array([r[q] if q < len(r) else -1 for r in grp] + [-1] * (32 - len(grp)))
+                        res["E_rotate_kernel"][0] += wavefronts([a[:16], a[16:]]); res["E_rotate_kernel"][1] += (a >= 0).sum()
+                    raw = rows[w0:w0 + 32]
+                    h0, h1 = schedule_half(raw[:16]), (schedule_half(raw[16:]) if len(raw) > 16 else [])
+                    cols["F_schedule_kernel"][0] += max(len(h0), len(h1)); cols["F_schedule_kernel"][1] += max((len(r) for r in raw), default=0)
+                    for h in (h0, h1):
+                        for col in h:
+                            a = np.array(col)
+                            res["F_schedule_kernel"][0] += wavefronts([a]); res["F_schedule_kernel"][1] += (a >= 0).sum()
                 # B: 8 lanes per atom, 4 atoms per warp
                 for name, gl in (("B_8lane_group", 8), ("C_16lane_group", 16)):
                     apw = 32 // gl
@@ -97,7 +155,8 @@ def main(region=(20, 20, 20), tile=(2, 2, 4), steps=25):
                                 a[gi * gl: gi * gl + len(seg)] = seg
                             res[name][0] += wavefronts([a[:16], a[16:]]); res[name][1] += (a >= 0).sum()
     for k, (w, p) in res.items():
-        print(f"{k}: {w / p * 32:.2f} wavefronts per 32 pairs per LDS.64  (x3 arrays = {3 * w / p * 32:.1f})")
+        extra = f"; columns = {cols[k][0] / max(cols[k][1], 1):.3f} x longest row of the warp" if k in cols else ""
+        print(f"{k}: {w / p * 32:.2f} wavefronts per 32 pairs per LDS.64  (x3 arrays = {3 * w / p * 32:.1f}){extra}")
 
 if __name__ == "__main__":
     main()
