@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(1024) tiles_order_kernel(TileArgs a, int ntile
 // The lane-serial dependency is a systolic pipeline: at step t lane l works on column t - l and
 // reads the state its predecessors left for that column in a shared-memory ring, so a warp
 // schedules its two half-warps in (columns + 16) steps.  tools/sim_lds_conflicts.py models both
-// re-orderings on an oracle liquid (variants E and F): per 32 pairs and LDS.64, 5.6 wavefronts in list
+// re-orderings on a reference liquid state (variants E and F): per 32 pairs and LDS.64, 5.6 wavefronts in list
 // order, 3.5 with the per-lane rotation, 2.15 (2 = conflict-free) with this schedule for 1 % more
 // columns than the longest row of the warp; the GPU test measures the same on the real lists.
 constexpr int kSchedWarps = 2;
