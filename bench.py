@@ -6,8 +6,8 @@
 A "step" is one MD timestep (initial_integrate -> halo update or, every 20th step, exchange + sort +
 halo + binning + neighbor build -> LJ force -> final_integrate) over the configuration BASELINE.json
 quotes the metric on: LJ fcc 2 048 000 atoms (in.lj with `region 0 80 0 80 0 80`), cutoff 2.5, skin
-0.3, half CSR list, one B200.  K should be a multiple of 20 so the timed region holds its share of
-re-neighborings (it starts right after one).
+0.3, half CSR list, one B200.  The timed region starts one step before a re-neighboring, so K steps hold
+ceil(K/20) re-neighborings (exactly their share when K is a multiple of 20).
 
   value     atom-steps/s, state resident in HBM, timed with CUDA events on the module stream
   e2e       same metric through the host-buffer session API: every step copies x,v,f from pinned
@@ -312,9 +312,10 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     app.advance(W)
-    # land on a step just after a re-neighboring so K steps hold K/20 rebuilds
+    # land on the step just BEFORE a re-neighboring: the K timed steps then hold ceil(K / rate) rebuilds -- exactly K / rate for a
+    # multiple of the deck's cadence (20), and never fewer than their share for any other K
     rate = app.get("exchange_rate")
-    app.advance((-app.get("step")) % rate)
+    app.advance((rate - 1 - app.get("step")) % rate)
     barrier()
     launches0 = app.launches()
     ms = C.c_float()
