@@ -137,12 +137,18 @@ static inline const int *orc_neigh_row(const orc_neighbor *n, int i, int *count)
 typedef struct {
   int ntypes, half_neigh, comm_newton;
   double *lj1, *lj2, *cutsq; /* [ntypes][ntypes] */
+  double *intensity;         /* [ntypes][ntypes], ForceLJIDialNeigh only (idial != 0) */
+  int idial;
 } orc_force_lj;
 void orc_force_lj_init(orc_force_lj *f, int ntypes, int half_neigh);
 void orc_force_lj_destroy(orc_force_lj *f);
 void orc_force_lj_init_coeff(orc_force_lj *f, int nargs, char args[][ORC_WORD]); /* _impl.h:57-98 */
 void orc_force_lj_compute(const orc_force_lj *f, orc_system *s, const orc_neighbor *n); /* _impl.h:100-126,161-254 */
 double orc_force_lj_energy(const orc_force_lj *f, const orc_system *s, const orc_neighbor *n); /* _impl.h:128-156,256-343 */
+/* ForceLJIDialNeigh (pair_style lj/cut/idial), src/force_types/force_lj_idial_neigh_impl.h: init_coeff :50-88, functors :113-213.
+ * No compute_energy (Force::compute_energy default: PE = 0). */
+void orc_force_lj_idial_init_coeff(orc_force_lj *f, int nargs, char args[][ORC_WORD]);
+void orc_force_lj_idial_compute(const orc_force_lj *f, orc_system *s, const orc_neighbor *n);
 
 /* src/integrator_nve.cpp:41-121 */
 void orc_initial_integrate(orc_system *s);

@@ -23,6 +23,10 @@ void *orcf_create_deck(const char *deck, int neigh_type, int iter_type, int nx, 
     orc_force_lj_init(&md->lj, md->sys.ntypes, half);
     for (int l = 0; l < md->in.n_coeff_lines; l++) orc_force_lj_init_coeff(&md->lj, md->in.coeff_nwords[l], md->in.coeff_words[l]);
     md->lj.comm_newton = md->in.comm_newton;
+  } else if (md->in.force_type == ORC_FORCE_LJ_IDIAL) { /* ForceLJIDialNeigh, force_lj_idial_neigh.h:47-57 */
+    orc_force_lj_init(&md->lj, md->sys.ntypes, half);
+    for (int l = 0; l < md->in.n_coeff_lines; l++) orc_force_lj_idial_init_coeff(&md->lj, md->in.coeff_nwords[l], md->in.coeff_words[l]);
+    md->lj.comm_newton = md->in.comm_newton;
   } else if (md->in.force_type == ORC_FORCE_SNAP) {
     md->snap = orc_force_snap_create(md->sys.ntypes);
     for (int l = 0; l < md->in.n_coeff_lines; l++)

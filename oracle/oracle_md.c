@@ -576,8 +576,9 @@ void orc_force_lj_init(orc_force_lj *f, int ntypes, int half_neigh) {
   f->ntypes = ntypes; f->half_neigh = half_neigh;
   size_t n = (size_t)ntypes * ntypes;
   f->lj1 = (double *)calloc(n, 8); f->lj2 = (double *)calloc(n, 8); f->cutsq = (double *)calloc(n, 8);
+  f->intensity = (double *)calloc(n, 8);
 }
-void orc_force_lj_destroy(orc_force_lj *f) { free(f->lj1); free(f->lj2); free(f->cutsq); memset(f, 0, sizeof(*f)); }
+void orc_force_lj_destroy(orc_force_lj *f) { free(f->lj1); free(f->lj2); free(f->cutsq); free(f->intensity); memset(f, 0, sizeof(*f)); }
 
 /* src/force_types/force_lj_neigh_impl.h:57-98.  args = the pair_coeff line's words:
  * args[1],args[2] types (1-based), args[3] eps, args[4] sigma, args[5] cut. */
@@ -653,6 +654,59 @@ void orc_force_lj_compute(const orc_force_lj *fl, orc_system *s, const orc_neigh
     } else
 #endif
     { f[3 * i] += fxi; f[3 * i + 1] += fyi; f[3 * i + 2] += fzi; }
+  }
+}
+
+/* ForceLJIDialNeigh::init_coeff, src/force_types/force_lj_idial_neigh_impl.h:50-88: args[6] = nrepeat; unlike ForceLJNeigh there
+ * is no stack-parameter path, a line sets its own (t1,t2)/(t2,t1) entries only. */
+void orc_force_lj_idial_init_coeff(orc_force_lj *f, int nargs, char args[][ORC_WORD]) {
+  (void)nargs;
+  const int t1 = atoi(args[1]) - 1, t2 = atoi(args[2]) - 1, nt = f->ntypes;
+  const double eps = atof(args[3]), sigma = atof(args[4]), cut = atof(args[5]);
+  const int nrepeat = atoi(args[6]);
+  f->idial = 1;
+  f->lj1[t1 * nt + t2] = 48.0 * eps * pow(sigma, 12.0);
+  f->lj2[t1 * nt + t2] = 24.0 * eps * pow(sigma, 6.0);
+  f->lj1[t2 * nt + t1] = f->lj1[t1 * nt + t2];
+  f->lj2[t2 * nt + t1] = f->lj2[t1 * nt + t2];
+  f->cutsq[t1 * nt + t2] = cut * cut;
+  f->cutsq[t2 * nt + t1] = cut * cut;
+  f->intensity[t1 * nt + t2] = nrepeat;
+  f->intensity[t2 * nt + t1] = nrepeat;
+}
+
+/* TagFullNeigh :113-163, TagHalfNeigh :165-213: the pair force is accumulated `intensity` times, each term divided by
+ * `intensity` (the loop bound compares the int counter with the double-valued view entry); half lists subtract from j only
+ * when j is an owned atom (:203-207), whatever `newton` says. */
+void orc_force_lj_idial_compute(const orc_force_lj *fl, orc_system *s, const orc_neighbor *n) {
+  const double *x = s->x;
+  double *f = s->f;
+  const int nt = fl->ntypes;
+  for (int i = 0; i < s->N_local; i++) {
+    const double x_i = x[3 * i], y_i = x[3 * i + 1], z_i = x[3 * i + 2];
+    const int type_i = s->type[i];
+    int num_neighs;
+    const int *row = orc_neigh_row(n, i, &num_neighs);
+    double fxi = 0.0, fyi = 0.0, fzi = 0.0;
+    for (int jj = 0; jj < num_neighs; jj++) {
+      const int j = row[jj];
+      const double dx = x_i - x[3 * j], dy = y_i - x[3 * j + 1], dz = z_i - x[3 * j + 2];
+      const int type_j = s->type[j];
+      const double rsq = dx * dx + dy * dy + dz * dz;
+      if (rsq < fl->cutsq[type_i * nt + type_j]) {
+        const double lj1_ij = fl->lj1[type_i * nt + type_j], lj2_ij = fl->lj2[type_i * nt + type_j];
+        const double inten = fl->intensity[type_i * nt + type_j];
+        double fpair = 0;
+        for (int repeat = 0; repeat < inten; repeat++) {
+          double r2inv = 1.0 / rsq;
+          double r6inv = r2inv * r2inv * r2inv;
+          fpair += (r6inv * (lj1_ij * r6inv - lj2_ij)) * r2inv / inten;
+        }
+        fxi += dx * fpair; fyi += dy * fpair; fzi += dz * fpair;
+        if (fl->half_neigh && j < s->N_local) { f[3 * j] -= dx * fpair; f[3 * j + 1] -= dy * fpair; f[3 * j + 2] -= dz * fpair; }
+      }
+    }
+    f[3 * i] += fxi; f[3 * i + 1] += fyi; f[3 * i + 2] += fzi;
   }
 }
 
@@ -755,6 +809,10 @@ int orc_md_init(orc_md *md, const char *deck, int neighbor_type, int force_itera
     orc_force_lj_init(&md->lj, md->sys.ntypes, half);
     for (int l = 0; l < md->in.n_coeff_lines; l++) orc_force_lj_init_coeff(&md->lj, md->in.coeff_nwords[l], md->in.coeff_words[l]);
     md->lj.comm_newton = md->in.comm_newton;
+  } else if (md->in.force_type == ORC_FORCE_LJ_IDIAL) {
+    orc_force_lj_init(&md->lj, md->sys.ntypes, half);
+    for (int l = 0; l < md->in.n_coeff_lines; l++) orc_force_lj_idial_init_coeff(&md->lj, md->in.coeff_nwords[l], md->in.coeff_words[l]);
+    md->lj.comm_newton = md->in.comm_newton;
   } else if (md->in.force_type == ORC_FORCE_SNAP) {
     md->snap = orc_force_snap_create(md->sys.ntypes);
     for (int l = 0; l < md->in.n_coeff_lines; l++)
@@ -773,6 +831,7 @@ int orc_md_init(orc_md *md, const char *deck, int neighbor_type, int force_itera
 static void md_force(orc_md *md) {
   memset(md->sys.f, 0, sizeof(double) * 3 * (size_t)md->sys.N_max); /* deep_copy(f,0): whole allocation */
   if (md->snap) orc_force_snap_compute(md->snap, &md->sys, &md->neigh);
+  else if (md->lj.idial) orc_force_lj_idial_compute(&md->lj, &md->sys, &md->neigh);
   else orc_force_lj_compute(&md->lj, &md->sys, &md->neigh);
 }
 
@@ -822,7 +881,7 @@ void orc_md_step(orc_md *md) {
 /* src/examinimd.cpp:252-255: T, PE/N, KE/N */
 void orc_md_thermo(orc_md *md, double *T, double *PE, double *KE) {
   *T = orc_temperature(&md->sys);
-  double pe = md->snap ? 0.0 /* Force::compute_energy default, force.h:54 */ : orc_force_lj_energy(&md->lj, &md->sys, &md->neigh);
+  double pe = (md->snap || md->lj.idial) ? 0.0 /* Force::compute_energy default, force.h:54 */ : orc_force_lj_energy(&md->lj, &md->sys, &md->neigh);
   *PE = pe / md->sys.N;
   *KE = orc_kine(&md->sys) / md->sys.N;
 }

@@ -32,6 +32,11 @@ CASES = [  # name, region, nsteps, newton, neigh, iteration, dump steps
 ]
 
 
+IDIAL_CASES = [  # pair_style lj/cut/idial (ForceLJIDialNeigh): name, region, nsteps, neigh, iteration, nrepeat, dump steps
+    ("ljidial_6x6x6_csr_full_r3", (6, 6, 6), 40, "CSR", "NEIGH_FULL", 3, (0, 1, 20, 40)),
+    ("ljidial_6x6x6_2d_half_r2", (6, 6, 6), 40, "2D", "NEIGH_HALF", 2, (0, 20, 40)),
+]
+
 SNAP_DIR = REPO / "input" / "snap"
 SNAP_CASES = [  # name, deck, region, nsteps, neigh, dump steps  (newton on, full list: the only mode ForceSNAP accepts)
     ("snap_W_4x4x4_csr", "in.snap.W", (4, 4, 4), 4, "CSR", (0, 1, 4)),
@@ -40,8 +45,11 @@ SNAP_CASES = [  # name, deck, region, nsteps, neigh, dump steps  (newton on, ful
 ]
 
 
-def make_deck(path, region, nsteps, newton, deck=DECK):
+def make_deck(path, region, nsteps, newton, deck=DECK, idial=0):
     txt = Path(deck).read_text()
+    if idial:  # the reference ships no lj/cut/idial deck: in.lj with the pair lines of src/input.cpp:367-369 / force_lj_idial_neigh_impl.h:50-57
+        txt = re.sub(r"pair_style\s+lj/cut\s+(\S+)", r"pair_style\tlj/cut/idial \1", txt)
+        txt = re.sub(r"(pair_coeff\s+\S+\s+\S+\s+\S+\s+\S+\s+\S+)", r"\1 %d" % idial, txt)
     txt = re.sub(r"region\s+box block.*", "region\t\tbox block 0 %d 0 %d 0 %d" % region, txt)
     txt = re.sub(r"run\s+\d+", "run\t\t%d" % nsteps, txt)
     txt = re.sub(r"newton \w+", "newton %s" % newton, txt)
@@ -67,11 +75,11 @@ def read_dump(p):
     return out
 
 
-def run_reference(region, nsteps, newton, neigh, iteration, dump_steps, exe=REF, deck_src=DECK):
+def run_reference(region, nsteps, newton, neigh, iteration, dump_steps, exe=REF, deck_src=DECK, idial=0):
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
         deck = td / "in.deck"
-        make_deck(deck, region, nsteps, newton, deck_src)
+        make_deck(deck, region, nsteps, newton, deck_src, idial)
         for f in SNAP_DIR.glob("*.snap*"):  # coefficient files are opened relative to the working directory
             (td / f.name).write_bytes(f.read_bytes())
         (td / "dump").mkdir()
@@ -95,6 +103,14 @@ def main():
         out["newton"] = np.array(1 if newton == "on" else 0)
         out["neigh"] = np.array(neigh)
         out["iteration"] = np.array(iteration)
+        np.savez_compressed(HERE / (name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items() if k.startswith("s0_") or k == "thermo"})
+    for name, region, nsteps, neigh, iteration, nrepeat, steps in IDIAL_CASES:
+        out = run_reference(region, nsteps, "off", neigh, iteration, steps, idial=nrepeat)
+        out["newton"] = np.array(0)
+        out["neigh"] = np.array(neigh)
+        out["iteration"] = np.array(iteration)
+        out["idial"] = np.array(nrepeat)
         np.savez_compressed(HERE / (name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith("s0_") or k == "thermo"})
     for name, deck, region, nsteps, neigh, steps in SNAP_CASES:

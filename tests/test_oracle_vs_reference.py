@@ -23,10 +23,10 @@ sys.path.insert(0, str(REPO / "tests" / "golden"))
 SNAP_DIR = REPO / "input" / "snap"
 
 
-def deck_for(tmp_path, region, nsteps, newton, deck=None):
+def deck_for(tmp_path, region, nsteps, newton, deck=None, idial=0):
     import make_golden
     p = tmp_path / "in.deck"
-    make_golden.make_deck(p, tuple(int(r) for r in region), int(nsteps), "on" if newton else "off", deck or make_golden.DECK)
+    make_golden.make_deck(p, tuple(int(r) for r in region), int(nsteps), "on" if newton else "off", deck or make_golden.DECK, idial)
     return p
 
 
@@ -45,7 +45,8 @@ def check_against(md, g, steps):
 def test_oracle_reproduces_reference_dumps_bit_for_bit(oracle_lib, tmp_path, path):
     g = np.load(path)
     snap = "deck" in g.files  # SNAP fixtures name the shipped deck they derive from (input/snap/)
-    deck = deck_for(tmp_path, g["region"], g["nsteps"], int(g["newton"]), SNAP_DIR / str(g["deck"]) if snap else None)
+    idial = int(g["idial"]) if "idial" in g.files else 0  # pair_style lj/cut/idial fixtures (ForceLJIDialNeigh)
+    deck = deck_for(tmp_path, g["region"], g["nsteps"], int(g["newton"]), SNAP_DIR / str(g["deck"]) if snap else None, idial)
     md = OracleMD.from_deck(deck, str(g["neigh"]), str(g["iteration"]), coeff_dir=SNAP_DIR if snap else None)
     steps = sorted(int(m.group(1)) for k in g.files if (m := re.match(r"s(\d+)_x", k)))
     assert steps[0] == 0
