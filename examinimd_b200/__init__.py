@@ -67,6 +67,7 @@ _SIGS = {
     "emd_ctx_stream": (_P, [_P]),
     "emd_ctx_sync": (C.c_int, [_P]),
     "emd_last_error": (C.c_char_p, []),
+    "emd_microbench_fp64": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emd_abi_version": (C.c_int, []),
     "emd_ctx_launch_count": (C.c_ulonglong, [_P]),
     "emd_ctx_tic": (C.c_int, [_P]),
@@ -91,6 +92,7 @@ _SIGS = {
                                     _P, _P, C.POINTER(C.c_int)]),
     "emd_force_lj_set_params": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "emd_force_lj_compute": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NeighList), C.c_int, C.c_int]),
+    "emd_force_lj_idial_compute": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NeighList), C.c_int, C.c_int, _P]),
     "emd_force_lj_energy": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(NeighList), C.c_int, C.POINTER(C.c_double)]),
     "emd_tiles_create": (C.c_int, [C.POINTER(_P)]),
     "emd_tiles_destroy": (None, [_P]),
@@ -156,6 +158,7 @@ _SIGS = {
     "emd_app_destroy": (None, [_P]),
     "emd_app_ctx": (_P, [_P]),
     "emd_app_advance": (C.c_int, [_P, C.c_int]),
+    "emd_app_run": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "emd_app_advance_timed": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "emd_app_thermo": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emd_app_get": (C.c_longlong, [_P, C.c_char_p]),
@@ -242,6 +245,12 @@ class App:
 
     def advance(self, nsteps: int) -> None:
         check(lib().emd_app_advance(self._h, nsteps), "emd_app_advance")
+
+    def run(self, nsteps: int):
+        """the reference's run loop: steps + thermo reductions at the deck's cadence; returns the last (T, PE, KE) or None"""
+        out = (C.c_double * 3)(float("nan"), float("nan"), float("nan"))
+        check(lib().emd_app_run(self._h, nsteps, out), "emd_app_run")
+        return None if out[0] != out[0] else (out[0], out[1], out[2])
 
     def advance_timed(self, nsteps: int) -> dict:
         """advance with the reference's phase timers; seconds per phase over the nsteps"""

@@ -6,7 +6,7 @@ BinningKKSort::BinningKKSort(System *s) : Binning(s) {}
 
 static void fail(const char *what) {
   fprintf(stderr, "BinningKKSort: %s: %s\n", what, emd_last_error());
-  exit(1);
+  emd_host_exit(1);
 }
 
 // src/binning_types/binning_kksort.cpp:71-140, expressed as three C-ABI calls.

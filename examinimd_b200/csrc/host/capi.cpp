@@ -3,14 +3,35 @@
 #include "emd_b200_app.h"
 #include "examinimd.h"
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
 struct emd_app {
-  ExaMiniMD *md;
+  ExaMiniMD *md = nullptr;
   std::vector<std::string> args;
   std::vector<char *> argv;
 };
+
+namespace emd { void set_error(const char *fmt, ...); }
+
+// Host-layer fatal errors (emd_host_exit, types.h) become return codes here instead of ending the embedding process.
+// The message the call site printed is also kept in emd_last_error() when the failing C-ABI call set one.
+template <class F>
+static int guarded(const char *where, F &&f) {
+  emd_host_throw_on_exit(true);
+  try {
+    f();
+  } catch (const EmdFatal &e) {
+    const std::string prev = emd_last_error();
+    emd::set_error("%s: fatal error in the host layer (exit code %d)%s%s", where, e.code, prev.empty() ? "" : ": ", prev.c_str());
+    return 1;
+  } catch (const std::exception &e) {
+    emd::set_error("%s: %s", where, e.what());
+    return 1;
+  }
+  return 0;
+}
 
 extern "C" {
 
@@ -19,9 +40,12 @@ int emd_app_create(emd_app **out, int argc, const char *const *argv, int device,
   a->args.push_back("ExaMiniMD");
   for (int i = 0; i < argc; i++) a->args.push_back(argv[i]);
   for (auto &s : a->args) a->argv.push_back(const_cast<char *>(s.c_str()));
-  a->md = new ExaMiniMD(device, stream);
-  a->md->quiet = true;
-  a->md->init((int)a->argv.size(), a->argv.data());
+  const int rc = guarded("emd_app_create", [&] {
+    a->md = new ExaMiniMD(device, stream);
+    a->md->quiet = true;
+    a->md->init((int)a->argv.size(), a->argv.data());
+  });
+  if (rc) { *out = nullptr; return rc; } // the half-built application is leaked on purpose: its destructors may touch a failed device context
   *out = a;
   return 0;
 }
@@ -35,22 +59,25 @@ void emd_app_destroy(emd_app *a) {
 emd_ctx *emd_app_ctx(emd_app *a) { return a->md->system->ctx; }
 
 int emd_app_advance(emd_app *a, int nsteps) {
-  a->md->advance(nsteps);
-  return 0;
+  return guarded("emd_app_advance", [&] { a->md->advance(nsteps); });
+}
+
+int emd_app_run(emd_app *a, int nsteps, double *h_last_thermo3) {
+  return guarded("emd_app_run", [&] { a->md->run_quiet(nsteps, h_last_thermo3); });
 }
 
 int emd_app_advance_timed(emd_app *a, int nsteps, double *h_seconds4) {
-  PhaseTimers tm(a->md->system->ctx);
-  for (int k = 0; k < nsteps; k++) a->md->step_once(++a->md->current_step, &tm, k + 1 < nsteps);
-  tm.flush();
-  h_seconds4[0] = tm.seconds[PhaseTimers::FORCE]; h_seconds4[1] = tm.seconds[PhaseTimers::NEIGH];
-  h_seconds4[2] = tm.seconds[PhaseTimers::COMM]; h_seconds4[3] = tm.seconds[PhaseTimers::OTHER];
-  return 0;
+  return guarded("emd_app_advance_timed", [&] {
+    PhaseTimers tm(a->md->system->ctx);
+    for (int k = 0; k < nsteps; k++) a->md->step_once(++a->md->current_step, &tm, k + 1 < nsteps);
+    tm.flush();
+    h_seconds4[0] = tm.seconds[PhaseTimers::FORCE]; h_seconds4[1] = tm.seconds[PhaseTimers::NEIGH];
+    h_seconds4[2] = tm.seconds[PhaseTimers::COMM]; h_seconds4[3] = tm.seconds[PhaseTimers::OTHER];
+  });
 }
 
 int emd_app_thermo(emd_app *a, double *T, double *PE, double *KE) {
-  a->md->thermo(T, PE, KE);
-  return 0;
+  return guarded("emd_app_thermo", [&] { a->md->thermo(T, PE, KE); });
 }
 
 long long emd_app_get(emd_app *a, const char *what) {
@@ -128,10 +155,10 @@ int emd_app_dump_binary(emd_app *a, const char *path, int step) {
   int old_rate = in->dumpbinary_rate;
   in->dumpbinary_path = const_cast<char *>(path);
   in->dumpbinary_rate = 1;
-  a->md->dump_binary(step);
+  const int rc = guarded("emd_app_dump_binary", [&] { a->md->dump_binary(step); });
   in->dumpbinary_path = old_path;
   in->dumpbinary_rate = old_rate;
-  return 0;
+  return rc;
 }
 
 } // extern "C"

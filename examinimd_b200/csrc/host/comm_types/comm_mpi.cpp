@@ -32,7 +32,7 @@ void CommMPI::init() {}
 
 void CommMPI::fail(const char *what) {
   fprintf(stderr, "CommMPI[rank %d]: %s: %s\n", proc_rank, what, emd_last_error());
-  exit(1);
+  emd_host_exit(1);
 }
 
 void CommMPI::ensure_bytes(DeviceArray<char> &b, size_t bytes) {
@@ -224,7 +224,7 @@ int CommMPI::num_processes() { return proc_size; }
 void CommMPI::error(const char *errormsg) { // :472-476 (MPI_Abort): a non-zero exit makes the launcher tear the job down
   if (proc_rank == 0) printf("%s\n", errormsg);
   fflush(stdout);
-  exit(1);
+  emd_host_exit(1);
 }
 
 const char *CommMPI::name() { return "CommMPI"; }

@@ -4,7 +4,7 @@
 
 static void fail(const char *what) {
   fprintf(stderr, "CommSerial: %s: %s\n", what, emd_last_error());
-  exit(1);
+  emd_host_exit(1);
 }
 
 CommSerial::CommSerial(System *s, T_X_FLOAT comm_depth_) : Comm(s, comm_depth_) {

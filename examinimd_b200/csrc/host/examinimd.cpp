@@ -38,12 +38,19 @@ void PhaseTimers::end(int phase) {
   emd_event_record(ctx, b);
   spans.push_back({cur, b, phase});
   cur = b; // phases are back to back on one stream: the end of one is the start of the next
-  if (spans.size() >= 4096) flush();
+  if (spans.size() >= 4096) {
+    // fold what has accumulated; `cur` must stay a live, recorded event (the next end() measures from it), so it moves to
+    // the front of the recycled pool instead of being dropped
+    flush();
+    std::swap(pool[0], *std::find(pool.begin(), pool.end(), b));
+    next = 1;
+    cur = b;
+  }
 }
 void PhaseTimers::flush() {
   for (const Span &s : spans) {
     float ms = 0.f;
-    emd_event_elapsed_ms(s.a, s.b, &ms);
+    emd_event_elapsed_ms(s.a, s.b, &ms); // synchronises on s.b
     seconds[s.phase] += 1e-3 * ms;
   }
   spans.clear();
@@ -57,7 +64,7 @@ ExaMiniMD::ExaMiniMD(int device, void *stream) {
   if (emd_ctx_create(&system->ctx, device, stream)) {
     // no CPU fallback: the product path needs the GPU
     fprintf(stderr, "ExaMiniMD: cannot create device context: %s\n", emd_last_error());
-    exit(1);
+    emd_host_exit(1);
   }
   system->init();
   input = new Input(system);
@@ -86,7 +93,7 @@ void ExaMiniMD::init(int argc, char *argv[]) {
 #define FORCE_MODULES_INSTANTIATION
 #include "modules_force.h"
 #undef FORCE_MODULES_INSTANTIATION
-  else { printf("Invalid ForceType\n"); exit(1); }
+  else { printf("Invalid ForceType\n"); emd_host_exit(1); }
   for (size_t l = 0; l < input->force_coeff_lines.size(); l++) {
     const int line = input->force_coeff_lines[l];
     force->init_coeff(input->input_data.words_in_line(line), input->input_data.words[line]);
@@ -96,13 +103,13 @@ void ExaMiniMD::init(int argc, char *argv[]) {
 #define NEIGHBOR_MODULES_INSTANTIATION
 #include "modules_neighbor.h"
 #undef NEIGHBOR_MODULES_INSTANTIATION
-  else { printf("Invalid NeighborType\n"); exit(1); }
+  else { printf("Invalid NeighborType\n"); emd_host_exit(1); }
 
   if (false) {}
 #define COMM_MODULES_INSTANTIATION
 #include "modules_comm.h"
 #undef COMM_MODULES_INSTANTIATION
-  else { printf("Invalid CommType\n"); exit(1); }
+  else { printf("Invalid CommType\n"); emd_host_exit(1); }
 
   force->comm_newton = input->comm_newton;
   if (neighbor) neighbor->comm_newton = input->comm_newton;
@@ -226,6 +233,20 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
 
 void ExaMiniMD::advance(int nsteps) {
   for (int k = 0; k < nsteps; k++) step_once(++current_step, nullptr, k + 1 < nsteps);
+}
+
+// run() without output: what bench.py times as the reference's own metric (thermo passes included)
+void ExaMiniMD::run_quiet(int nsteps, T_FLOAT *last_thermo3) {
+  for (int s = 1; s <= nsteps; s++) {
+    const int step = ++current_step;
+    const bool observed = input->thermo_rate > 0 && step % input->thermo_rate == 0;
+    step_once(step, nullptr, s < nsteps && !observed);
+    if (observed) {
+      T_FLOAT T, PE, KE;
+      thermo(&T, &PE, &KE);
+      if (last_thermo3) { last_thermo3[0] = T; last_thermo3[1] = PE; last_thermo3[2] = KE; }
+    }
+  }
 }
 
 void ExaMiniMD::run(int nsteps) {
@@ -353,7 +374,7 @@ void ExaMiniMD::check_correctness(int step) {
   }
   for (int q = 0; q < 3; q++) { comm->reduce_float(&sumsq[q], 1); comm->reduce_max_float(&maxd[q], 1); }
 
-  if (system->do_print || quiet) {
+  if (comm->process_rank() == 0) { // one writer (quiet library sessions included)
     FILE *fpout = fopen(input->correctness_file, step == 0 ? "w" : "a");
     if (fpout) {
       if (step == 0) fprintf(fpout, "# timestep deltarnorm maxdelr deltavnorm maxdelv deltafnorm maxdelf\n");

@@ -57,6 +57,8 @@ public:
   bool initial_done = false; // the pending step's initial_integrate has already been applied
   // advance `nsteps` steps continuing the global step counter (rebuild cadence preserved)
   void advance(int nsteps);
+  // run() without its output: steps + the thermo reductions at the deck's cadence (the work the reference's Atomsteps/s spans)
+  void run_quiet(int nsteps, T_FLOAT *last_thermo3);
   void thermo(T_FLOAT *T, T_FLOAT *PE, T_FLOAT *KE);
 
   void dump_binary(int);

@@ -5,7 +5,7 @@
 
 static void fail(const char *what) {
   fprintf(stderr, "ForceLJNeigh: %s: %s\n", what, emd_last_error());
-  exit(1);
+  emd_host_exit(1);
 }
 
 ForceLJNeigh::ForceLJNeigh(char **args, System *system, bool half_neigh_) : Force(args, system, half_neigh_), sys(system) {

@@ -8,7 +8,7 @@
 
 static void snap_abort(const char *msg) { // the reference uses Kokkos::abort(msg)
   fprintf(stderr, "%s\n", msg);
-  exit(1);
+  emd_host_exit(1);
 }
 
 ForceSNAP::ForceSNAP(char **args, System *system, bool half_neigh_)
@@ -132,7 +132,7 @@ void ForceSNAP::init_coeff(int narg, char **arg) {
   if (snap) { emd_snap_destroy(snap); snap = nullptr; }
   if (emd_snap_create(&snap, &p)) { // includes the reference's "Incorrect SNAP parameter file" check (ncoeff vs twojmax, :315-318)
     fprintf(stderr, "ForceSNAP: %s\n", emd_last_error());
-    exit(1);
+    emd_host_exit(1);
   }
 }
 
@@ -144,7 +144,7 @@ void ForceSNAP::compute(System *system, Binning *, Neighbor *neighbor) {
   if (emd_force_snap_compute(system->ctx, snap, system->x, system->type, system->f, system->N_local,
                              system->N_local + system->N_ghost, &l)) {
     fprintf(stderr, "ForceSNAP: compute: %s\n", emd_last_error());
-    exit(1);
+    emd_host_exit(1);
   }
 }
 

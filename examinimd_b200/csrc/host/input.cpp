@@ -190,7 +190,7 @@ void Input::read_command_line_args(int argc, char *argv[]) {
       override_nsteps = atoi(argv[++i]);
     } else if (strstr(a, "--kokkos-") == NULL) {
       if (system->do_print) printf("ERROR: Unknown command line argument: %s\n", a);
-      exit(1);
+      emd_host_exit(1);
     }
   }
 #undef MODULES_OPTION_CHECK
@@ -203,7 +203,7 @@ void Input::read_file(const char *filename) {
     return;
   }
   if (system->do_print) printf("ERROR: Unknown input file type\n");
-  exit(1);
+  emd_host_exit(1);
 }
 
 void Input::read_lammps_file(const char *filename) {
@@ -216,7 +216,7 @@ void Input::read_lammps_file(const char *filename) {
   std::ifstream file(filename);
   if (!file.good()) {
     if (system->do_print) printf("ERROR: cannot open input file %s\n", filename);
-    exit(1);
+    emd_host_exit(1);
   }
   std::string line;
   while (std::getline(file, line)) {

@@ -13,14 +13,14 @@ void IntegratorNVE::initial_integrate() {
   if (emd_nve_initial_integrate(system->ctx, system->x, system->v, system->f, system->type, system->mass, system->N_local,
                                 dtf, dtv)) {
     fprintf(stderr, "IntegratorNVE::initial_integrate: %s\n", emd_last_error());
-    exit(1);
+    emd_host_exit(1);
   }
 }
 
 void IntegratorNVE::final_integrate() {
   if (emd_nve_final_integrate(system->ctx, system->v, system->f, system->type, system->mass, system->N_local, dtf)) {
     fprintf(stderr, "IntegratorNVE::final_integrate: %s\n", emd_last_error());
-    exit(1);
+    emd_host_exit(1);
   }
 }
 
@@ -28,7 +28,7 @@ void IntegratorNVE::final_initial_integrate() {
   if (emd_nve_final_initial_integrate(system->ctx, system->x, system->v, system->f, system->type, system->mass, system->N_local,
                                       dtf, dtv)) {
     fprintf(stderr, "IntegratorNVE::final_initial_integrate: %s\n", emd_last_error());
-    exit(1);
+    emd_host_exit(1);
   }
 }
 

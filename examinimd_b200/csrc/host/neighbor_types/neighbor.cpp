@@ -6,7 +6,7 @@
 
 static void fail(const char *who, const char *what) {
   fprintf(stderr, "%s: %s: %s\n", who, what, emd_last_error());
-  exit(1);
+  emd_host_exit(1);
 }
 
 bool Neighbor::build_tiles(System *system, Binning *binning, T_X_FLOAT neigh_cut) {

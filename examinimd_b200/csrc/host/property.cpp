@@ -6,7 +6,7 @@ static T_V_FLOAT sum_mv2(System *system) {
   double s = 0.0;
   if (emd_reduce_mv2(system->ctx, system->v, system->type, system->mass, system->N_local, &s)) {
     fprintf(stderr, "thermo reduction failed: %s\n", emd_last_error());
-    exit(1);
+    emd_host_exit(1);
   }
   return s;
 }

@@ -5,7 +5,7 @@
 
 static void die(const char *what) {
   fprintf(stderr, "System: %s: %s\n", what, emd_last_error());
-  exit(1);
+  emd_host_exit(1);
 }
 
 System::System() {

@@ -18,6 +18,13 @@ enum { INPUT_LAMMPS };
 
 #define MAX_TYPES_STACKPARAMS 12
 
+// Fatal errors of the host layer.  The reference prints and calls exit(1)/MPI_Abort (src/comm.cpp:65-68); the driver
+// binary keeps that.  Inside the session C API (capi.cpp) the same call sites must not take the embedding process down:
+// emd_host_exit then throws EmdFatal, which every emd_app_* entry point turns into a non-zero return code + emd_last_error().
+struct EmdFatal { int code; };
+void emd_host_throw_on_exit(bool on);
+[[noreturn]] void emd_host_exit(int code);
+
 typedef int T_INT;
 typedef double T_FLOAT;
 typedef double T_X_FLOAT;

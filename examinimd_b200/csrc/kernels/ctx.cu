@@ -113,7 +113,47 @@ int exclusive_scan_int(emd_ctx *ctx, const int *d_in, int *d_out, int n, int *d_
 
 using namespace emd;
 
+namespace {
+// FP64 FMA peak of this device (the SNAP roofline's denominator; MEASURED_PEAKS.json carries HBM and bf16 only):
+// 8 independent DFMA chains per thread, 8 CTAs of 256 threads per SM, best of `reps` launches.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, double a, double b, int iters) {
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = threadIdx.x * 1e-9 + k;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = fma(acc[k], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += acc[k];
+  if (s == 12345.678) out[0] = s;
+}
+} // namespace
+
 extern "C" {
+
+int emd_microbench_fp64(emd_ctx *ctx, int reps, double *h_tflops_best, double *h_tflops_mean) {
+  if (ctx->s_c.ensure(64)) return 1;
+  const int iters = 4096, grid = ctx->num_sms * 8;
+  const double flop = 2.0 * grid * 256.0 * 8 * iters;
+  cudaEvent_t a, b;
+  EMD_CUDA(cudaEventCreate(&a)); EMD_CUDA(cudaEventCreate(&b));
+  float best = 1e30f, sum = 0.f;
+  for (int r = 0; r < reps + 2; r++) {
+    EMD_CUDA(cudaEventRecord(a, ctx->stream));
+    dfma_peak_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->s_c.as<double>(), 1.0000001, 1e-9, iters);
+    EMD_CUDA(cudaEventRecord(b, ctx->stream));
+    EMD_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    EMD_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (r >= 2) { best = ms < best ? ms : best; sum += ms; }
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (h_tflops_best) *h_tflops_best = flop / (best * 1e-3) / 1e12;
+  if (h_tflops_mean) *h_tflops_mean = flop / (sum / reps * 1e-3) / 1e12;
+  return 0;
+}
 
 const char *emd_last_error(void) { return emd::g_err; }
 int emd_abi_version(void) { return EMD_ABI_VERSION; }

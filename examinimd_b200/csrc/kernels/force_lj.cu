@@ -78,6 +78,57 @@ __global__ void __launch_bounds__(128) lj_force_kernel(const double *__restrict_
   }
 }
 
+
+// ForceLJIDialNeigh (pair_style lj/cut/idial): the same pair force accumulated `intensity` times, each term divided by
+// `intensity` -- a compute-intensity dial (src/force_types/force_lj_idial_neigh_impl.h:113-163 full, :165-213 half).  The
+// repeat loop is kept as arithmetic (the asm statement makes rsq opaque per iteration, so the divide and the five multiplies
+// are really issued `intensity` times and the rounding sequence of fpair += term / intensity is the reference's).  Half
+// lists subtract from j only when j is an owned atom (:203-207), whatever `newton` says.
+struct IDialTable { double intensity[kMaxTypesConst * kMaxTypesConst]; };
+
+template <bool HALF>
+__global__ void __launch_bounds__(128) lj_idial_force_kernel(const double *__restrict__ x, const int *__restrict__ type, double *f,
+                                                              int n_local, emd_neigh_list list, const LJTable tab, const IDialTable dial,
+                                                              int overwrite) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_local) return;
+  const double x_i = x[3 * (size_t)i], y_i = x[3 * (size_t)i + 1], z_i = x[3 * (size_t)i + 2];
+  const int type_i = type[i];
+  const int *row;
+  int num_neighs;
+  row_of(list, i, row, num_neighs);
+  double fxi = 0.0, fyi = 0.0, fzi = 0.0;
+  for (int jj = 0; jj < num_neighs; jj++) {
+    const int j = row[jj];
+    const double dx = x_i - x[3 * (size_t)j], dy = y_i - x[3 * (size_t)j + 1], dz = z_i - x[3 * (size_t)j + 2];
+    const int tij = type_i * tab.ntypes + type[j];
+    double rsq = dx * dx + dy * dy + dz * dz;
+    if (rsq < tab.cutsq[tij]) {
+      const double lj1 = tab.lj1[tij], lj2 = tab.lj2[tij], inten = dial.intensity[tij];
+      double fpair = 0.0;
+      for (int repeat = 0; repeat < inten; repeat++) {
+        asm volatile("" : "+d"(rsq));
+        const double r2inv = 1.0 / rsq;
+        const double r6inv = r2inv * r2inv * r2inv;
+        fpair += (r6inv * (lj1 * r6inv - lj2)) * r2inv / inten;
+      }
+      fxi += dx * fpair; fyi += dy * fpair; fzi += dz * fpair;
+      if (HALF && j < n_local) {
+        atomicAdd(&f[3 * (size_t)j], -(dx * fpair));
+        atomicAdd(&f[3 * (size_t)j + 1], -(dy * fpair));
+        atomicAdd(&f[3 * (size_t)j + 2], -(dz * fpair));
+      }
+    }
+  }
+  if (HALF) {
+    atomicAdd(&f[3 * (size_t)i], fxi); atomicAdd(&f[3 * (size_t)i + 1], fyi); atomicAdd(&f[3 * (size_t)i + 2], fzi);
+  } else if (overwrite) {
+    f[3 * (size_t)i] = fxi; f[3 * (size_t)i + 1] = fyi; f[3 * (size_t)i + 2] = fzi;
+  } else {
+    f[3 * (size_t)i] += fxi; f[3 * (size_t)i + 1] += fyi; f[3 * (size_t)i + 2] += fzi;
+  }
+}
+
 constexpr int kRedThreads = 256;
 
 __device__ __forceinline__ double block_sum(double v, double *sm) {
@@ -198,6 +249,26 @@ int emd_force_lj_compute(emd_ctx *ctx, const double *d_x, const int *d_type, dou
     if (one) EMD_LAUNCH(ctx, (lj_force_kernel<false, true>), grid, 128, 0, d_x, d_type, d_f, n_local, *list, tab, zero_f);
     else EMD_LAUNCH(ctx, (lj_force_kernel<false, false>), grid, 128, 0, d_x, d_type, d_f, n_local, *list, tab, zero_f);
   }
+  return 0;
+}
+
+int emd_force_lj_idial_compute(emd_ctx *ctx, const double *d_x, const int *d_type, double *d_f, int n_local, int n_all,
+                               const emd_neigh_list *list, int half, int zero_f, const double *h_intensity) {
+  if (ctx->lj.ntypes == 0) { set_error("emd_force_lj_idial_compute: parameters not set"); return 1; }
+  if (!h_intensity) { set_error("emd_force_lj_idial_compute: intensity table missing"); return 1; }
+  if (n_local <= 0) return 0;
+  LJTable tab;
+  fill_table(ctx, tab);
+  IDialTable dial;
+  memset(&dial, 0, sizeof dial);
+  memcpy(dial.intensity, h_intensity, sizeof(double) * ctx->lj.ntypes * ctx->lj.ntypes);
+  if (zero_f) {
+    const long long b = half ? 0 : 3LL * n_local, e = 3LL * n_all;
+    if (e > b) EMD_LAUNCH(ctx, zero_rows_kernel, grid_for(e - b, 256), 256, 0, d_f, b, e);
+  }
+  const int grid = grid_for(n_local, 128);
+  if (half) EMD_LAUNCH(ctx, (lj_idial_force_kernel<true>), grid, 128, 0, d_x, d_type, d_f, n_local, *list, tab, dial, 0);
+  else EMD_LAUNCH(ctx, (lj_idial_force_kernel<false>), grid, 128, 0, d_x, d_type, d_f, n_local, *list, tab, dial, zero_f);
   return 0;
 }
 

@@ -28,6 +28,9 @@ int emd_ctx_create(emd_ctx **out, int device, void *stream);
 void emd_ctx_destroy(emd_ctx *ctx);
 void *emd_ctx_stream(emd_ctx *ctx);
 int emd_ctx_sync(emd_ctx *ctx);                 /* replaces Kokkos::fence() */
+/* measurement aid (bench.py): FP64 FMA peak of the device in TFLOP/s, DFMA loop on every SM, `reps` launches after two
+ * warm-ups -- best and mean.  The SNAP roofline's denominator (MEASURED_PEAKS.json holds HBM and bf16 only). */
+int emd_microbench_fp64(emd_ctx *ctx, int reps, double *h_tflops_best, double *h_tflops_mean);
 const char *emd_last_error(void);
 int emd_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
@@ -137,6 +140,13 @@ int emd_force_lj_set_params(emd_ctx *ctx, int ntypes, const double *h_lj1, const
 int emd_force_lj_compute(emd_ctx *ctx, const double *d_x, const int *d_type, double *d_f,
                          int n_local, int n_all, const emd_neigh_list *list, int half_neigh,
                          int zero_f);
+/* ForceLJIDialNeigh<>::compute, src/force_types/force_lj_idial_neigh_impl.h:90-111 (functors :113-163 full, :165-213 half):
+ * the LJ pair force accumulated intensity(ti,tj) times, each term divided by it; h_intensity = host [ntypes][ntypes] table
+ * set by init_coeff (:50-88); lj1/lj2/cutsq come from emd_force_lj_set_params.  Half lists subtract from j only if j is
+ * owned (:203-207).  zero_f as above.  The module has no energy (Force::compute_energy default, src/force.h:54). */
+int emd_force_lj_idial_compute(emd_ctx *ctx, const double *d_x, const int *d_type, double *d_f,
+                               int n_local, int n_all, const emd_neigh_list *list, int half_neigh,
+                               int zero_f, const double *h_intensity);
 /* compute_energy (:128-156; functors :256-296 full, :298-343 half): shifted PE, host result */
 int emd_force_lj_energy(emd_ctx *ctx, const double *d_x, const int *d_type, int n_local,
                         const emd_neigh_list *list, int half_neigh, double *h_pe);

@@ -21,6 +21,10 @@ int emd_app_create(emd_app **out, int argc, const char *const *argv, int device,
 void emd_app_destroy(emd_app *app);
 emd_ctx *emd_app_ctx(emd_app *app);
 int emd_app_advance(emd_app *app, int nsteps);
+/* the loop of ExaMiniMD::run as the reference times it (src/examinimd.cpp:192-267): nsteps steps WITH the thermo
+ * reductions (Temperature, PotE = a second pass over the list, KinE) every `thermo` steps of the deck, nothing printed;
+ * h_last_thermo3 (may be NULL) = {T, PE/atom, KE/atom} of the last thermo step executed */
+int emd_app_run(emd_app *app, int nsteps, double *h_last_thermo3);
 /* same, with the reference's four phase timers (src/examinimd.cpp:183-189) taken as device events:
  * h_seconds4 = {T_Force, T_Neigh, T_Comm, T_Other} accumulated over the nsteps */
 int emd_app_advance_timed(emd_app *app, int nsteps, double *h_seconds4);

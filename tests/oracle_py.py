@@ -164,3 +164,63 @@ class OracleMD:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------ whole CPU runs (binaries)
+REF_OMP = ODIR / "_ref" / "ExaMiniMD_ref_omp"   # the unmodified reference over the OpenMP Kokkos stand-in (oracle/Makefile.ref)
+ORACLE_OMP = ODIR / "oracle_md_omp"             # OpenMP build of the restatement
+
+
+def cpu_run_dump(deck_text, steps, neigh="CSR", iteration="NEIGH_HALF", threads=None, files=(), exe=None):
+    """One whole CPU run of `deck_text` (restricted LAMMPS deck) with --dumpbinary at `steps`: the reference binary itself when
+    it was built (oracle/_ref), else the OpenMP restatement.  Returns {step: {id, x, v, f}} and the stdout."""
+    import os
+    import sys
+    import tempfile
+    sys.path.insert(0, str(REPO / "tests" / "golden"))
+    import make_golden
+    exe = exe or (REF_OMP if REF_OMP.exists() else ORACLE_OMP)
+    if not Path(exe).exists():
+        subprocess.run(["make", "-C", str(ODIR), "oracle_md_omp"], check=True, capture_output=True)
+    threads = threads or os.cpu_count() or 1
+    rate = steps[0] if len(steps) == 1 else int(np.gcd.reduce(steps))
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        (td / "in.deck").write_text(deck_text)
+        for f in files:
+            (td / Path(f).name).write_bytes(Path(f).read_bytes())
+        (td / "dump").mkdir()
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close", OMP_PLACES="cores")
+        r = subprocess.run([str(exe), "-il", "in.deck", "--comm-type", "SERIAL", "--neigh-type", neigh, "--force-iteration", iteration,
+                            "--dumpbinary", str(max(rate, 1)), "dump"], capture_output=True, text=True, check=True, cwd=td, env=env)
+        out = {}
+        for s_ in steps:
+            d = make_golden.read_dump(td / "dump" / ("output.%010d.000" % s_))
+            out[s_] = {k: np.array(d[k]) for k in ("id", "x", "v", "f")}
+    return out, r.stdout
+
+
+def lj_total_energy(x, v, box, iteration="NEIGH_HALF", mass=2.0):
+    """PE + KE per atom (full precision) of an LJ state of the in.lj deck, evaluated by the serial oracle"""
+    md = OracleMD.from_arrays(x, box, v=v, mass=[mass], neigh="CSR", iteration=iteration)
+    md.setup()
+    _, pe, ke = md.thermo()
+    md.close()
+    return pe + ke
+
+
+def lj_energy_envelope(region, nsteps, iteration="NEIGH_HALF"):
+    """The reference's own run-to-run envelope of the total energy after `nsteps` (north_star): the OpenMP restatement run with
+    1 thread and with all cores (atomic force accumulation changes the summation order).  Returns (E_1thread, E_allcores, E_0)."""
+    import os
+    import re
+    txt = (REPO / "input" / "in.lj").read_text()
+    txt = re.sub(r"region\s+box block.*", "region\t\tbox block 0 %d 0 %d 0 %d" % tuple(region), txt)
+    txt = re.sub(r"run\s+\d+", "run\t\t%d" % nsteps, txt)
+    a = (4.0 / 0.8442) ** (1.0 / 3.0)
+    box = [r * a for r in region]
+    one, _ = cpu_run_dump(txt, [nsteps], iteration=iteration, threads=1, exe=ORACLE_OMP)
+    many, _ = cpu_run_dump(txt, [nsteps], iteration=iteration, threads=max(2, os.cpu_count() or 2), exe=ORACLE_OMP)
+    e1 = lj_total_energy(one[nsteps]["x"], one[nsteps]["v"], box, iteration)
+    en = lj_total_energy(many[nsteps]["x"], many[nsteps]["v"], box, iteration)
+    return e1, en

@@ -22,12 +22,11 @@ TOL = 1e-10
 def test_app_matches_reference_dumps(emd, tmp_path, path):
     import make_golden
     g = np.load(path)
-    if "idial" in g.files:
-        pytest.skip("pair_style lj/cut/idial (ForceLJIDialNeigh, SURVEY 8(f) rank 3) is pinned in the oracle only; the CUDA module is not built yet")
+    idial = int(g["idial"]) if "idial" in g.files else 0  # pair_style lj/cut/idial (ForceLJIDialNeigh) with this nrepeat
     deck = tmp_path / "in.deck"
     snap = "deck" in g.files  # SNAP fixtures derive from a shipped input/snap deck; its coefficient files sit beside the deck
     src = make_golden.SNAP_DIR / str(g["deck"]) if snap else make_golden.DECK
-    make_golden.make_deck(deck, tuple(int(r) for r in g["region"]), int(g["nsteps"]), "on" if int(g["newton"]) else "off", src)
+    make_golden.make_deck(deck, tuple(int(r) for r in g["region"]), int(g["nsteps"]), "on" if int(g["newton"]) else "off", src, idial)
     if snap:
         for f in make_golden.SNAP_DIR.glob("*.snap*"):
             (tmp_path / f.name).write_bytes(f.read_bytes())

@@ -10,7 +10,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from oracle_py import OracleMD, REPO
+from oracle_py import OracleMD, REPO, lj_energy_envelope
 
 DECK = REPO / "input" / "in.lj"
 TOL = 1e-10
@@ -57,7 +57,17 @@ def test_100_steps_vs_oracle(emd, neigh, iteration):
     assert app.get("N_ghost") == md.geti("N_ghost")
     if neigh == "CSR":
         assert app.get("total_neighs") == md.geti("total_neighs")
-    assert abs((PEa + KEa) - (PE0 + KE0)) < 2e-3  # NVE energy drift envelope of the oracle itself
+    # total-energy drift within the reference's own run-to-run envelope (north_star): the CPU path run with one thread and with
+    # all cores (atomic force accumulation = another summation order) ends 100 steps at energies e1 and en; the GPU changes the
+    # order of every row sum and contracts FMAs, so its energy may sit up to 100 spreads (floor: 1e-12 per atom) from the
+    # 1-thread value -- four to five orders of magnitude below the drift itself (~4e-5 per atom over these 100 steps)
+    e1, en = lj_energy_envelope(region, 100, iteration)
+    envelope = max(100.0 * abs(e1 - en), 1e-12)
+    drift_ref, drift_gpu = e1 - (PE0 + KE0), (PEa + KEa) - (PE0 + KE0)
+    print(f"DRIFT {neigh} {iteration}: reference {drift_ref:.6e} gpu {drift_gpu:.6e} |diff| {abs(drift_gpu - drift_ref):.2e} "
+          f"thread-to-thread spread {abs(e1 - en):.2e} envelope {envelope:.2e}")
+    assert abs(e1 - (PEo + KEo)) <= envelope  # the serial library oracle is one of the reference's own runs
+    assert abs(drift_gpu - drift_ref) <= envelope
     app.close(); md.close()
 
 
@@ -129,7 +139,7 @@ def test_full_size_invariants(emd):
     assert np.abs(st["f"]).max() < 1e-10
     app.advance(45)
     T, PE, KE = app.thermo()
-    assert abs((PE + KE) - (PE0 + KE0)) < 2e-3
+    assert abs((PE + KE) - (PE0 + KE0)) < 5e-4  # sanity only: the drift is compared with the reference's in tests/test_gpu_fullsize.py
     st = app.download()
     assert np.array_equal(np.sort(st["id"]), np.arange(1, n + 1, dtype=np.int32))  # a permutation of all atoms
     p = st["v"].sum(0) * 2.0
