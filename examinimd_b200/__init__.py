@@ -100,7 +100,7 @@ _SIGS = {
     "emd_tiles_invalidate": (None, [_P]),
     "emd_tiles_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int)]),
-    "emd_tiles_lists": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "emd_tiles_lists": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "emd_neigh_tiles_build": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(BinGeom), _P, _P, _P, C.c_double]),
     "emd_neigh_tiles_count": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
     "emd_neigh_tiles_fill_csr": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),

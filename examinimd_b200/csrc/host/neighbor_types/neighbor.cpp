@@ -29,19 +29,22 @@ void NeighborCSR::create_neigh_list(System *system, Binning *binning, bool half_
   const emd_bin_geom g = binning->geom();
   int total = 0;
   if (build_tiles(system, binning, neigh_cut)) {
-    // fast path: exact CSR rows emitted from the tile lists (same rows, same order)
-    if (emd_neigh_tiles_count(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_offsets.ptr, &total))
-      fail("NeighborCSR", "tiles count");
-    if (neighs.extent() < (size_t)total) {
-      if (!neighs.alloc((size_t)total + total / 16)) fail("NeighborCSR", "alloc entries");
+    // fast path: exact CSR rows made from the tile search (same rows, same order); 3 = a tile outgrew the fast path
+    const int rc = emd_neigh_tiles_count(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_offsets.ptr, &total);
+    if (rc != 0 && rc != 3) fail("NeighborCSR", "tiles count");
+    if (rc == 0) {
+      if (neighs.extent() < (size_t)total) {
+        if (!neighs.alloc((size_t)total + total / 16)) fail("NeighborCSR", "alloc entries");
+      }
+      if (emd_neigh_tiles_fill_csr(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_offsets.ptr, neighs.ptr))
+        fail("NeighborCSR", "tiles fill");
+      neigh_list.row_map = neigh_offsets.ptr;
+      neigh_list.entries = neighs.ptr;
+      neigh_list.N_local = N_local;
+      neigh_list.total = total;
+      return;
     }
-    if (emd_neigh_tiles_fill_csr(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_offsets.ptr, neighs.ptr))
-      fail("NeighborCSR", "tiles fill");
-    neigh_list.row_map = neigh_offsets.ptr;
-    neigh_list.entries = neighs.ptr;
-    neigh_list.N_local = N_local;
-    neigh_list.total = total;
-    return;
+    emd_tiles_invalidate(tile_lists);
   }
   if (emd_neigh_csr_count(system->ctx, system->x, N_local, &g, binning->bincount, binning->binoffsets,
                           binning->permute_vector, neigh_cut, half_neigh_, comm_newton, neigh_offsets.ptr, &total))
@@ -67,7 +70,7 @@ void Neighbor2D::create_neigh_list(System *system, Binning *binning, bool half_n
   const emd_bin_geom g = binning->geom();
   fill_passes = 0;
   bool resize;
-  const bool fast = build_tiles(system, binning, neigh_cut);
+  bool fast = build_tiles(system, binning, neigh_cut);
   do {
     if (rows_cap < (size_t)N_local + 1 || cols_cap != (size_t)neigh_list.maxneighs) {
       rows_cap = (size_t)N_local + 1;
@@ -75,10 +78,14 @@ void Neighbor2D::create_neigh_list(System *system, Binning *binning, bool half_n
       if (!neighs_buf.alloc(rows_cap * cols_cap)) fail("Neighbor2D", "alloc neighs");
     }
     int max_count = 0;
+    int rc2d = 3;
     if (fast) {
-      if (emd_neigh_tiles_fill_2d(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_list.maxneighs, num_neighs_buf.ptr,
-                                  neighs_buf.ptr, &max_count))
-        fail("Neighbor2D", "tiles fill");
+      rc2d = emd_neigh_tiles_fill_2d(system->ctx, tile_lists, half_neigh_, comm_newton, neigh_list.maxneighs, num_neighs_buf.ptr,
+                                     neighs_buf.ptr, &max_count);
+      if (rc2d != 0 && rc2d != 3) fail("Neighbor2D", "tiles fill");
+      if (rc2d == 3) { emd_tiles_invalidate(tile_lists); fast = false; }
+    }
+    if (rc2d == 0) {
     } else if (emd_neigh_2d_fill(system->ctx, system->x, N_local, &g, binning->bincount, binning->binoffsets,
                           binning->permute_vector, neigh_cut, half_neigh_, comm_newton, neigh_list.maxneighs,
                           num_neighs_buf.ptr, neighs_buf.ptr, &max_count))

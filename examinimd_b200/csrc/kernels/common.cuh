@@ -63,6 +63,7 @@ struct emd_ctx {
   int *h_pinned = nullptr;            // small pinned staging area for scalar read-backs (64 ints)
   // LJ parameters
   emd::LJParams lj;
+  unsigned long long lj_version = 0; // bumped by emd_force_lj_set_params (device copies of the table are uploaded once per version)
   double *d_lj_tables = nullptr; // for ntypes > 12: [3][ntypes][ntypes]
   int lj_tables_ntypes = 0;
 };

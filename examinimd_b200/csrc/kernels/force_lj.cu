@@ -220,6 +220,7 @@ int emd_force_lj_set_params(emd_ctx *ctx, int ntypes, const double *h_lj1, const
     return 1;
   }
   ctx->lj.ntypes = ntypes;
+  ctx->lj_version++;
   memset(ctx->lj.lj1, 0, sizeof ctx->lj.lj1);
   memset(ctx->lj.lj2, 0, sizeof ctx->lj.lj2);
   memset(ctx->lj.cutsq, 0, sizeof ctx->lj.cutsq);

@@ -3,26 +3,34 @@
 //
 // Why (measured on B200, profiles/r01_microbench_b200.json): a thread-per-atom walk over a CSR
 // list is bound by the L1/L2 gather of x[j] (184 G rows/s) and, for Newton-3 half lists, by
-// REDG.F64 (224 Gop/s; shared-memory FP64 atomics are CAS loops) -- 14 % FP64-pipe use at
-// 0.96 ms for 2 M atoms.  FP64 FMA issue (36.8 TFLOP/s) is the cheap resource on this part, so
-// the fast path recomputes each pair from both sides instead of scattering -f to j, and serves
-// every x[j] from shared memory:
+// REDG.F64 (224 Gop/s; shared-memory FP64 atomics are CAS loops).  FP64 FMA issue (36.8 TFLOP/s)
+// is the cheap resource on this part, so the fast path recomputes each pair from both sides
+// instead of scattering -f to j, and serves every x[j] from shared memory:
 //
 //   * the interior bins of BinningKKSort's grid are grouped into tiles of tx*ty*tz cells; one
 //     CTA owns one tile and stages the coordinates of the (tx+2)(ty+2)(tz+2) cells around it
-//     ONCE (coalesced: atoms are cell-sorted), ~6x re-read instead of 78 gathers per atom;
-//   * the neighbor build emits, next to the reference's CSR/2D list, a tile-local FULL adjacency
-//     in ELL layout (uint16 slot numbers into the staged array, 4 entries packed per 8-byte
-//     word, atom-major so a warp reads 256 contiguous bytes per 4 neighbors).  It is filled by
-//     an FP32 pre-filter with a conservative radius (warp = one cell, broadcast LDS of the
-//     candidate, 7 FP32 ops per pair instead of 8 FP64); the exact FP64 inclusion test of the
-//     reference (rsq <= cut*cut, no FMA contraction; half-list owner rule) is applied when the
-//     CSR/2D list is emitted from it, so the API-visible list is bit-identical to the reference
-//     and the ELL list is a superset that differs only by pairs within 1e-4 of the list radius
-//     (which the force kernel's own cutoff test rejects);
-//   * the force kernel walks the ELL rows with x[j] from shared memory, f_i in registers, one
-//     coalesced store per atom, no atomics, no zero-f pass; the summation order is the
-//     reference's serial row order.
+//     ONCE (coalesced: atoms are cell-sorted);
+//   * the neighbor build is three kernels per re-neighboring:
+//       tiles_search_kernel  warp = one interior cell, lane = atom; every candidate of the 27-bin
+//                            stencil costs 6 instructions (broadcast LDS.128 of a pre-scaled FP32
+//                            record, 3 FFMA, FADD, funnel shift of the sign bit) and leaves ONE BIT
+//                            in a mask word -- a conservative FP32 superset of the list;
+//       tiles_lists_kernel   thread = atom row: pops the mask bits, applies the reference's exact
+//                            FP64 inclusion test (rsq <= cut*cut, no FMA contraction; half-list
+//                            owner rule) and leaves the exact rows as 16-bit staged-slot numbers
+//                            in the reference's order + their lengths (= CSR row counts); in the
+//                            same pass the FP32 superset is re-ordered in shared memory into the
+//                            force kernel's bank-conflict-free column layout and written ONCE;
+//       tiles_fill_kernel    CSR entries / 2D table = slot numbers -> atom indices at the offsets
+//                            of the scanned counts: no coordinates, no arithmetic.
+//     The API-visible list is bit-identical to the reference's; the force kernel's list is a
+//     superset that differs only by pairs within ~1e-4 of the list radius (which the force
+//     kernel's own cutoff test rejects);
+//   * the force kernel walks its rows with x[j] from shared memory, f_i in registers, one
+//     coalesced store per atom, no atomics, no zero-f pass.  Warps are decoupled: coordinate
+//     buffers are handed from the producer warp to the consumers and back through mbarriers
+//     (cp.async completion -> `full`, one arrival per warp -> `empty`); there is no CTA-wide barrier in the
+//     tile loop, and a warp may run up to two tiles ahead of the slowest one.
 //
 // Replaces, when applicable (list radius <= bin width, tile fits in shared memory):
 //   NeighborCSR/2D::create_neigh_list  src/neighbor_types/neighbor_csr.h:370-435, neighbor_2d.h:280-331
@@ -42,41 +50,52 @@ namespace {
 
 constexpr int kMaxStagedCells = 400;
 constexpr int kMaxInteriorCells = 128;
-constexpr int kFilterThreads = 256;
+constexpr int kSearchThreads = 256;
+constexpr int kRowThreads = 384;  // dense atom slots (rows) per tile = threads of the lists / fill / force kernels
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kDummySlots = 16;   // the force kernel's coordinate buffers start with 16 far-away atoms (one per bank), the targets of padding entries
+constexpr int kCapMax = 2688;     // (kDummySlots + cap) * 24 must fit in 16 bits
+constexpr int kMaxRowLimit = 248; // bucket heads and counts of the bank sort are bytes
+constexpr double kFarAway = 1e100;
+
+enum { OVF_CAP = 1, OVF_INT = 2, OVF_ROW = 4, OVF_WORDS = 8 };
+enum { FL_BITS = 0, FL_NEED_ROW = 1, FL_NEED_CAP = 2, FL_NEED_INT = 3, FL_OWNED_ROWS = 4, FL_NFREE = 5, FL_NEED_WORDS = 6, FL_MAX2D = 7, FL_COUNT = 16 };
 
 struct TileArgs {
   int nbx, nby, nbz, nhalo; // bin grid incl. halo bins
   int tx, ty, tz;           // interior cells per tile
   int ntx, nty, ntz;        // tiles per dimension
-  int stride;               // atom slots (= threads of the per-atom kernels) per tile, multiple of 32
-  int maxrow;               // ELL row capacity, multiple of 8
-  int cap;                  // staged-atom capacity of the shared-memory arrays
+  int stride;               // row slots per tile (= kRowThreads)
+  int maxrow;               // row capacity (entries), multiple of 8, <= kMaxRowLimit
+  int cap;                  // staged-atom capacity of the shared-memory arrays, multiple of 32
+  int fcap;                 // the force kernel's coordinate buffers: the largest tile of this build, multiple of 32 (<= cap)
   int n_local;
   const int *bincount, *binoffsets, *permute;
   const double *x;
   const int *type;
   double ox, oy, oz; // bin grid origin
   double wx, wy, wz; // bin widths
-  unsigned short *ell; // [ntiles][maxrow/8][stride][8]: 8 entries of one atom = one 16-byte word
+  // search result: the FP32 superset rows in list order (the stencil is 9 runs of 3 z-adjacent bins = 9 contiguous
+  // staged-slot ranges, walked in the reference's order), staged-slot numbers, 8 per 16-byte word
+  unsigned short *ell; // [ntiles][maxrow/8][stride][8]
   int *nell;           // [ntiles][stride]
-  // the same adjacency re-ordered for the force kernel (tiles_schedule_kernel): every warp's rows are laid
-  // out in COLUMNS that a half-warp can read from shared memory without bank conflicts.  Entries with bit 15
-  // set are padding (the slot in the low bits is one another lane of the half-warp reads in that column).
-  unsigned short *ell_s; // [ntiles][maxrow_s/8][stride][8]
+  // exact rows (reference order, reference inclusion rules) as staged-slot numbers, 8 per 16-byte word
+  unsigned short *csr16; // [ntiles][maxrow/8][stride][8]
+  int *ncsr;             // [ntiles][stride] exact row lengths
+  // the force kernel's rows: the FP32 superset in COLUMNS that a half-warp reads from shared memory without bank
+  // conflicts; an entry is the BYTE offset 24*slot of the neighbor's coordinates; padding entries point at a dummy slot
+  unsigned short *ell_s; // [ntiles][maxrow/8][stride][8]
   int *nell_s;           // [ntiles][stride]: columns of the thread's warp, multiple of 8
-  int maxrow_s;          // column capacity, multiple of 8
-  // per-tile staging tables written once per build (tiles_tables_kernel), so that the per-step
-  // force kernel needs no cell arithmetic: global index of every staged slot, and for every
-  // dense atom slot its staged slot / global index
-  int *stg_j;                // [ntiles][cap]
+  // per-tile staging tables, so that the per-step force kernel needs no cell arithmetic
+  int *stg_j;                // [ntiles][cap]  global index of every staged slot
   int *stg_n;                // [ntiles]  staged atoms
-  unsigned short *int_slot;  // [ntiles][stride]
-  int *int_glob;             // [ntiles][stride]  (>= n_local or 0x7fffffff: no row)
+  unsigned short *int_slot;  // [ntiles][stride]  staged slot of the row's own atom
+  int *int_glob;             // [ntiles][stride]  its global index (>= n_local or 0x7fffffff: no row)
   // tiles whose staged cells hold only owned atoms come first in `order` (their forces do not depend on the halo, so a
   // decomposed run computes them while the halo exchange is in flight); has_ghost[tile] is the classification
-  int *order;          // [ntiles] tile numbers, halo-independent tiles first (stable)
+  int *order;          // [ntiles]
   int *has_ghost;      // [ntiles]
-  int *flags;          // [0] overflow bits (1 staged, 2 interior, 4 row)  [1] max row  [2] max staged  [3] max interior
+  int *flags;          // FL_*
 };
 
 struct TileCtx {
@@ -112,8 +131,9 @@ __device__ __forceinline__ int staged_of_interior(const TileCtx &t, const TileAr
   return ((cx + 1) * t.syn + (cy + 1)) * t.szn + (cz + 1);
 }
 
-// cell tables of this CTA's tile: s_start[c] = first staged slot of staged cell c, s_goff[c] =
-// its offset in the permute vector, s_ibase[ci] = first dense atom slot of interior cell ci
+// cell tables of this CTA's tile: s_start[c] = first staged slot of staged cell c (cells z-fastest, so the three
+// z-adjacent cells of a stencil run are one contiguous slot range), s_goff[c] = its offset in the permute vector,
+// s_ibase[ci] = first dense atom slot of interior cell ci
 __device__ __forceinline__ void tile_setup(const TileArgs &a, TileCtx &t, int *s_start, int *s_goff, int *s_ibase) {
   t.tile = blockIdx.x;
   const int tZ = t.tile % a.ntz, tY = (t.tile / a.ntz) % a.nty, tX = t.tile / (a.ntz * a.nty);
@@ -145,68 +165,55 @@ __device__ __forceinline__ void tile_setup(const TileArgs &a, TileCtx &t, int *s
   t.n_int = s_ibase[t.nci];
 }
 
-enum { ST_F32 = 1, ST_F64 = 2, ST_J = 4, ST_TYPE = 8, ST_AOS = 16 }; // ST_AOS: FP64 coordinates as sx[3*slot + {0,1,2}]
-
-template <int WHAT>
-__device__ __forceinline__ void tile_stage(const TileArgs &a, const TileCtx &t, const int *s_start, const int *s_goff,
-                                           float4 *sf, double *sx, double *sy, double *sz, int *sj, unsigned char *st) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // FP32 coordinates are relative to the staged region's low corner
-  const double cx0 = a.ox + (t.bx0 - 1) * a.wx, cy0 = a.oy + (t.by0 - 1) * a.wy, cz0 = a.oz + (t.bz0 - 1) * a.wz;
-  for (int c = warp; c < t.ncs; c += nwarps) {
-    const int base = s_start[c], n = s_start[c + 1] - base, goff = s_goff[c];
-    for (int k = lane; k < n; k += 32) {
-      const int j = a.permute[goff + k];
-      const double xj = a.x[3 * (size_t)j], yj = a.x[3 * (size_t)j + 1], zj = a.x[3 * (size_t)j + 2];
-      const int s = base + k;
-      if (WHAT & ST_F32) sf[s] = make_float4((float)(xj - cx0), (float)(yj - cy0), (float)(zj - cz0), 0.f);
-      if (WHAT & ST_F64) { sx[s] = xj; sy[s] = yj; sz[s] = zj; }
-      if (WHAT & ST_AOS) { sx[3 * s] = xj; sx[3 * s + 1] = yj; sx[3 * s + 2] = zj; }
-      if (WHAT & ST_J) sj[s] = j;
-      if (WHAT & ST_TYPE) st[s] = (unsigned char)a.type[j];
-    }
-  }
+// stencil run r (0..8) of the interior cell whose staged index is c_i: staged slots [lo, hi)
+__device__ __forceinline__ void stencil_run(const TileCtx &t, const int *s_start, int c_i, int r, int &lo, int &hi) {
+  const int c0 = c_i + ((r / 3 - 1) * t.syn + (r % 3 - 1)) * t.szn - 1;
+  lo = s_start[c0];
+  hi = s_start[c0 + 3];
 }
 
-// dense atom slot t -> staged slot / global index of the interior atoms
-__device__ __forceinline__ void tile_interior_table(const TileArgs &a, const TileCtx &t, const int *s_start, const int *s_goff,
-                                                    const int *s_ibase, unsigned short *s_islot, int *s_iglob) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int ci = warp; ci < t.nci; ci += nwarps) {
-    const int n = s_ibase[ci + 1] - s_ibase[ci];
-    if (n == 0) continue;
-    const int c = staged_of_interior(t, a, ci);
-    for (int k = lane; k < n; k += 32) {
-      s_islot[s_ibase[ci] + k] = (unsigned short)(s_start[c] + k);
-      if (s_iglob) s_iglob[s_ibase[ci] + k] = a.permute[s_goff[c] + k];
-    }
-  }
-}
-
-__device__ __forceinline__ size_t ell_index(const TileArgs &a, int tile, int q, int t) {
-  return (((size_t)tile * (a.maxrow >> 3) + (q >> 3)) * a.stride + t) * 8 + (q & 7);
-}
-
-// ---------------------------------------------------------------------------- FP32 pre-filter
-// warp = one interior cell (lane = atom), candidates broadcast from shared memory in the
-// reference's stencil order (bx-1..bx+1, by, bz; permute order inside a bin)
-__global__ void __launch_bounds__(kFilterThreads) tiles_filter_kernel(TileArgs a, float cutf2) {
-  __shared__ int s_start[kMaxStagedCells + 1], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
+// --------------------------------------------------------------------------------- search
+// FP32 record of a staged atom, relative to the centre of the staged region: (-2x, -2y, -2z, x^2+y^2+z^2).
+// r^2(i,j) = |p_i|^2 + (w_j + x_i X_j + y_i Y_j + z_i Z_j): three FFMA per candidate; the candidate is kept when
+// r^2 - thr2 < 0, whose sign bit is shifted into the mask word.  thr2 carries the rounding margin of this form
+// (|p| <= half the staged extent), so the mask is a superset of the exact list.
+__global__ void __launch_bounds__(kSearchThreads) tiles_search_kernel(TileArgs a, float thr2) {
+  __shared__ int s_start[kMaxStagedCells + 4], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
   extern __shared__ __align__(16) unsigned char dyn[];
   float4 *sf = reinterpret_cast<float4 *>(dyn);
   TileCtx t;
   tile_setup(a, t, s_start, s_goff, s_ibase);
   if (threadIdx.x == 0) {
-    atomicMax(&a.flags[2], t.total);
-    atomicMax(&a.flags[3], t.n_int);
-    if (t.total > a.cap || t.total > 65535) atomicOr(&a.flags[0], 1);
-    if (t.n_int > a.stride) atomicOr(&a.flags[0], 2);
+    atomicMax(&a.flags[FL_NEED_CAP], t.total);
+    atomicMax(&a.flags[FL_NEED_INT], t.n_int);
+    if (t.total > a.cap) atomicOr(&a.flags[FL_BITS], OVF_CAP);
+    if (t.n_int > a.stride) atomicOr(&a.flags[FL_BITS], OVF_INT);
+    a.stg_n[t.tile] = min(t.total, a.cap);
   }
-  if (t.total > a.cap || t.total > 65535 || t.n_int > a.stride) return;
-  for (int k = t.n_int + threadIdx.x; k < a.stride; k += blockDim.x) a.nell[(size_t)t.tile * a.stride + k] = 0;
-  tile_stage<ST_F32>(a, t, s_start, s_goff, sf, nullptr, nullptr, nullptr, nullptr, nullptr);
-  __syncthreads();
+  if (t.total > a.cap || t.n_int > a.stride) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const double cx0 = a.ox + (t.bx0 - 1 + 0.5 * t.sxn) * a.wx, cy0 = a.oy + (t.by0 - 1 + 0.5 * t.syn) * a.wy,
+               cz0 = a.oz + (t.bz0 - 1 + 0.5 * t.szn) * a.wz;
+  // stage the records and write the staging table of the force kernel
+  int ghost = 0;
+  for (int c = warp; c < t.ncs; c += nwarps) {
+    const int base = s_start[c], n = s_start[c + 1] - base, goff = s_goff[c];
+    for (int k = lane; k < n; k += 32) {
+      const int j = a.permute[goff + k];
+      const float xr = (float)(a.x[3 * (size_t)j] - cx0), yr = (float)(a.x[3 * (size_t)j + 1] - cy0), zr = (float)(a.x[3 * (size_t)j + 2] - cz0);
+      sf[base + k] = make_float4(-2.f * xr, -2.f * yr, -2.f * zr, fmaf(zr, zr, fmaf(yr, yr, xr * xr)));
+      a.stg_j[(size_t)t.tile * a.cap + base + k] = j;
+      ghost |= (j >= a.n_local);
+    }
+  }
+  ghost = __syncthreads_or(ghost);
+  if (threadIdx.x == 0) a.has_ghost[t.tile] = ghost ? 1 : 0;
+  for (int k = t.n_int + threadIdx.x; k < a.stride; k += blockDim.x) {
+    a.nell[(size_t)t.tile * a.stride + k] = 0;
+    a.int_slot[(size_t)t.tile * a.stride + k] = 0;
+    a.int_glob[(size_t)t.tile * a.stride + k] = 0x7fffffff;
+  }
+  int owned_rows = 0;
   for (int ci = warp; ci < t.nci; ci += nwarps) {
     const int cnt = s_ibase[ci + 1] - s_ibase[ci];
     if (cnt == 0) continue;
@@ -217,27 +224,52 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_filter_kernel(TileArgs a
       const int i_glob = in_cell ? a.permute[s_goff[c_i] + k] : 0x7fffffff;
       const bool active = i_glob < a.n_local; // neighbor_csr.h:184 (ghosts inside interior bins get no row)
       const int own = s_start[c_i] + k;
-      const float4 p = in_cell ? sf[own] : make_float4(0.f, 0.f, 0.f, 0.f);
       const int tslot = s_ibase[ci] + k;
+      if (in_cell) {
+        a.int_slot[(size_t)t.tile * a.stride + tslot] = (unsigned short)own;
+        a.int_glob[(size_t)t.tile * a.stride + tslot] = i_glob;
+        owned_rows += active;
+      }
+      const float4 me = in_cell ? sf[own] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float xi = -0.5f * me.x, yi = -0.5f * me.y, zi = -0.5f * me.z, ci_thr = thr2 - me.w;
       // Accepted slots are shifted into a 64-bit accumulator from the top (after four of them the first sits in the low 16
-      // bits) and leave as whole 16-byte words: one store per 8 entries instead of eight 2-byte stores with their index math.
+      // bits) and leave as whole 16-byte words: one store per 8 entries.
       int q = 0;
-      unsigned long long acc = 0ull, lo = 0ull;
+      unsigned long long acc = 0ull, lo64 = 0ull;
       uint4 *const wrow = reinterpret_cast<uint4 *>(a.ell) + ((size_t)t.tile * (a.maxrow >> 3)) * a.stride + tslot;
-      for (int sc = 0; sc < 27; sc++) {
-        const int c = c_i + ((sc / 9 - 1) * t.syn + ((sc / 3) % 3 - 1)) * t.szn + (sc % 3 - 1);
-        const int e = s_start[c + 1];
+      for (int r = 0; r < 9; r++) {
+        int lo, hi;
+        stencil_run(t, s_start, c_i, r, lo, hi);
+        for (int s = lo; s < hi; s += 32) {
+          const int n = min(32, hi - s);
+          unsigned m = 0u;
+          const float4 *cand = sf + s; // same address in every lane: broadcast
+          if (n == 32) {
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+              const float4 pj = cand[u];
+              const float d = fmaf(zi, pj.z, fmaf(yi, pj.y, fmaf(xi, pj.x, pj.w))) - ci_thr;
+              m = __funnelshift_l(__float_as_uint(d), m, 1);
+            }
+          } else {
 #pragma unroll 4
-        for (int s = s_start[c]; s < e; s++) {
-          const float4 pj = sf[s]; // same address in every lane: broadcast
-          const float dx = p.x - pj.x, dy = p.y - pj.y, dz = p.z - pj.z;
-          const float r2 = dx * dx + dy * dy + dz * dz;
-          if (active && r2 <= cutf2 && s != own) {
-            acc = (acc >> 16) | ((unsigned long long)s << 48);
+            for (int u = 0; u < n; u++) {
+              const float4 pj = cand[u];
+              const float d = fmaf(zi, pj.z, fmaf(yi, pj.y, fmaf(xi, pj.x, pj.w))) - ci_thr;
+              m = __funnelshift_l(__float_as_uint(d), m, 1);
+            }
+          }
+          unsigned word = __brev(m) >> (32 - n); // bit u = candidate s + u
+          if ((unsigned)(own - s) < (unsigned)n) word &= ~(1u << (own - s));
+          if (!active) word = 0u;
+          while (word) { // list order = ascending slot
+            const unsigned slot = (unsigned)(s + __ffs(word) - 1);
+            word &= word - 1;
+            acc = (acc >> 16) | ((unsigned long long)slot << 48);
             q++;
             if ((q & 3) == 0) {
-              if (q & 4) lo = acc;
-              else if (q <= a.maxrow) wrow[(size_t)((q >> 3) - 1) * a.stride] = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)acc, (unsigned)(acc >> 32));
+              if (q & 4) lo64 = acc;
+              else if (q <= a.maxrow) wrow[(size_t)((q >> 3) - 1) * a.stride] = make_uint4((unsigned)lo64, (unsigned)(lo64 >> 32), (unsigned)acc, (unsigned)(acc >> 32));
             }
           }
         }
@@ -245,61 +277,25 @@ __global__ void __launch_bounds__(kFilterThreads) tiles_filter_kernel(TileArgs a
       if (in_cell) {
         const int rem = q & 7;
         if (rem && q < a.maxrow) { // the last, partial word (entries beyond the row length are never read)
-          unsigned long long hi = 0ull;
-          if (rem < 4) lo = acc >> (16 * (4 - rem));
-          else if (rem > 4) hi = acc >> (16 * (8 - rem));
-          wrow[(size_t)(q >> 3) * a.stride] = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+          unsigned long long hi64 = 0ull;
+          if (rem < 4) lo64 = acc >> (16 * (4 - rem));
+          else if (rem > 4) hi64 = acc >> (16 * (8 - rem));
+          wrow[(size_t)(q >> 3) * a.stride] = make_uint4((unsigned)lo64, (unsigned)(lo64 >> 32), (unsigned)hi64, (unsigned)(hi64 >> 32));
         }
         a.nell[(size_t)t.tile * a.stride + tslot] = min(q, a.maxrow);
-        if (q > a.maxrow) { atomicOr(&a.flags[0], 4); atomicMax(&a.flags[1], q); }
+        if (q > a.maxrow) { atomicOr(&a.flags[FL_BITS], OVF_ROW); atomicMax(&a.flags[FL_NEED_ROW], q); }
       }
     }
   }
-}
-
-// per-tile staging tables for the force kernel (see TileArgs)
-__global__ void __launch_bounds__(kFilterThreads) tiles_tables_kernel(TileArgs a) {
-  __shared__ int s_start[kMaxStagedCells + 1], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
-  TileCtx t;
-  tile_setup(a, t, s_start, s_goff, s_ibase);
-  if (t.total > a.cap || t.n_int > a.stride) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  if (threadIdx.x == 0) a.stg_n[t.tile] = t.total;
-  int ghost = 0, owned_rows = 0;
-  for (int c = warp; c < t.ncs; c += nwarps) {
-    const int base = s_start[c], n = s_start[c + 1] - base, goff = s_goff[c];
-    for (int k = lane; k < n; k += 32) {
-      const int j = a.permute[goff + k];
-      a.stg_j[(size_t)t.tile * a.cap + base + k] = j;
-      ghost |= (j >= a.n_local);
-    }
-  }
-  ghost = __syncthreads_or(ghost);
-  if (threadIdx.x == 0) a.has_ghost[t.tile] = ghost ? 1 : 0;
-  for (int k = t.n_int + threadIdx.x; k < a.stride; k += blockDim.x) {
-    a.int_slot[(size_t)t.tile * a.stride + k] = 0;
-    a.int_glob[(size_t)t.tile * a.stride + k] = 0x7fffffff;
-  }
-  for (int ci = warp; ci < t.nci; ci += nwarps) {
-    const int n = s_ibase[ci + 1] - s_ibase[ci];
-    if (n == 0) continue;
-    const int c = staged_of_interior(t, a, ci);
-    for (int k = lane; k < n; k += 32) {
-      const int ig = a.permute[s_goff[c] + k];
-      a.int_slot[(size_t)t.tile * a.stride + s_ibase[ci] + k] = (unsigned short)(s_start[c] + k);
-      a.int_glob[(size_t)t.tile * a.stride + s_ibase[ci] + k] = ig;
-      owned_rows += (ig < a.n_local);
-    }
-  }
-  // flags[4]: owned atoms that have a row (= n_local unless an owned atom sits outside the interior bins, which the
-  // reference leaves without neighbors, neighbor_csr.h:184; the fused force + integrator launch requires equality)
+  // flags[FL_OWNED_ROWS]: owned atoms that have a row (= n_local unless an owned atom sits outside the interior bins, which
+  // the reference leaves without neighbors, neighbor_csr.h:184; the fused force + integrator launch requires equality)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) owned_rows += __shfl_down_sync(0xffffffffu, owned_rows, o);
-  if (lane == 0 && owned_rows) atomicAdd(&a.flags[4], owned_rows);
+  if (lane == 0 && owned_rows) atomicAdd(&a.flags[FL_OWNED_ROWS], owned_rows);
 }
 
 // order[]: halo-independent tiles first, then the others, each group in tile order.  One block: every thread owns a
-// contiguous chunk of tiles; flags[2] receives the number of halo-independent tiles.
+// contiguous chunk of tiles; flags[FL_NFREE] receives the number of halo-independent tiles.
 __global__ void __launch_bounds__(1024) tiles_order_kernel(TileArgs a, int ntiles) {
   __shared__ int s_cnt[1024];
   const int chunk = (ntiles + 1023) / 1024;
@@ -320,429 +316,298 @@ __global__ void __launch_bounds__(1024) tiles_order_kernel(TileArgs a, int ntile
     if (a.has_ghost[k]) a.order[total_free + (k - free_before)] = k;
     else a.order[free_before++] = k;
   }
-  if (threadIdx.x == 0) a.flags[2] = total_free;
+  if (threadIdx.x == 0) a.flags[FL_NFREE] = total_free;
 }
 
-// ------------------------------------------------------- bank-conflict-free column schedule
-// The force kernel reads x[j] of 32 different neighbors per warp instruction from shared memory
-// (LDS.64, served per half-warp: 16 lanes x 8 bytes = one wavefront if the 16 words lie in 16
-// different bank pairs or are the same word).  In list order the 16 rows of a half-warp hit
-// ~2.5 words per bank pair (ncu: 57 % of the kernel's shared-memory wavefronts were conflicts
-// and the LSU pipe, not FP64, bounded it).  Rows are therefore re-ordered once per build:
-// column q of a half-warp holds, for every lane, an entry whose bank (slot mod 16: the AoS
-// stride 3 is odd, so x, y and z all map slot -> bank pair bijectively) is different from
-// every other lane's, or the SAME slot as another lane's (broadcast).  A lane with no such
-// entry left idles in that column (a flagged copy of a slot another lane reads).
-//
-// Greedy, lane after lane (lane 0 of the half-warp picks first): join a slot already taken in
-// this column if it is the head of one of my buckets (atoms of one cell share most neighbors),
-// else take, among my non-empty buckets whose bank is free, one that holds more than its share
-// of what I have left (the bottleneck banks drain first), searching from bank (q + lane) mod 16.
-// The lane-serial dependency is a systolic pipeline: at step t lane l works on column t - l and
-// reads the state its predecessors left for that column in a shared-memory ring, so a warp
-// schedules its two half-warps in (columns + 16) steps.  tools/sim_lds_conflicts.py models both
-// re-orderings on a reference liquid state (variants E and F): per 32 pairs and LDS.64, 5.6 wavefronts in list
-// order, 3.5 with the per-lane rotation, 2.15 (2 = conflict-free) with this schedule for 1 % more
-// columns than the longest row of the warp; the GPU test measures the same on the real lists.
-constexpr int kSchedWarps = 2;
-constexpr int kSchedMaxRow = 248;        // bucket positions and prefix sums are bytes
-constexpr unsigned kNoSlot = 0xffffu;    // head of an empty bucket
-constexpr unsigned kFreeBank = 0xfffeu;  // bank not taken in this column
+// ------------------------------------------------------------------ exact rows + force rows
+// Bank-conflict-free columns.  The force kernel reads x[j] of 32 different neighbors per warp instruction from shared
+// memory (LDS.64, served per half-warp: one wavefront if the 16 words lie in 16 different bank pairs or are the same
+// word).  In list order the 16 rows of a half-warp hit ~2.5 words per bank pair, and the shared-memory pipe, not FP64,
+// bounds the kernel (profiles/r01e).  Rows are therefore re-ordered once per build: counting sort of the row by bank
+// (slot mod 16: the AoS stride 3 is odd, so x, y and z all map slot -> bank pair bijectively), then lane l takes, at
+// column q, an entry of bank (q + l) mod 16 while it has one, else of a bank that still holds more than its share.
+// 1.1 instead of 3.6 extra wavefronts per half-warp column (test_tiles_force_rows_are_a_conflict_light_permutation).
+struct ListArgs {
+  double cutsq;
+  int half, newton;
+  int *counts; // counts[i] = exact row length (the CSR row_map before its scan), or nullptr
+};
 
-__device__ __forceinline__ unsigned nib_of_bytes(unsigned x) { // byte i non-zero (0xff) -> bit i
-  return ((x & 0x08040201u) * 0x01010101u) >> 24;
-}
-__device__ __forceinline__ unsigned half_eq_mask(const uint4 &h0, const uint4 &h1, const uint4 &t0, const uint4 &t1) {
-  // bit b set iff 16-bit element b of h equals element b of t
-  const unsigned e0 = __vcmpeq2(h0.x, t0.x), e1 = __vcmpeq2(h0.y, t0.y), e2 = __vcmpeq2(h0.z, t0.z), e3 = __vcmpeq2(h0.w, t0.w);
-  const unsigned e4 = __vcmpeq2(h1.x, t1.x), e5 = __vcmpeq2(h1.y, t1.y), e6 = __vcmpeq2(h1.z, t1.z), e7 = __vcmpeq2(h1.w, t1.w);
-  return nib_of_bytes(__byte_perm(e0, e1, 0x6420)) | (nib_of_bytes(__byte_perm(e2, e3, 0x6420)) << 4) |
-         (nib_of_bytes(__byte_perm(e4, e5, 0x6420)) << 8) | (nib_of_bytes(__byte_perm(e6, e7, 0x6420)) << 12);
-}
-__device__ __forceinline__ unsigned bytes_gt_mask(const uint4 &c, unsigned th) { // bit b set iff byte b of c > th
-  const unsigned t4 = th * 0x01010101u;
-  return nib_of_bytes(__vcmpgtu4(c.x, t4)) | (nib_of_bytes(__vcmpgtu4(c.y, t4)) << 4) | (nib_of_bytes(__vcmpgtu4(c.z, t4)) << 8) |
-         (nib_of_bytes(__vcmpgtu4(c.w, t4)) << 12);
-}
+// thread = row.  Pass A walks the row's words (8 entries each, independent of one another): bank histogram, exact FP64 test
+// of the reference (+ half-list owner rule) -> exact row (csr16) and its length.  Pass B scatters the entries into 16 bank
+// buckets in shared memory (the coordinates are dead by then: same memory).  Then the columns of the force row: round t of
+// a lane (hl = lane & 15) = the 16 columns 16t .. 16t+15, in which it visits the banks hl, hl+1, ... once each: column q
+// takes the (q >> 4)-th entry of bank (q + hl) & 15 (slot mod 16: the AoS stride 3 is odd, so x, y and z all map slot ->
+// bank pair bijectively) if the bucket is that deep.  Entries whose column does not exist (beyond the row length) are the
+// "excess"; they fill, in order, the columns whose bucket was too shallow.  As many excess entries as holes, so every
+// lane is done after n columns.  In list order the 16 rows of a half-warp hit ~2.5 words per bank pair and the
+// shared-memory pipe, not FP64, bounds the force kernel (profiles/r01e); with these columns every bank pair is hit by the
+// two lanes l, l+16 except where a hole was filled (test_tiles_force_rows_are_a_conflict_light_permutation).
+constexpr int kExcessRoom = 40; // bank-sorted row + its excess entries (typically < 25)
 
-size_t sched_warp_smem(int maxrow, int maxrow_s) {
-  return (size_t)32 * maxrow * 2 + (size_t)32 * maxrow_s * 2 + 32 * 16 * 2 /*hs*/ + 32 * 16 /*cnt*/ + 32 * 16 /*hp*/ + 2 * 32 * 16 * 2 /*ring*/ +
-         2 * 32 * 2 /*ring masks*/ + 128;
-}
-
-// MODE: SCHED_FULL = the conflict-free column schedule above; SCHED_ROT = every lane re-orders its own row so that at
-// column q it reads bank (q + lane) mod 16 whenever it still has an entry there (no negotiation between lanes: conflicts
-// remain where a bucket ran dry, 3.2 wavefronts per LDS.64 instead of 5.0 / 1.93, at a tenth of the scheduling cost);
-// SCHED_NONE = list order (rows longer than kSchedMaxRow), only the flagged padding.
-enum { SCHED_FULL = 0, SCHED_NONE = 1, SCHED_ROT = 2 };
-template <int MODE>
-__global__ void __launch_bounds__(32 * kSchedWarps) tiles_schedule_kernel(TileArgs a, int ntiles, unsigned warp_smem) {
+template <bool EXACT>
+__global__ void __launch_bounds__(kRowThreads, 2) tiles_lists_kernel(TileArgs a, ListArgs e, unsigned coords_bytes, int rowcap) {
+  __shared__ int s_start[kMaxStagedCells + 4], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
   extern __shared__ __align__(16) unsigned char dyn[];
+  // region A: FP64 coordinates + global indices while the exact rows are made, then the bank-sorted rows
+  double *sx = reinterpret_cast<double *>(dyn);                 // [cap][3]
+  int *sj = reinterpret_cast<int *>(dyn + (size_t)a.cap * 24);  // [cap]
+  unsigned short *srow = reinterpret_cast<unsigned short *>(dyn) + threadIdx.x;                  // srow[pos * kRowThreads]
+  unsigned short *state = reinterpret_cast<unsigned short *>(dyn + coords_bytes) + threadIdx.x;  // state[bank * kRowThreads]
+  TileCtx t;
+  tile_setup(a, t, s_start, s_goff, s_ibase);
+  if (t.total > a.cap || t.n_int > a.stride) return; // flagged by the search kernel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wrows = a.stride >> 5;
-  const long long gw = (long long)blockIdx.x * kSchedWarps + warp;
-  if (gw >= (long long)ntiles * wrows) return; // whole warps leave; no block-wide barrier below
-  const int tile = (int)(gw / wrows), ts = (int)(gw % wrows) * 32 + lane;
-  unsigned char *base = dyn + (size_t)warp * warp_smem;
-  unsigned short *out = reinterpret_cast<unsigned short *>(base);                 // [lane][maxrow_s]
-  unsigned short *srow = out + 32 * a.maxrow_s;                                    // [pos][lane], bank-sorted
-  unsigned short *hs = srow + 32 * a.maxrow;                                       // [lane][16] slot at the head of every bucket
-  unsigned short *ring = hs + 32 * 16;                                             // [half][32 columns][16] slot taken per bank
-  unsigned short *rmask = ring + 2 * 32 * 16;                                      // [half][32] taken banks
-  unsigned char *cnt = reinterpret_cast<unsigned char *>(rmask + 2 * 32);          // [lane][16]
-  unsigned char *hp = cnt + 32 * 16;                                               // [lane][16] position of the bucket head in srow
-
-  const int n = a.nell[(size_t)tile * a.stride + ts];
-  const unsigned own = a.int_slot[(size_t)tile * a.stride + ts];
-  const uint4 *row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)tile * (a.maxrow >> 3)) * a.stride + ts;
-  { // every column starts as padding
-    const unsigned pad2 = (0x8000u | own) * 0x00010001u;
-    uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)lane * a.maxrow_s);
-    for (int c = 0; c < (a.maxrow_s >> 3); c++) o[c] = make_uint4(pad2, pad2, pad2, pad2);
-  }
-  int last = 0;      // columns this lane really uses
-  bool ovf = false;
-  int need = 0;
-  if (MODE == SCHED_NONE) {
-    if (n > a.maxrow_s) { ovf = true; need = n; }
-    else {
-      for (int c = 0; c * 8 < n; c++) {
-        const uint4 w = row[(size_t)c * a.stride];
-        const unsigned e[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          if (c * 8 + k < n) out[(size_t)lane * a.maxrow_s + c * 8 + k] = (unsigned short)((e[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+  const bool ghost_rule = EXACT && e.half && !e.newton && a.has_ghost[t.tile]; // only then does j < n_local matter below
+  if (EXACT) {
+    for (int c = warp; c < t.ncs; c += kRowWarps) {
+      const int base = s_start[c], n = s_start[c + 1] - base, goff = s_goff[c];
+      for (int k = lane; k < n; k += 32) {
+        const int j = a.permute[goff + k];
+        const int s = base + k;
+        sx[3 * s] = a.x[3 * (size_t)j]; sx[3 * s + 1] = a.x[3 * (size_t)j + 1]; sx[3 * s + 2] = a.x[3 * (size_t)j + 2];
+        if (ghost_rule) sj[s] = j;
       }
-      last = n;
     }
-  } else {
-    // ---- counting sort of the row by bank (stable: buckets stay in ascending slot order)
-    unsigned long long c_lo = 0, c_hi = 0; // bucket sizes, one byte per bank
-    for (int c = 0; c * 8 < n; c++) {
-      const uint4 w = row[(size_t)c * a.stride];
-      const unsigned e[4] = {w.x, w.y, w.z, w.w};
+    __syncthreads();
+  }
+  const int ts = threadIdx.x;
+  const size_t rbase = (size_t)t.tile * a.stride + ts;
+  const int i = ts < t.n_int ? a.int_glob[rbase] : 0x7fffffff;
+  const bool active = i < a.n_local;
+  const int own = active ? a.int_slot[rbase] : 0;
+  const int n = active ? a.nell[rbase] : 0;
+  const uint4 *const row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)t.tile * (a.maxrow >> 3)) * a.stride + ts;
+  const int nchunk = (n + 7) >> 3;
+  // ---- pass A
+  int count = 0;
+  unsigned long long cnt0 = 0ull, cnt1 = 0ull; // 16 bank counters, one byte each (a row holds <= 248 entries)
+  if (n > 0) {
+    double x_i = 0.0, y_i = 0.0, z_i = 0.0;
+    if (EXACT) { x_i = sx[3 * own]; y_i = sx[3 * own + 1]; z_i = sx[3 * own + 2]; }
+    const long long cutsq_bits = __double_as_longlong(e.cutsq);
+    unsigned long long acc = 0ull, lo = 0ull;
+    uint4 *const wrow = reinterpret_cast<uint4 *>(a.csr16) + ((size_t)t.tile * (a.maxrow >> 3)) * a.stride + ts;
+    uint4 cur = row[0];
+    for (int c = 0; c < nchunk; c++) {
+      const uint4 nxt = (c + 1 < nchunk) ? row[(size_t)(c + 1) * a.stride] : make_uint4(0, 0, 0, 0);
+      const unsigned w4[4] = {cur.x, cur.y, cur.z, cur.w};
+      bool keep[8];
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        if (c * 8 + k < n) {
-          const unsigned b = (e[k >> 1] >> (16 * (k & 1))) & 15u;
-          if (b < 8) c_lo += 1ull << (8 * b); else c_hi += 1ull << (8 * (b - 8));
+      for (int k = 0; k < 8; k++) {
+        const int slot = (int)((w4[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+        const bool valid = c * 8 + k < n;
+        if (valid) { // bank histogram
+          const unsigned long long inc = 1ull << ((slot & 7) * 8);
+          if (slot & 8) cnt1 += inc; else cnt0 += inc;
         }
-    }
-    const unsigned long long M = 0x0101010101010101ull;
-    const unsigned long long inc_lo = c_lo * M; // byte k = c_lo[0] + ... + c_lo[k]  (n <= 248: no carries)
-    const unsigned long long tot_lo = inc_lo >> 56;
-    const unsigned long long inc_hi = c_hi * M + tot_lo * M;
-    const unsigned long long st_lo = inc_lo << 8, st_hi = (inc_hi << 8) | tot_lo; // first position of every bucket
-    unsigned long long p_lo = st_lo, p_hi = st_hi;
-    for (int c = 0; c * 8 < n; c++) {
-      const uint4 w = row[(size_t)c * a.stride];
-      const unsigned e[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        if (c * 8 + k < n) {
-          const unsigned s = (e[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-          const unsigned b = s & 15u;
-          unsigned pos;
-          if (b < 8) { pos = (unsigned)(p_lo >> (8 * b)) & 0xffu; p_lo += 1ull << (8 * b); }
-          else { pos = (unsigned)(p_hi >> (8 * (b - 8))) & 0xffu; p_hi += 1ull << (8 * (b - 8)); }
-          srow[pos * 32 + lane] = (unsigned short)s;
-        }
-    }
-    unsigned N = 0; // non-empty buckets
-#pragma unroll
-    for (int b = 0; b < 16; b++) {
-      const unsigned cb = (unsigned)((b < 8 ? c_lo >> (8 * b) : c_hi >> (8 * (b - 8))) & 0xffu);
-      const unsigned sb = (unsigned)((b < 8 ? st_lo >> (8 * b) : st_hi >> (8 * (b - 8))) & 0xffu);
-      cnt[lane * 16 + b] = (unsigned char)cb;
-      hp[lane * 16 + b] = (unsigned char)sb;
-      hs[lane * 16 + b] = cb ? srow[sb * 32 + lane] : (unsigned short)kNoSlot;
-      if (cb) N |= 1u << b;
-    }
-    int rem = n;
-    const int half = lane >> 4, hl = lane & 15;
-    unsigned short *rg = ring + half * 32 * 16;
-    unsigned short *rm = rmask + half * 32;
-    unsigned big = 0;   // banks holding more than th entries
-    int th = -1;
-    __syncwarp();
-    for (int t = 0;; t++) {
-      if (!__any_sync(0xffffffffu, rem > 0)) break;
-      const int q = t - hl;
-      if (q >= 0) {
-        unsigned short *tq = rg + (q & 31) * 16;
-        if (hl == 0) { // first lane of the half-warp opens the column
-          const unsigned f2 = kFreeBank * 0x00010001u;
-          reinterpret_cast<uint4 *>(tq)[0] = make_uint4(f2, f2, f2, f2);
-          reinterpret_cast<uint4 *>(tq)[1] = make_uint4(f2, f2, f2, f2);
-          rm[q & 31] = 0;
-        }
-        if (rem > 0 && q >= a.maxrow_s) { ovf = true; need = q + rem; rem = 0; }
-        if (q < a.maxrow_s) {
-          const unsigned tm = rm[q & 31];
-          int b = -1;
-          bool join = false;
-          if (rem > 0) {
-            if (tm) {
-              const uint4 t0 = reinterpret_cast<const uint4 *>(tq)[0], t1 = reinterpret_cast<const uint4 *>(tq)[1];
-              const uint4 h0 = reinterpret_cast<const uint4 *>(hs + lane * 16)[0], h1 = reinterpret_cast<const uint4 *>(hs + lane * 16)[1];
-              const unsigned jm = half_eq_mask(h0, h1, t0, t1);
-              if (jm) { b = __ffs(jm) - 1; join = true; }
-            }
-            if (!join) {
-              const unsigned m = N & ~tm;
-              if (m) {
-                const int th_now = (rem + 15) >> 4;
-                if (th_now != th) { th = th_now; big = bytes_gt_mask(reinterpret_cast<const uint4 *>(cnt + lane * 16)[0], (unsigned)th); }
-                const unsigned mb = m & big;
-                const unsigned sel = mb ? mb : m;
-                const unsigned r = (unsigned)(q + hl) & 15u;
-                const unsigned rot = ((sel >> r) | (sel << (16 - r))) & 0xffffu;
-                b = (int)((__ffs(rot) - 1 + r) & 15u);
-              }
-            }
+        keep[k] = false;
+        if (EXACT) {
+          const double dx = x_i - sx[3 * slot], dy = y_i - sx[3 * slot + 1], dz = z_i - sx[3 * slot + 2];
+          bool kp = valid;
+          if (e.half) {
+            // neighbor_csr.h:290-291 (j != i by construction): j stays if it is a ghost without newton, or "greater" than i:
+            // x_j > x_i || (x_j == x_i && (y_j > y_i || (y_j == y_i && z_j > z_i))).  x_j > x_i <=> dx < 0 and x_j == x_i <=> dx == +0
+            // exactly (IEEE subtraction), so the rule is read off the sign / zero bits of the differences on the integer pipe.
+            const bool owned_j = ghost_rule ? sj[slot] < a.n_local : true; // newton on, or no ghost staged: the rule applies to every j
+            const long long bx = __double_as_longlong(dx), by = __double_as_longlong(dy), bz = __double_as_longlong(dz);
+            const bool greater = bx < 0 || (bx == 0 && (by < 0 || (by == 0 && bz < 0)));
+            kp = valid && (!owned_j || greater);
           }
-          if (b >= 0) {
-            const unsigned s = hs[lane * 16 + b];
-            out[(size_t)lane * a.maxrow_s + q] = (unsigned short)s;
-            const unsigned c = (unsigned)cnt[lane * 16 + b] - 1u, p = (unsigned)hp[lane * 16 + b] + 1u;
-            cnt[lane * 16 + b] = (unsigned char)c;
-            hp[lane * 16 + b] = (unsigned char)p;
-            hs[lane * 16 + b] = c ? srow[p * 32 + lane] : (unsigned short)kNoSlot;
-            if (!c) N &= ~(1u << b);
-            if ((int)c <= th) big &= ~(1u << b);
-            rem--;
-            last = q + 1;
-            if (!join) { tq[b] = (unsigned short)s; rm[q & 31] = (unsigned short)(tm | (1u << b)); }
-          } else if (tm) {
-            // idle: read what another lane of the half-warp reads in this column (no extra wavefront)
-            out[(size_t)lane * a.maxrow_s + q] = (unsigned short)(0x8000u | tq[__ffs(tm) - 1]);
+          const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          keep[k] = kp && __double_as_longlong(rsq) <= cutsq_bits; // rsq <= cutsq, neighbor_csr.h:206,299 (both non-negative: bit order)
+        }
+      }
+      if (EXACT) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (keep[k]) {
+            const unsigned long long slot = (w4[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            acc = (acc >> 16) | (slot << 48);
+            count++;
+            if ((count & 3) == 0) {
+              if (count & 4) lo = acc;
+              else wrow[(size_t)((count >> 3) - 1) * a.stride] = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)acc, (unsigned)(acc >> 32));
+            }
           }
         }
       }
-      __syncwarp();
+      cur = nxt;
+    }
+    if (EXACT) {
+      const int rem = count & 7;
+      if (rem) { // the last, partial word (count <= n <= maxrow)
+        unsigned long long hi = 0ull;
+        if (rem < 4) lo = acc >> (16 * (4 - rem));
+        else if (rem > 4) hi = acc >> (16 * (8 - rem));
+        wrow[(size_t)(count >> 3) * a.stride] = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+      }
+      if (e.counts) e.counts[i] = count;
     }
   }
-  const int cols = __reduce_max_sync(0xffffffffu, last);
-  if (__any_sync(0xffffffffu, ovf)) {
-    if (ovf) { atomicOr(&a.flags[0], 8); atomicMax(&a.flags[1], need); }
-    return;
-  }
-  const int c8 = (cols + 7) & ~7;
-  __syncwarp();
-  uint4 *dst = reinterpret_cast<uint4 *>(a.ell_s) + ((size_t)tile * (a.maxrow_s >> 3)) * a.stride + ts;
-  const uint4 *o = reinterpret_cast<const uint4 *>(out + (size_t)lane * a.maxrow_s);
-  for (int c = 0; c < (c8 >> 3); c++) dst[(size_t)c * a.stride] = o[c];
-  a.nell_s[(size_t)tile * a.stride + ts] = c8;
-}
-
-// The default re-ordering (SCHED_ROT), lean version: no negotiation between lanes, so no per-column state.  Per lane: the
-// bank-sorted row ([pos][lane]) and one word per bucket ([bank][lane]: head position | entries left << 8) in shared memory,
-// both laid out so that a warp access never has a bank conflict; 8 columns are emitted as one coalesced 16-byte word.
-constexpr int kRotWarps = 4;
-size_t rot_warp_smem(int maxrow) { return (size_t)32 * maxrow * sizeof(unsigned short) + 16 * 32 * sizeof(unsigned); }
-
-__global__ void __launch_bounds__(32 * kRotWarps) tiles_rotate_kernel(TileArgs a, int ntiles, unsigned warp_smem) {
-  extern __shared__ __align__(16) unsigned char dyn[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wrows = a.stride >> 5;
-  const long long gw = (long long)blockIdx.x * kRotWarps + warp;
-  if (gw >= (long long)ntiles * wrows) return;
-  const int tile = (int)(gw / wrows), ts = (int)(gw % wrows) * 32 + lane;
-  unsigned *state = reinterpret_cast<unsigned *>(dyn + (size_t)warp * warp_smem) + lane;       // state[bank * 32]
-  unsigned short *srow = reinterpret_cast<unsigned short *>(dyn + (size_t)warp * warp_smem + 16 * 32 * sizeof(unsigned)) + lane; // srow[pos * 32]
-  const int n = a.nell[(size_t)tile * a.stride + ts];
-  const unsigned own = a.int_slot[(size_t)tile * a.stride + ts];
-  const uint4 *__restrict__ row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)tile * (a.maxrow >> 3)) * a.stride + ts;
+  if (EXACT) a.ncsr[rbase] = count;
   const int nmax = __reduce_max_sync(0xffffffffu, n);
-  if (nmax > a.maxrow_s) {
-    if (lane == 0) { atomicOr(&a.flags[0], 8); atomicMax(&a.flags[1], nmax); }
-    return;
-  }
-  // counting sort by bank (stable): sizes -> starts -> scatter
-#pragma unroll
-  for (int b = 0; b < 16; b++) state[b * 32] = 0;
-  // (both passes request word c+1 before they work on word c: the row comes from DRAM)
-  uint4 wnext = n > 0 ? __ldg(row) : make_uint4(0, 0, 0, 0);
-  for (int c = 0; c * 8 < n; c++) {
-    const uint4 w = wnext;
-    if ((c + 1) * 8 < n) wnext = __ldg(row + (size_t)(c + 1) * a.stride);
-    const unsigned e[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (c * 8 + k < n) state[((e[k >> 1] >> (16 * (k & 1))) & 15u) * 32] += 1;
-  }
-  unsigned N = 0;
+  __syncthreads(); // every thread is done with the coordinates: region A becomes the bank-sorted rows
+  // ---- bucket heads from the histogram: state[b] = head position | entries << 8
   {
-    unsigned run = 0;
+    unsigned run = 0u;
 #pragma unroll
     for (int b = 0; b < 16; b++) {
-      const unsigned cb = state[b * 32];
-      state[b * 32] = run | (cb << 8);
-      if (cb) N |= 1u << b;
+      const unsigned cb = (unsigned)((b < 8 ? cnt0 : cnt1) >> ((b & 7) * 8)) & 0xffu;
+      state[b * kRowThreads] = (unsigned short)(run | (cb << 8));
       run += cb;
     }
   }
-  wnext = n > 0 ? __ldg(row) : make_uint4(0, 0, 0, 0);
-  for (int c = 0; c * 8 < n; c++) {
-    const uint4 w = wnext;
-    if ((c + 1) * 8 < n) wnext = __ldg(row + (size_t)(c + 1) * a.stride);
-    const unsigned e[4] = {w.x, w.y, w.z, w.w};
+  // ---- pass B: scatter into the buckets (stable: list order inside a bank)
+  if (n > 0) {
+    uint4 cur = row[0];
+    for (int c = 0; c < nchunk; c++) {
+      const uint4 nxt = (c + 1 < nchunk) ? row[(size_t)(c + 1) * a.stride] : make_uint4(0, 0, 0, 0);
+      const unsigned w4[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (c * 8 + k < n) {
-        const unsigned s = (e[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-        const unsigned st = state[(s & 15u) * 32];
-        srow[(st & 0xffu) * 32] = (unsigned short)s;
-        state[(s & 15u) * 32] = st + 1;
+      for (int k = 0; k < 8; k++) {
+        if (c * 8 + k < n) {
+          const unsigned slot = (w4[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+          const unsigned st = state[(slot & 15u) * kRowThreads];
+          srow[(st & 0xffu) * kRowThreads] = (unsigned short)slot;
+          state[(slot & 15u) * kRowThreads] = (unsigned short)(st + 1u);
+        }
       }
-  }
+      cur = nxt;
+    }
 #pragma unroll
-  for (int b = 0; b < 16; b++) { // heads back to the bucket starts
-    const unsigned st = state[b * 32];
-    state[b * 32] = st - (st >> 8);
+    for (int b = 0; b < 16; b++) { // heads back to the bucket starts
+      const unsigned st = state[b * kRowThreads];
+      state[b * kRowThreads] = (unsigned short)(st - (st >> 8));
+    }
   }
+  // ---- columns: 8 at a time as one coalesced 16-byte word
   const int hl = lane & 15;
-  const unsigned pad = 0x8000u | own;
-  unsigned big = 0;
-  int th = -1;
+  const int T = (n + 15) >> 4, last = n - 16 * (T - 1);
+  int nexc = 0;
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    const int c = state[b * kRowThreads] >> 8;
+    const int fe = T - ((((b - hl) & 15) >= last) ? 1 : 0); // first round of this bank that has no column
+    nexc += max(0, c - fe);
+  }
+  const bool plain = n + nexc > rowcap; // (pathological rows: bank-sorted order as it is)
+  if (!plain && nexc > 0) {
+    int k = n;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const unsigned st = state[b * kRowThreads];
+      const int S = st & 0xffu, c = st >> 8;
+      const int fe = T - ((((b - hl) & 15) >= last) ? 1 : 0);
+      for (int tt = fe; tt < c; tt++) srow[(k++) * kRowThreads] = srow[(S + tt) * kRowThreads];
+    }
+  }
+  int cursor = n;
   const int c8 = (nmax + 7) & ~7;
-  uint4 *dst = reinterpret_cast<uint4 *>(a.ell_s) + ((size_t)tile * (a.maxrow_s >> 3)) * a.stride + ts;
+  uint4 *dst = reinterpret_cast<uint4 *>(a.ell_s) + ((size_t)t.tile * (a.maxrow >> 3)) * a.stride + ts;
   for (int q0 = 0; q0 < c8; q0 += 8) {
     unsigned wv[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int q = q0 + k;
-      unsigned s = pad;
+      const unsigned b = (unsigned)(q + hl) & 15u;
+      unsigned ent = b * 24u; // padding: the dummy atom of this lane's bank in this column
       if (q < n) {
-        const unsigned pref = (unsigned)(q + hl) & 15u;
-        unsigned b = pref;
-        if (!((N >> pref) & 1u)) { // my bucket for this column's bank ran dry: take from one that holds more than its share
-          const int th_now = (n - q + 15) >> 4;
-          if (th_now != th) {
-            th = th_now;
-            big = 0;
-#pragma unroll
-            for (int bb = 0; bb < 16; bb++) if ((int)(state[bb * 32] >> 8) > th) big |= 1u << bb;
-          }
-          const unsigned mb = N & big;
-          const unsigned sel = mb ? mb : N;
-          const unsigned rot = ((sel >> pref) | (sel << (16 - pref))) & 0xffffu;
-          b = (unsigned)(__ffs(rot) - 1 + pref) & 15u;
+        int idx = q;
+        if (!plain) {
+          const unsigned st = state[b * kRowThreads];
+          const int tt = q >> 4;
+          idx = tt < (int)(st >> 8) ? (int)(st & 0xffu) + tt : cursor++;
         }
-        const unsigned st = state[b * 32];
-        s = srow[(st & 0xffu) * 32];
-        const unsigned left = (st >> 8) - 1u;
-        state[b * 32] = ((st + 1u) & 0xffu) | (left << 8);
-        if (!left) N &= ~(1u << b);
-        if ((int)left <= th) big &= ~(1u << b);
+        ent = ((unsigned)srow[idx * kRowThreads] + kDummySlots) * 24u;
       }
-      wv[k >> 1] |= s << (16 * (k & 1));
+      wv[k >> 1] |= ent << (16 * (k & 1));
     }
     dst[(size_t)(q0 >> 3) * a.stride] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
   }
-  a.nell_s[(size_t)tile * a.stride + ts] = c8;
+  a.nell_s[rbase] = c8;
 }
 
-// ------------------------------------------------------------ exact lists from the ELL superset
-enum { EMIT_COUNT = 0, EMIT_CSR = 1, EMIT_2D = 2 };
+// counts[i] from the stored exact row lengths (a second list type asked of the same build)
+__global__ void __launch_bounds__(kRowThreads) tiles_counts_kernel(TileArgs a, int *counts) {
+  const size_t rbase = (size_t)blockIdx.x * a.stride + threadIdx.x;
+  const int i = a.int_glob[rbase];
+  if (i < a.n_local) counts[i] = a.ncsr[rbase];
+}
 
-struct EmitArgs {
-  double cutsq;
-  int newton;
-  int *counts;        // COUNT: counts[i]; 2D: num_neighs[i]
+// CSR entries / 2D table from the exact rows: slot number -> atom index, nothing else
+enum { FILL_CSR = 0, FILL_2D = 1 };
+struct FillArgs {
   const int *row_map; // CSR
   int *entries;       // CSR entries / 2D table
+  int *num_neighs;    // 2D
   int maxneighs;      // 2D
-  int *max_count;     // 2D
 };
 
-template <bool HALF, int MODE>
-__global__ void __launch_bounds__(512) tiles_emit_kernel(TileArgs a, EmitArgs e) {
-  __shared__ int s_start[kMaxStagedCells + 1], s_goff[kMaxStagedCells], s_ibase[kMaxInteriorCells + 1];
-  extern __shared__ __align__(16) unsigned char dyn[];
-  double *sx = reinterpret_cast<double *>(dyn), *sy = sx + a.cap, *sz = sy + a.cap;
-  int *sj = reinterpret_cast<int *>(sz + a.cap);
-  unsigned short *s_islot = reinterpret_cast<unsigned short *>(sj + a.cap);
-  TileCtx t;
-  tile_setup(a, t, s_start, s_goff, s_ibase);
-  if (t.total > a.cap || t.n_int > a.stride) return; // cannot happen after a successful filter pass
-  tile_stage<ST_F64 | ST_J>(a, t, s_start, s_goff, nullptr, sx, sy, sz, sj, nullptr);
-  tile_interior_table(a, t, s_start, s_goff, s_ibase, s_islot, nullptr);
-  __syncthreads();
-  const int ts = threadIdx.x;
-  if (ts >= t.n_int) return;
-  const int own = s_islot[ts];
-  const int i = sj[own];
-  if (i >= a.n_local) return;
-  const int n = a.nell[(size_t)t.tile * a.stride + ts];
-  const double x_i = sx[own], y_i = sy[own], z_i = sz[own];
-  const size_t base = (MODE == EMIT_CSR) ? (size_t)e.row_map[i] : (size_t)i * e.maxneighs;
-  int count = 0;
-  // one 16-byte word = 8 entries of the row; the next word is requested before the current one is used
-  const uint4 *row = reinterpret_cast<const uint4 *>(a.ell) + ((size_t)t.tile * (a.maxrow >> 3)) * a.stride + ts;
-  const int nchunk = (n + 7) >> 3;
-  uint4 cur = nchunk > 0 ? row[0] : make_uint4(0, 0, 0, 0);
-  for (int c = 0; c < nchunk; c++) {
-    const uint4 nxt = (c + 1 < nchunk) ? row[(size_t)(c + 1) * a.stride] : make_uint4(0, 0, 0, 0);
-    const unsigned w4[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      if (c * 8 + k >= n) break;
-      const int s = (int)((w4[k >> 1] >> (16 * (k & 1))) & 0xffffu);
-      const int j = sj[s];
-      const double x_j = sx[s], y_j = sy[s], z_j = sz[s];
-      if (HALF) { // neighbor_csr.h:290-291 (j != i by construction)
-        const bool skip = (j < a.n_local || e.newton) &&
-                          !((x_j > x_i) || ((x_j == x_i) && ((y_j > y_i) || ((y_j == y_i) && (z_j > z_i)))));
-        if (skip) continue;
-      }
-      const double dx = x_i - x_j, dy = y_i - y_j, dz = z_i - z_j;
-      const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-      if (rsq <= e.cutsq) { // neighbor_csr.h:206,299
-        if (MODE == EMIT_CSR) e.entries[base + count] = j;
-        if (MODE == EMIT_2D && count < e.maxneighs) e.entries[base + count] = j; // neighbor_2d.h:207-208
-        count++;
-      }
+// warp = 32 consecutive rows = (cell-sorted atoms) a contiguous piece of the CSR entries: the warp copies row after row,
+// lane = entry, so the stores are coalesced
+template <int MODE>
+__global__ void __launch_bounds__(kRowThreads) tiles_fill_kernel(TileArgs a, FillArgs e) {
+  const int tile = blockIdx.x, ts = threadIdx.x, lane = ts & 31;
+  const size_t rbase = (size_t)tile * a.stride + ts;
+  const int i = a.int_glob[rbase];
+  const bool active = i < a.n_local;
+  const int count = active ? a.ncsr[rbase] : 0;
+  long long base = 0;
+  if (active) base = (MODE == FILL_CSR) ? (long long)e.row_map[i] : (long long)i * e.maxneighs;
+  const int nw = (MODE == FILL_2D) ? min(count, e.maxneighs) : count; // neighbor_2d.h:207-208
+  if (MODE == FILL_2D && active) { e.num_neighs[i] = count; atomicMax(&a.flags[FL_MAX2D], count); }
+  const unsigned short *tile16 = a.csr16 + ((size_t)tile * (a.maxrow >> 3)) * a.stride * 8;
+  const int *__restrict__ jmap = a.stg_j + (size_t)tile * a.cap;
+  const unsigned rows = __ballot_sync(0xffffffffu, nw > 0);
+  for (unsigned m = rows; m; m &= m - 1) {
+    const int src = __ffs(m) - 1;
+    const int nw_r = __shfl_sync(0xffffffffu, nw, src);
+    const long long base_r = __shfl_sync(0xffffffffu, base, src);
+    const int ts_r = (ts & ~31) + src;
+    for (int q = lane; q < nw_r; q += 32) {
+      const unsigned slot = tile16[((size_t)(q >> 3) * a.stride + ts_r) * 8 + (q & 7)];
+      e.entries[base_r + q] = __ldg(jmap + slot);
     }
-    cur = nxt;
   }
-  if (MODE == EMIT_COUNT) e.counts[i] = count;
-  if (MODE == EMIT_2D) { e.counts[i] = count; atomicMax(e.max_count, count); }
 }
 
 // ------------------------------------------------------------------------------ LJ force
-struct LJOne { double lj1, lj2, cutsq; };
+struct LJOne { double lj1, lj2, cutsq, e1, e2, eshift; };
 struct LJTab {
   double lj1[kMaxTypesConst * kMaxTypesConst], lj2[kMaxTypesConst * kMaxTypesConst], cutsq[kMaxTypesConst * kMaxTypesConst];
+  double e1[kMaxTypesConst * kMaxTypesConst], e2[kMaxTypesConst * kMaxTypesConst], eshift[kMaxTypesConst * kMaxTypesConst];
   int ntypes;
 };
-
-// 1/a to <= 1 ulp: MUFU.RCP64H seed y0 (~2^-20) and one cubic step y0 (1 + e + e^2), e = 1 - a y0: three
-// DFMA (error e^3 ~ 2^-60) instead of the four of two Newton steps; the library division adds range
-// fix-ups that rsq in (0, cutsq) never needs
-__device__ __forceinline__ double fast_rcp(double a) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  const double e = fma(-a, y, 1.0);
-  const double t = fma(e, e, e);
-  return fma(y, t, y);
+// energy of a pair seen from one side (force_lj_neigh_impl.h:271-278 with fac = 0.5): 0.5 (r6inv (0.5 lj1 r6inv - lj2) / 6 - the
+// same at the cutoff) = r6inv (e1 r6inv - e2) - eshift
+inline void lj_energy_consts(double lj1, double lj2, double cutsq, double &e1, double &e2, double &eshift) {
+  e1 = lj1 / 24.0; e2 = lj2 / 12.0;
+  const double r2invc = 1.0 / cutsq, r6invc = r2invc * r2invc * r2invc;
+  eshift = r6invc * (e1 * r6invc - e2);
 }
 
-// Four pairs (one ELL word) at a time, branch-free and written stage by stage so that the four
-// ~20-instruction FP64 dependency chains are interleaved by the scheduler.
+// Four pairs at a time, branch-free and written stage by stage so that the four FP64 dependency chains are interleaved
+// by the scheduler.  17 FP64 instructions per pair: 3 DADD, DMUL + 2 DFMA (rsq), 3 DFMA (reciprocal: MUFU.RCP64H seed
+// y0 ~2^-20 and one cubic step y0 (1 + e + e^2), e = 1 - a y0, error e^3 ~ 2^-60), 2 DMUL (r6inv), DFMA + 2 DMUL (fpair),
+// 3 DFMA (f).  Everything else is kept off the pair: an entry IS the byte offset of the neighbor's coordinates; the strict
+// cutoff test (force_lj_neigh_impl.h:189) runs on the integer pipe (rsq and cutsq are non-negative, so the IEEE order is
+// the order of the bit patterns) and its ONE consequence is a select on the high word of the reciprocal seed: a zero seed
+// gives r2inv = 0 exactly and the pair contributes +-0.  Padding entries point at a far-away dummy atom and fail the
+// same test; no entry is the atom itself.
 template <bool ONETYPE, bool ENERGY>
-__device__ __forceinline__ void lj_quad(const double *__restrict__ sp, const int *__restrict__ st, const unsigned w01, const unsigned w23,
+__device__ __forceinline__ void lj_quad(const unsigned char *__restrict__ spb, const int *__restrict__ st, const unsigned w01, const unsigned w23,
                                         double x_i, double y_i, double z_i, int type_i, const LJOne &one, const LJTab *__restrict__ tab,
                                         double &fx, double &fy, double &fz, double &pe) {
-  const unsigned raw[4] = {w01 & 0xffffu, w01 >> 16, w23 & 0xffffu, w23 >> 16};
+  const unsigned off[4] = {w01 & 0xffffu, w01 >> 16, w23 & 0xffffu, w23 >> 16};
   double dx[4], dy[4], dz[4], rsq[4], lj1[4], lj2[4], cutsq[4];
+  int tij[4];
 #pragma unroll
   for (int u = 0; u < 4; u++) {
-    const unsigned sl = raw[u] & 0x7fffu;
-    const double *p = sp + 3 * sl;
+    const double *p = reinterpret_cast<const double *>(spb + off[u]);
     dx[u] = x_i - p[0]; dy[u] = y_i - p[1]; dz[u] = z_i - p[2];
-    if (ONETYPE) { lj1[u] = one.lj1; lj2[u] = one.lj2; cutsq[u] = one.cutsq; }
-    else { const int tij = type_i * tab->ntypes + st[sl]; lj1[u] = tab->lj1[tij]; lj2[u] = tab->lj2[tij]; cutsq[u] = tab->cutsq[tij]; }
+    if (ONETYPE) { lj1[u] = one.lj1; lj2[u] = one.lj2; cutsq[u] = one.cutsq; tij[u] = 0; }
+    else { tij[u] = type_i * tab->ntypes + st[off[u] / 24u]; lj1[u] = tab->lj1[tij[u]]; lj2[u] = tab->lj2[tij[u]]; cutsq[u] = tab->cutsq[tij[u]]; }
   }
 #pragma unroll
   for (int u = 0; u < 4; u++) rsq[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
@@ -750,20 +615,22 @@ __device__ __forceinline__ void lj_quad(const double *__restrict__ sp, const int
   double r2inv[4];
 #pragma unroll
   for (int u = 0; u < 4; u++) {
-    // force_lj_neigh_impl.h:189 (strict).  rsq and cutsq are non-negative, so the IEEE order is the order of the bit
-    // patterns: the test runs on the integer pipe and leaves the FP64 pipe to the arithmetic.  Bit 15 marks padding.
-    in[u] = !(raw[u] & 0x8000u) && __double_as_longlong(rsq[u]) < __double_as_longlong(cutsq[u]);
-    r2inv[u] = fast_rcp(rsq[u]); // a padding entry that is the atom itself (rsq = 0) gives inf/NaN below, discarded by the select
+    in[u] = __double_as_longlong(rsq[u]) < __double_as_longlong(cutsq[u]);
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(rsq[u]));
+    y0 = __hiloint2double(in[u] ? __double2hiint(y0) : 0, 0);
+    const double e = fma(-rsq[u], y0, 1.0);
+    const double t = fma(e, e, e);
+    r2inv[u] = fma(y0, t, y0);
   }
 #pragma unroll
   for (int u = 0; u < 4; u++) {
     const double r6inv = r2inv[u] * r2inv[u] * r2inv[u];
-    const double fpair = in[u] ? (r6inv * (lj1[u] * r6inv - lj2[u])) * r2inv[u] : 0.0;
+    const double fpair = (r6inv * (lj1[u] * r6inv - lj2[u])) * r2inv[u];
     fx += dx[u] * fpair; fy += dy[u] * fpair; fz += dz[u] * fpair;
-    if (ENERGY) { // force_lj_neigh_impl.h:271-278 with fac = 0.5 (every pair is seen from both sides)
-      const double r2invc = 1.0 / cutsq[u], r6invc = r2invc * r2invc * r2invc;
-      const double e = 0.5 * r6inv * (0.5 * lj1[u] * r6inv - lj2[u]) / 6.0 - 0.5 * r6invc * (0.5 * lj1[u] * r6invc - lj2[u]) / 6.0;
-      pe += in[u] ? e : 0.0;
+    if (ENERGY) { // force_lj_neigh_impl.h:271-278 with fac = 0.5 (every pair is seen from both sides); r6inv = 0 outside the cutoff
+      const double e1 = ONETYPE ? one.e1 : tab->e1[tij[u]], e2 = ONETYPE ? one.e2 : tab->e2[tij[u]], es = ONETYPE ? one.eshift : tab->eshift[tij[u]];
+      pe += fma(r6inv, fma(e1, r6inv, -e2), in[u] ? -es : 0.0);
     }
   }
 }
@@ -772,148 +639,166 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
-// The ELL words of a row are read once per step, one 16-byte word per 8 pairs.  The register budget (80 at two 384-thread
-// CTAs per SM) makes the compiler place the load of word c+1 at the END of iteration c, next to its first use (as a plain
-// load AND as volatile asm), and 26 % of the kernel's stall samples were warps waiting for it (profiles/, round 1).  A
-// prefetch holds no register: word c+2 is requested into L1 at the top of iteration c, so the late load hits L1.
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 ldg_nc_v4(const uint4 *p) {
   uint4 v;
   asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// mbarriers (shared::cta).  `full`: the 32 lanes of the producer warp attach their cp.async groups (arrive.noinc: the
+// arrival happens when the lane's copies have landed).  `empty`: one arrival per warp.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_copies(unsigned long long *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
 
-constexpr int kForceThreads = 384;
-constexpr int kStagePerThread = 8; // cap <= kForceThreads * kStagePerThread
+constexpr int kForceThreads = kRowThreads;
+constexpr int kForceWarps = kForceThreads / 32;
+constexpr int kMaxBuf = 3;
 
-// Persistent CTAs (2 per SM), each walking tiles blockIdx.x, +gridDim.x, ...  The coordinates of
-// tile n+1 are copied global->shared with cp.async (LDGSTS) into the second buffer while tile n
-// is computed, and the staging indices of tile n+2 are prefetched into registers, so no global
-// latency is exposed between tiles.
-// The CTA walks the tiles a.order[first + blockIdx.x], [first + blockIdx.x + gridDim.x], ... below first + ntiles.
-// RING: the ELL words travel global -> shared with cp.async into one 16-byte slot per thread (no register is held while
-// the copy is in flight, so -- unlike a register prefetch, which ptxas sinks to the end of the loop body at this register
-// budget -- the request really is issued a whole 8-pair iteration before its use); word 0 of the next tile's row is
-// requested during the last iteration of the current one.  Needs two CTAs to still fit on an SM with the extra 6 KB.
-// An experiment that did not pay (see lj_tiles_launch): kept behind EMD_TILES_RING=1.
-// FUSE: the epilogue also applies IntegratorNVE::final_integrate of this step and initial_integrate of the next one to the
+// Persistent CTAs (2 per SM), each walking the tiles a.order[first + blockIdx.x], [first + blockIdx.x + gridDim.x], ...
+// below first + ntiles.  NBUF coordinate buffers; tile k of the CTA lives in buffer k mod NBUF.
+//   producer = the last warp (its rows are the sparse tail of the tile): before it works on tile k it waits until every warp
+//     has released the buffer of tile k - 1 (`empty`), then issues the copies of tile k + NBUF - 1 into it (LDGSTS through the
+//     staging table; completion is attached to `full`);
+//   every warp: waits for `full` of tile k, walks its 32 rows, releases the buffer.  No CTA-wide barrier.
+// MODE_NVE: the epilogue also applies IntegratorNVE::final_integrate of this step and initial_integrate of the next one to the
 // atom whose force was just accumulated (src/integrator_nve.cpp:47-74, 87-112: same operations, same order, so v and x are
 // bit-identical to the separate kernels): v is updated in place, the new position goes to a SECOND position array because
 // other CTAs still stage the old coordinates (the host swaps the two arrays after the launch).
 struct NveFuse { double *v; double *x_new; const double *mass; double dtf, dtv; };
+enum { MODE_FORCE = 0, MODE_ENERGY = 1, MODE_NVE = 2 };
 
-template <bool ONETYPE, bool ENERGY, bool RING, bool FUSE>
-__global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, LJOne one, const LJTab *__restrict__ tab,
-                                                                   double *__restrict__ f, double *__restrict__ pe_partial, unsigned ring_offset,
-                                                                   NveFuse nve) {
-  __shared__ double s_red[kForceThreads / 32];
+template <bool ONETYPE, int MODE>
+__global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, int nbuf, LJOne one, const LJTab *__restrict__ tab,
+                                                                   double *__restrict__ f, double *__restrict__ pe_partial, NveFuse nve) {
+  constexpr bool ENERGY = MODE == MODE_ENERGY;
+  __shared__ double s_red[kForceWarps];
+  __shared__ unsigned long long s_full[kMaxBuf], s_empty[kMaxBuf];
   extern __shared__ __align__(16) unsigned char dyn[];
-  double *const sp0 = reinterpret_cast<double *>(dyn); // 2 x [cap][3]: x,y,z of a staged atom adjacent (one address computation per pair)
-  int *const st0 = reinterpret_cast<int *>(sp0 + 6 * (size_t)a.cap); // 2 x [cap] types (multi-type systems only)
-  uint4 *const ering = reinterpret_cast<uint4 *>(dyn + ring_offset) + threadIdx.x; // RING: this thread's slot
-  const int ts = threadIdx.x;
+  const unsigned buf_bytes = (unsigned)(a.fcap + kDummySlots) * 24u;           // [16 dummy atoms + fcap][3] doubles: x,y,z of a staged atom adjacent
+  int *const st0 = reinterpret_cast<int *>(dyn + (size_t)nbuf * buf_bytes);    // nbuf x [16 + fcap] types (multi-type systems only)
+  const int tstride = a.fcap + kDummySlots;
+  const int ts = threadIdx.x, lane = ts & 31, warp = ts >> 5;
   const int G = gridDim.x;
-  int jreg[kStagePerThread];
+  const bool producer = warp == kForceWarps - 1;
 
-  auto tile_at = [&](int pos) { return pos < ntiles ? a.order[first + pos] : -1; }; // pos-th tile of this launch's range
-  auto load_j = [&](int tile) { // staging indices of `tile` into registers (coalesced)
-    if (tile >= 0) {
-      const int n = a.stg_n[tile];
-      const int *src = a.stg_j + (size_t)tile * a.cap;
-#pragma unroll
-      for (int k = 0; k < kStagePerThread; k++) { const int s = ts + k * kForceThreads; jreg[k] = s < n ? src[s] : -1; }
-    } else {
-#pragma unroll
-      for (int k = 0; k < kStagePerThread; k++) jreg[k] = -1;
+  if (ts == 0) {
+    for (int b = 0; b < nbuf; b++) { mbar_init(&s_full[b], 32u); mbar_init(&s_empty[b], (unsigned)kForceWarps); }
+  }
+  if (ts < kDummySlots * 3) // the dummy atoms of every buffer
+    for (int b = 0; b < nbuf; b++) {
+      reinterpret_cast<double *>(dyn + (size_t)b * buf_bytes)[ts] = kFarAway;
+      if (!ONETYPE && ts < kDummySlots) st0[(size_t)b * tstride + ts] = 0;
     }
-  };
-  auto issue_copies = [&](int buf) {
+  __syncthreads();
+
+  const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + G - 1) / G : 0;
+  auto tile_of = [&](int k) { return a.order[first + blockIdx.x + k * G]; };
+  // producer: copies of the CTA's kk-th tile (the caller has made sure that its buffer is free)
+  auto produce = [&](int kk) {
+    const int b = kk % nbuf;
+    if (kk < my_tiles) {
+      const int tl = tile_of(kk);
+      const int n = a.stg_n[tl];
+      const int *__restrict__ src = a.stg_j + (size_t)tl * a.cap;
+      double *dstb = reinterpret_cast<double *>(dyn + (size_t)b * buf_bytes) + 3 * kDummySlots;
+      int *dstt = st0 + (size_t)b * tstride + kDummySlots;
+      for (int s0 = 0; s0 < n; s0 += 32 * 8) {
+        int j[8];
 #pragma unroll
-    for (int k = 0; k < kStagePerThread; k++) {
-      const int j = jreg[k];
-      if (j >= 0) {
-        const int s = ts + k * kForceThreads;
-        const double *src = a.x + 3 * (size_t)j;
-        double *dst = sp0 + (size_t)buf * 3 * a.cap + 3 * s;
-        cp_async8(dst, src); cp_async8(dst + 1, src + 1); cp_async8(dst + 2, src + 2);
-        if (!ONETYPE) cp_async4(st0 + (size_t)buf * a.cap + s, a.type + j);
+        for (int u = 0; u < 8; u++) { const int s = s0 + u * 32 + lane; j[u] = s < n ? __ldg(src + s) : -1; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (j[u] >= 0) {
+            const int s = s0 + u * 32 + lane;
+            const double *g = a.x + 3 * (size_t)j[u];
+            cp_async8(dstb + 3 * s, g); cp_async8(dstb + 3 * s + 1, g + 1); cp_async8(dstb + 3 * s + 2, g + 2);
+            if (!ONETYPE) cp_async4(dstt + s, a.type + j[u]);
+          }
+        }
       }
     }
+    mbar_arrive_on_copies(&s_full[b]); // also for a tile that does not exist: nobody waits for it
   };
 
-  int pos = blockIdx.x;
-  int tile = tile_at(pos), tile_nxt = tile_at(pos + G);
-  load_j(tile);
-  issue_copies(0);
-  load_j(tile_nxt);
-  // per-thread row descriptors of the current tile
-  int i_cur = 0x7fffffff, own_cur = 0, n_cur = 0;
-  if (tile >= 0) {
-    i_cur = a.int_glob[(size_t)tile * a.stride + ts];
-    own_cur = a.int_slot[(size_t)tile * a.stride + ts];
-    n_cur = a.nell_s[(size_t)tile * a.stride + ts];
-  }
-  auto row_of_tile = [&](int tl) { return reinterpret_cast<const uint4 *>(a.ell_s) + ((size_t)tl * (a.maxrow_s >> 3)) * a.stride + ts; };
-  if (RING && tile >= 0 && i_cur < a.n_local && n_cur > 0) cp_async16(ering, row_of_tile(tile)); // word 0 of the first row
-  double pe = 0.0;
-  int buf = 0;
-  for (; pos < ntiles; pos += G, buf ^= 1) {
-    cp_async_wait_all();
-    __syncthreads(); // buffer `buf` is complete; every thread is done with buffer `buf^1`
-    issue_copies(buf ^ 1);  // tile_nxt
-    const int tile_nn = tile_at(pos + 2 * G);
-    load_j(tile_nn);
-    int i_nxt = 0x7fffffff, own_nxt = 0, n_nxt = 0;
-    if (tile_nxt >= 0) {
-      i_nxt = a.int_glob[(size_t)tile_nxt * a.stride + ts];
-      own_nxt = a.int_slot[(size_t)tile_nxt * a.stride + ts];
-      n_nxt = a.nell_s[(size_t)tile_nxt * a.stride + ts];
+  if (producer)
+    for (int kk = 0; kk < nbuf - 1; kk++) produce(kk);
+
+  // per-thread row descriptors, one tile ahead
+  int i_nxt = 0x7fffffff, own_nxt = 0, n_nxt = 0, tile_nxt = -1;
+  auto load_desc = [&](int k) {
+    i_nxt = 0x7fffffff; own_nxt = 0; n_nxt = 0; tile_nxt = -1;
+    if (k < my_tiles) {
+      tile_nxt = tile_of(k);
+      const size_t rb = (size_t)tile_nxt * a.stride + ts;
+      i_nxt = a.int_glob[rb];
+      own_nxt = a.int_slot[rb];
+      n_nxt = a.nell_s[rb];
     }
-    const double *sp = sp0 + (size_t)buf * 3 * a.cap;
-    const int *st = st0 + (size_t)buf * a.cap;
-    if (i_cur < a.n_local) {
-      const double x_i = sp[3 * own_cur], y_i = sp[3 * own_cur + 1], z_i = sp[3 * own_cur + 2];
-      const int type_i = ONETYPE ? 0 : st[own_cur];
+  };
+  auto row_of_tile = [&](int tl) { return reinterpret_cast<const uint4 *>(a.ell_s) + ((size_t)tl * (a.maxrow >> 3)) * a.stride + ts; };
+  load_desc(0);
+  double pe = 0.0;
+  int b = 0;
+  unsigned parity = 0u;
+  for (int k = 0; k < my_tiles; k++) {
+    const int i_cur = i_nxt, own_cur = own_nxt, n_cur = n_nxt, tile = tile_nxt;
+    const bool has_row = i_cur < a.n_local;
+    const uint4 *row = row_of_tile(tile);
+    const int nchunk = n_cur >> 3;
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (has_row && nchunk > 0) cur = ldg_nc_v4(row); // in flight while the warp waits for the coordinates
+    if (has_row && nchunk > 1) prefetch_l1(row + a.stride);
+    if (MODE == MODE_NVE && has_row) { prefetch_l1(nve.v + 3 * (size_t)i_cur); prefetch_l1(nve.v + 3 * (size_t)i_cur + 2); } // the epilogue's v
+    if (producer) {
+      // buffer (k + nbuf - 1) mod nbuf held tile k - 1
+      if (k > 0) {
+        const int kb = (k - 1) % nbuf;
+        mbar_wait(&s_empty[kb], (unsigned)(((k - 1) / nbuf) & 1));
+      }
+      produce(k + nbuf - 1);
+    }
+    load_desc(k + 1);
+    mbar_wait(&s_full[b], parity);
+    const unsigned char *spb = dyn + (size_t)b * buf_bytes;
+    const int *st = st0 + (size_t)b * tstride;
+    if (has_row) {
+      const double *me = reinterpret_cast<const double *>(spb) + 3 * (own_cur + kDummySlots);
+      const double x_i = me[0], y_i = me[1], z_i = me[2];
+      const int type_i = ONETYPE ? 0 : st[own_cur + kDummySlots];
       double fx = 0.0, fy = 0.0, fz = 0.0;
-      // one 16-byte word = 8 columns of the warp's schedule (n_cur is the same multiple of 8 in every lane of the warp);
-      // the next word is requested before the current one is used
-      const uint4 *row = row_of_tile(tile);
-      const int nchunk = n_cur >> 3;
-      if (RING) {
-        // word 0 arrived with the tile's coordinates (wait + barrier above); the row of the next tile, if this thread has one
-        const uint4 *row_nxt = (tile_nxt >= 0 && i_nxt < a.n_local && n_nxt > 0) ? row_of_tile(tile_nxt) : nullptr;
-        for (int c = 0; c < nchunk; c++) {
-          if (c > 0) cp_async_wait_all(); // the word requested one iteration ago (and, long since, the next tile's coordinates)
-          const uint4 cur = *ering;
-          const uint4 *nextp = (c + 1 < nchunk) ? row + (size_t)(c + 1) * a.stride : row_nxt;
-          if (nextp) cp_async16(ering, nextp); // same thread: the read above precedes the asynchronous write
-          lj_quad<ONETYPE, ENERGY>(sp, st, cur.x, cur.y, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
-          lj_quad<ONETYPE, ENERGY>(sp, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
-        }
-      } else {
-        uint4 cur = make_uint4(0, 0, 0, 0);
-        if (nchunk > 0) cur = ldg_nc_v4(row);
-        if (nchunk > 1) prefetch_l1(row + a.stride);
-        for (int c = 0; c < nchunk; c++) {
-          if (c + 2 < nchunk) prefetch_l1(row + (size_t)(c + 2) * a.stride);
-          uint4 nxt = make_uint4(0, 0, 0, 0);
-          if (c + 1 < nchunk) nxt = ldg_nc_v4(row + (size_t)(c + 1) * a.stride);
-          lj_quad<ONETYPE, ENERGY>(sp, st, cur.x, cur.y, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
-          lj_quad<ONETYPE, ENERGY>(sp, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
-          cur = nxt;
-        }
+      // one 16-byte word = 8 columns of the warp's schedule (n_cur is the same multiple of 8 in every lane of the warp)
+      const size_t rstep = (size_t)a.stride;
+      for (int c = 0; c < nchunk; c++, row += rstep) {
+        if (c + 2 < nchunk) prefetch_l1(row + 2 * rstep);
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (c + 1 < nchunk) nxt = ldg_nc_v4(row + rstep);
+        lj_quad<ONETYPE, ENERGY>(spb, st, cur.x, cur.y, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+        lj_quad<ONETYPE, ENERGY>(spb, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
+        cur = nxt;
       }
       if (!ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
-      if (FUSE) {
+      if (MODE == MODE_NVE) {
         const double dtfm = nve.dtf / nve.mass[ONETYPE ? a.type[i_cur] : type_i]; // integrator_nve.cpp:67,106
         double *vp = nve.v + 3 * (size_t)i_cur, *xp = nve.x_new + 3 * (size_t)i_cur;
         const double fi[3] = {fx, fy, fz}, xi[3] = {x_i, y_i, z_i};
@@ -927,27 +812,30 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
         }
       }
     }
-    if (RING && !(i_cur < a.n_local && n_cur > 0) && tile_nxt >= 0 && i_nxt < a.n_local && n_nxt > 0)
-      cp_async16(ering, row_of_tile(tile_nxt)); // no row here, one in the next tile: its word 0
-    i_cur = i_nxt; own_cur = own_nxt; n_cur = n_nxt;
-    tile = tile_nxt; tile_nxt = tile_nn;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[b]);
+    if (++b == nbuf) { b = 0; parity ^= 1u; }
   }
-  cp_async_wait_all();
+  if (producer) asm volatile("cp.async.wait_all;" ::: "memory"); // copies of tiles that do not exist were never issued; be tidy anyway
   if (ENERGY) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pe += __shfl_down_sync(0xffffffffu, pe, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = pe;
+    if (lane == 0) s_red[warp] = pe;
     __syncthreads();
     if (threadIdx.x == 0) {
       double s = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += s_red[w];
+      for (int w = 0; w < kForceWarps; w++) s += s_red[w];
       pe_partial[blockIdx.x] = s;
     }
   }
 }
 
-size_t emit_smem(int cap, int stride) { return (size_t)cap * (3 * sizeof(double) + sizeof(int)) + (size_t)stride * sizeof(unsigned short); }
-size_t force_smem(int cap, bool types) { return 2 * ((size_t)cap * 3 * sizeof(double) + (types ? (size_t)cap * sizeof(int) : 0)); }
+size_t lists_coords_bytes(int cap, int maxrow) { // region A of tiles_lists_kernel
+  const size_t coords = (size_t)cap * 28, rows = (size_t)(maxrow + kExcessRoom) * kRowThreads * sizeof(unsigned short);
+  return (std::max(coords, rows) + 15) / 16 * 16;
+}
+size_t lists_smem(int cap, int maxrow) { return lists_coords_bytes(cap, maxrow) + (size_t)16 * kRowThreads * sizeof(unsigned short); }
+size_t force_smem(int fcap, bool types, int nbuf) { return (size_t)nbuf * ((size_t)(fcap + kDummySlots) * 24 + (types ? (size_t)(fcap + kDummySlots) * sizeof(int) : 0)); }
 
 } // namespace
 
@@ -956,9 +844,14 @@ namespace emd { int device_sum_partials(emd_ctx *ctx, const double *d_partial, i
 struct emd_tiles {
   TileArgs a;
   int ntiles = 0;
-  bool valid = false;
+  bool valid = false;       // search done (masks + tables), parameters below describe it
+  bool checked = false;     // its overflow flags have been read back
+  bool rows_ready = false;  // ell_s of this build written
+  int exact_key = -1;       // half | newton << 1 of the exact rows (csr16 / ncsr) of this build, -1: none
   unsigned short *d_ell = nullptr; size_t ell_cap = 0;
   int *d_nell = nullptr; size_t nell_cap = 0;
+  unsigned short *d_csr16 = nullptr; size_t csr16_cap = 0;
+  int *d_ncsr = nullptr; size_t ncsr_cap = 0;
   unsigned short *d_ell_s = nullptr; size_t ell_s_cap = 0;
   int *d_nell_s = nullptr; size_t nell_s_cap = 0;
   int *d_stg_j = nullptr; size_t stg_j_cap = 0;
@@ -970,12 +863,17 @@ struct emd_tiles {
   int n_free_tiles = 0;  // tiles that do not read the halo (first in d_order)
   bool all_owned_have_rows = false; // every owned atom is listed (precondition of the fused force + integrator launch)
   int *d_flags = nullptr;
+  emd_ctx *ctx = nullptr; // the context of the last build (the lazy list / flag check of the const accessors runs on it)
   int num_sms = 148;
-  LJTab *d_tab = nullptr;
+  LJTab *d_tab = nullptr, *h_tab = nullptr; // device copy of the pair table and its pinned staging copy
+  unsigned long long tab_version = ~0ull; // ctx->lj version the device table was uploaded for
   double neigh_cut = 0.0;
-  float cutf2 = 0.f;
+  float thr2 = 0.f;
   int max_smem_optin = 0;
   int max_smem_sm = 0;
+  // the inputs of the last build (a regrow re-runs the search)
+  double m_density = 0.0;
+  int staged_cells = 0;
 };
 
 namespace {
@@ -997,6 +895,100 @@ int ensure_bytes(void **p, size_t *cap, size_t bytes) {
   return 0;
 }
 
+// buffers for the current parameters (grow-only: a steady-state re-neighboring allocates nothing) and the search launches
+int launch_search(emd_ctx *ctx, emd_tiles *t) {
+  TileArgs &a = t->a;
+  const size_t rows = (size_t)t->ntiles * a.stride;
+  if (ensure_bytes((void **)&t->d_ell, &t->ell_cap, rows * a.maxrow * sizeof(unsigned short))) return 1;
+  if (ensure_bytes((void **)&t->d_nell, &t->nell_cap, rows * sizeof(int))) return 1;
+  if (ensure_bytes((void **)&t->d_csr16, &t->csr16_cap, rows * a.maxrow * sizeof(unsigned short))) return 1;
+  if (ensure_bytes((void **)&t->d_ell_s, &t->ell_s_cap, rows * a.maxrow * sizeof(unsigned short))) return 1;
+  if (ensure_bytes((void **)&t->d_ncsr, &t->ncsr_cap, rows * sizeof(int))) return 1;
+  if (ensure_bytes((void **)&t->d_nell_s, &t->nell_s_cap, rows * sizeof(int))) return 1;
+  if (ensure_bytes((void **)&t->d_stg_j, &t->stg_j_cap, (size_t)t->ntiles * a.cap * sizeof(int))) return 1;
+  if (ensure_bytes((void **)&t->d_stg_n, &t->stg_n_cap, (size_t)t->ntiles * sizeof(int))) return 1;
+  if (ensure_bytes((void **)&t->d_int_slot, &t->int_slot_cap, rows * sizeof(unsigned short))) return 1;
+  if (ensure_bytes((void **)&t->d_int_glob, &t->int_glob_cap, rows * sizeof(int))) return 1;
+  if (ensure_bytes((void **)&t->d_order, &t->order_cap, (size_t)t->ntiles * sizeof(int))) return 1;
+  if (ensure_bytes((void **)&t->d_has_ghost, &t->has_ghost_cap, (size_t)t->ntiles * sizeof(int))) return 1;
+  a.ell = t->d_ell; a.nell = t->d_nell; a.csr16 = t->d_csr16; a.ncsr = t->d_ncsr; a.ell_s = t->d_ell_s; a.nell_s = t->d_nell_s;
+  a.stg_j = t->d_stg_j; a.stg_n = t->d_stg_n; a.int_slot = t->d_int_slot; a.int_glob = t->d_int_glob;
+  a.order = t->d_order; a.has_ghost = t->d_has_ghost; a.flags = t->d_flags;
+  EMD_CUDA(cudaMemsetAsync(t->d_flags, 0, FL_COUNT * sizeof(int), ctx->stream));
+  const size_t smem = (size_t)a.cap * sizeof(float4);
+  if (smem > (size_t)t->max_smem_optin) return 3;
+  if (set_smem(tiles_search_kernel, smem)) return 1;
+  EMD_LAUNCH(ctx, tiles_search_kernel, t->ntiles, kSearchThreads, smem, a, t->thr2);
+  EMD_LAUNCH(ctx, tiles_order_kernel, 1, 1024, 0, a, t->ntiles);
+  t->valid = true; t->checked = false; t->rows_ready = false; t->exact_key = -1;
+  return 0;
+}
+
+int launch_lists(emd_ctx *ctx, emd_tiles *t, bool exact, int half, int newton, int *d_counts) {
+  TileArgs &a = t->a;
+  ListArgs e;
+  e.cutsq = t->neigh_cut * t->neigh_cut; e.half = half; e.newton = newton; e.counts = d_counts;
+  const size_t cb = lists_coords_bytes(a.cap, a.maxrow), smem = lists_smem(a.cap, a.maxrow);
+  if (smem > (size_t)t->max_smem_optin) return 3;
+  if (exact) { if (set_smem(tiles_lists_kernel<true>, smem)) return 1; EMD_LAUNCH(ctx, tiles_lists_kernel<true>, t->ntiles, kRowThreads, smem, a, e, (unsigned)cb, a.maxrow + kExcessRoom); }
+  else { if (set_smem(tiles_lists_kernel<false>, smem)) return 1; EMD_LAUNCH(ctx, tiles_lists_kernel<false>, t->ntiles, kRowThreads, smem, a, e, (unsigned)cb, a.maxrow + kExcessRoom); }
+  t->rows_ready = true;
+  if (exact) t->exact_key = (half ? 1 : 0) | (newton ? 2 : 0);
+  return 0;
+}
+
+// Reads the flags of the search (+ lists) launches back -- the ONE host synchronisation of a re-neighboring -- and, if a
+// capacity was exceeded, grows it and reports 2 (the caller re-runs the launches); 3: the fast path does not apply.
+int check_flags(emd_ctx *ctx, emd_tiles *t, int n_local, const int *d_extra, int *h_extra) {
+  EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (d_extra) EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned + FL_COUNT, d_extra, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  EMD_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int *h = ctx->h_pinned;
+  if (h_extra && d_extra) *h_extra = h[FL_COUNT];
+  const int bits = h[FL_BITS];
+  TileArgs &a = t->a;
+  if (bits == 0) {
+    a.fcap = std::min(a.cap, std::max(32, (h[FL_NEED_CAP] + 31) / 32 * 32));
+    t->n_free_tiles = h[FL_NFREE];
+    t->all_owned_have_rows = h[FL_OWNED_ROWS] == n_local;
+    t->checked = true;
+    return 0;
+  }
+  t->valid = false;
+  if (bits & OVF_INT) return 3; // a tile holds more atoms than rows: density far from the estimate
+  if (bits & OVF_CAP) {
+    if (h[FL_NEED_CAP] > kCapMax) return 3;
+    a.cap = std::min(kCapMax, (h[FL_NEED_CAP] + h[FL_NEED_CAP] / 8 + 31) / 32 * 32);
+  }
+  if (bits & OVF_ROW) {
+    a.maxrow = (h[FL_NEED_ROW] + h[FL_NEED_ROW] / 8 + 7) / 8 * 8;
+    if (a.maxrow > kMaxRowLimit) return 3;
+  }
+  return 2;
+}
+
+// makes sure that the force rows (and, if asked, the exact rows of this list type) of the current build exist and that the
+// build has been checked; d_counts (optional) receives the exact row lengths by atom.  0, 1 (error) or 3 (not applicable).
+int ensure_lists(emd_ctx *ctx, emd_tiles *t, bool exact, int half, int newton, int *d_counts) {
+  const int key = (half ? 1 : 0) | (newton ? 2 : 0);
+  for (int attempt = 0; attempt < 5; attempt++) {
+    if (!t->valid) { const int rc = launch_search(ctx, t); if (rc) return rc; }
+    bool launched = false;
+    if (!t->rows_ready || (exact && t->exact_key != key)) {
+      const int rc = launch_lists(ctx, t, exact, half, newton, d_counts);
+      if (rc) return rc;
+      launched = true;
+    } else if (exact && d_counts) {
+      EMD_LAUNCH(ctx, tiles_counts_kernel, t->ntiles, kRowThreads, 0, t->a, d_counts);
+    }
+    if (t->checked && !launched) return 0;
+    const int rc = check_flags(ctx, t, t->a.n_local, nullptr, nullptr);
+    if (rc == 0) return 0;
+    if (rc != 2) return rc;
+  }
+  return 3;
+}
+
 } // namespace
 
 extern "C" {
@@ -1005,8 +997,9 @@ int emd_tiles_create(emd_tiles **out) {
   if (!out) { set_error("emd_tiles_create: out == NULL"); return 1; }
   emd_tiles *t = new emd_tiles();
   memset(&t->a, 0, sizeof t->a);
-  EMD_CUDA(cudaMalloc((void **)&t->d_flags, 8 * sizeof(int)));
+  EMD_CUDA(cudaMalloc((void **)&t->d_flags, FL_COUNT * sizeof(int)));
   EMD_CUDA(cudaMalloc((void **)&t->d_tab, sizeof(LJTab)));
+  EMD_CUDA(cudaMallocHost((void **)&t->h_tab, sizeof(LJTab)));
   int dev = 0;
   EMD_CUDA(cudaGetDevice(&dev));
   EMD_CUDA(cudaDeviceGetAttribute(&t->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -1018,18 +1011,10 @@ int emd_tiles_create(emd_tiles **out) {
 
 void emd_tiles_destroy(emd_tiles *t) {
   if (!t) return;
-  if (t->d_ell) cudaFree(t->d_ell);
-  if (t->d_nell) cudaFree(t->d_nell);
-  if (t->d_ell_s) cudaFree(t->d_ell_s);
-  if (t->d_nell_s) cudaFree(t->d_nell_s);
-  if (t->d_stg_j) cudaFree(t->d_stg_j);
-  if (t->d_stg_n) cudaFree(t->d_stg_n);
-  if (t->d_int_slot) cudaFree(t->d_int_slot);
-  if (t->d_int_glob) cudaFree(t->d_int_glob);
-  if (t->d_order) cudaFree(t->d_order);
-  if (t->d_has_ghost) cudaFree(t->d_has_ghost);
-  if (t->d_flags) cudaFree(t->d_flags);
-  if (t->d_tab) cudaFree(t->d_tab);
+  void *bufs[] = {t->d_ell, t->d_nell, t->d_csr16, t->d_ncsr, t->d_ell_s, t->d_nell_s, t->d_stg_j, t->d_stg_n, t->d_int_slot, t->d_int_glob,
+                  t->d_order, t->d_has_ghost, t->d_flags, t->d_tab};
+  for (void *p : bufs) if (p) cudaFree(p);
+  if (t->h_tab) cudaFreeHost(t->h_tab);
   delete t;
 }
 
@@ -1046,23 +1031,26 @@ int emd_tiles_info(const emd_tiles *t, int *tile_dims, int *ntiles, int *stride,
   return 0;
 }
 
-int emd_tiles_lists(const emd_tiles *t, const unsigned short **d_ell, const int **d_nell, int *maxrow_s, const unsigned short **d_ell_s,
-                    const int **d_nell_s, const unsigned short **d_int_slot) {
-  if (!t || !t->valid) { set_error("emd_tiles_lists: tiles not built"); return 1; }
-  if (d_ell) *d_ell = t->a.ell;
-  if (d_nell) *d_nell = t->a.nell;
-  if (maxrow_s) *maxrow_s = t->a.maxrow_s;
+int emd_tiles_lists(const emd_tiles *t, const unsigned short **d_csr16, const int **d_ncsr, const unsigned short **d_ell_s,
+                    const int **d_nell_s, const unsigned short **d_int_slot, const int **d_stg_j) {
+  if (!t || !t->valid || !t->rows_ready) { set_error("emd_tiles_lists: lists not built"); return 1; }
+  if (d_csr16) *d_csr16 = t->exact_key >= 0 ? t->a.csr16 : nullptr;
+  if (d_ncsr) *d_ncsr = t->exact_key >= 0 ? t->a.ncsr : nullptr;
   if (d_ell_s) *d_ell_s = t->a.ell_s;
   if (d_nell_s) *d_nell_s = t->a.nell_s;
   if (d_int_slot) *d_int_slot = t->a.int_slot;
+  if (d_stg_j) *d_stg_j = t->a.stg_j;
   return 0;
 }
 
-// Build the tile-local full adjacency.  Returns 0 on success, 3 if the fast path does not apply
-// to this configuration (the caller then uses emd_neigh_csr_* / emd_neigh_2d_fill), 1 on error.
+// Starts a build: tile shape and capacities from the mean density, then the search launches (no host synchronisation:
+// the overflow flags are read back together with the row total in emd_neigh_tiles_count, or before the first force launch).
+// Returns 0 on success, 3 if the fast path does not apply to this configuration (the caller then uses
+// emd_neigh_csr_* / emd_neigh_2d_fill), 1 on error.
 int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_local, int n_all, const emd_bin_geom *g,
                           const int *d_bincount, const int *d_binoffsets, const int *d_permute, double neigh_cut) {
   t->valid = false;
+  t->ctx = ctx;
   const int nix = g->nbinx - 2 * g->nhalo, niy = g->nbiny - 2 * g->nhalo, niz = g->nbinz - 2 * g->nhalo;
   if (nix <= 0 || niy <= 0 || niz <= 0 || n_local <= 0) return 3;
   const double wx = (g->maxx - g->minx) / g->nbinx, wy = (g->maxy - g->miny) / g->nbiny, wz = (g->maxz - g->minz) / g->nbinz;
@@ -1071,211 +1059,142 @@ int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_l
   // misses pairs otherwise, and the generic kernels reproduce that
   if (neigh_cut > wx || neigh_cut > wy || neigh_cut > wz) return 3;
   TileArgs &a = t->a;
+  const bool same_grid = a.nbx == g->nbinx && a.nby == g->nbiny && a.nbz == g->nbinz && a.nhalo == g->nhalo && t->neigh_cut == neigh_cut;
   a.nbx = g->nbinx; a.nby = g->nbiny; a.nbz = g->nbinz; a.nhalo = g->nhalo;
   a.n_local = n_local;
   a.bincount = d_bincount; a.binoffsets = d_binoffsets; a.permute = d_permute;
   a.x = d_x; a.type = nullptr;
   a.ox = g->minx; a.oy = g->miny; a.oz = g->minz;
   a.wx = wx; a.wy = wy; a.wz = wz;
-  a.stride = kForceThreads;
+  a.stride = kRowThreads;
   // mean atoms per cell -> tile shape with ~0.9*stride atoms whose halo fits in shared memory
   const double m = std::max(1e-3, (double)n_all / ((double)g->nbinx * g->nbiny * g->nbinz));
-  const int cap_max = 3000; // 72 KB of FP64 coordinates: three force CTAs per SM
   static const int shapes[][3] = {{4, 4, 8}, {4, 4, 4}, {2, 4, 4}, {2, 2, 8}, {2, 2, 4}, {2, 2, 2}, {1, 2, 2}, {1, 1, 2}, {1, 1, 1}};
   int pick = -1;
   for (int s = 0; s < (int)(sizeof shapes / sizeof shapes[0]); s++) {
     const int *d = shapes[s];
     const double atoms = m * d[0] * d[1] * d[2], staged = m * (d[0] + 2) * (d[1] + 2) * (d[2] + 2);
     if ((d[0] + 2) * (d[1] + 2) * (d[2] + 2) > kMaxStagedCells || d[0] * d[1] * d[2] > kMaxInteriorCells) continue;
-    if (atoms <= 0.9 * a.stride && staged * 1.2 + 64 <= cap_max) { pick = s; break; }
+    if (atoms <= 0.9 * a.stride && staged * 1.2 + 64 <= kCapMax) { pick = s; break; }
   }
   if (pick < 0) return 3;
-  a.tx = std::min(shapes[pick][0], nix); a.ty = std::min(shapes[pick][1], niy); a.tz = std::min(shapes[pick][2], niz);
+  const int tx = std::min(shapes[pick][0], nix), ty = std::min(shapes[pick][1], niy), tz = std::min(shapes[pick][2], niz);
+  const bool same_shape = same_grid && tx == a.tx && ty == a.ty && tz == a.tz;
+  a.tx = tx; a.ty = ty; a.tz = tz;
   a.ntx = (nix + a.tx - 1) / a.tx; a.nty = (niy + a.ty - 1) / a.ty; a.ntz = (niz + a.tz - 1) / a.tz;
   const long long ntiles_ll = (long long)a.ntx * a.nty * a.ntz;
   if (ntiles_ll > 0x7fffffffLL) return 3;
   t->ntiles = (int)ntiles_ll;
   const int staged_cells = (a.tx + 2) * (a.ty + 2) * (a.tz + 2);
-  a.cap = std::min(cap_max, ((int)(m * staged_cells * 1.25) + 64 + 31) / 32 * 32);
-  // expected full-list row: density * sphere volume, +35 % head room
+  // capacities: from the density with head room; a build on the same grid keeps what an earlier build had to grow to
+  const int cap = std::min(kCapMax, ((int)(m * staged_cells * 1.25) + 64 + 31) / 32 * 32);
   const double rho = m / (wx * wy * wz);
-  int maxrow = (int)(rho * 4.18879020478639 * neigh_cut * neigh_cut * neigh_cut * 1.35) + 8;
-  maxrow = std::max(16, (maxrow + 7) / 8 * 8);
-  // conservative FP32 radius: coordinates are relative to the staged region (extent E), so the
-  // FP32 distance is off by < 8*E*2^-24; take 32*E*2^-23 + 2^-20 relative as the margin
-  const double E = std::max({(a.tx + 2) * wx, (a.ty + 2) * wy, (a.tz + 2) * wz});
-  const double thr = neigh_cut * (1.0 + 1.0 / 1048576.0) + 32.0 * E / 8388608.0;
-  t->cutf2 = nextafterf((float)(thr * thr), INFINITY);
+  int maxrow = (int)(rho * 4.18879020478639 * neigh_cut * neigh_cut * neigh_cut * 1.35) + 8; // expected full-list row + 35 %
+  maxrow = std::min(kMaxRowLimit, std::max(16, (maxrow + 7) / 8 * 8));
+  if (same_shape) { a.cap = std::max(a.cap, cap); a.maxrow = std::max(a.maxrow, maxrow); }
+  else { a.cap = cap; a.maxrow = maxrow; }
+  // Rounding margin of the FP32 search: coordinates are relative to the centre of the staged region, |p|^2 <= R2; the
+  // expanded form w_j + p_i.P_j carries ~4 roundings of magnitude <= 2 R2 plus the input rounding of p (2 r |dp|).
+  const double R2 = 0.25 * ((a.tx + 2) * wx * (a.tx + 2) * wx + (a.ty + 2) * wy * (a.ty + 2) * wy + (a.tz + 2) * wz * (a.tz + 2) * wz);
+  const double thr2 = neigh_cut * neigh_cut * (1.0 + 1e-5) + 64.0 * R2 / 8388608.0;
+  t->thr2 = nextafterf((float)thr2, INFINITY);
   t->neigh_cut = neigh_cut;
-
-  for (int attempt = 0; attempt < 4; attempt++) {
-    a.maxrow = maxrow;
-    const size_t ell_bytes = (size_t)t->ntiles * a.maxrow * a.stride * sizeof(unsigned short);
-    if (ensure_bytes((void **)&t->d_ell, &t->ell_cap, ell_bytes)) return 1;
-    if (ensure_bytes((void **)&t->d_nell, &t->nell_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
-    a.ell = t->d_ell; a.nell = t->d_nell; a.flags = t->d_flags;
-    EMD_CUDA(cudaMemsetAsync(t->d_flags, 0, 4 * sizeof(int), ctx->stream));
-    const size_t smem = (size_t)a.cap * sizeof(float4);
-    if (set_smem(tiles_filter_kernel, smem)) return 1;
-    EMD_LAUNCH(ctx, tiles_filter_kernel, t->ntiles, kFilterThreads, smem, a, t->cutf2);
-    EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    EMD_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int bits = ctx->h_pinned[0], need_row = ctx->h_pinned[1], need_cap = ctx->h_pinned[2], need_int = ctx->h_pinned[3];
-    if (bits == 0) {
-      // the slot numbering does not depend on cap: shrink it to the largest tile, so that the force
-      // kernel's two coordinate buffers leave room for two CTAs per SM
-      a.cap = std::max(32, (need_cap + 31) / 32 * 32);
-      if (a.cap > kForceThreads * kStagePerThread) return 3;
-      if (ensure_bytes((void **)&t->d_stg_j, &t->stg_j_cap, (size_t)t->ntiles * a.cap * sizeof(int))) return 1;
-      if (ensure_bytes((void **)&t->d_stg_n, &t->stg_n_cap, (size_t)t->ntiles * sizeof(int))) return 1;
-      if (ensure_bytes((void **)&t->d_int_slot, &t->int_slot_cap, (size_t)t->ntiles * a.stride * sizeof(unsigned short))) return 1;
-      if (ensure_bytes((void **)&t->d_int_glob, &t->int_glob_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
-      if (ensure_bytes((void **)&t->d_order, &t->order_cap, (size_t)t->ntiles * sizeof(int))) return 1;
-      if (ensure_bytes((void **)&t->d_has_ghost, &t->has_ghost_cap, (size_t)t->ntiles * sizeof(int))) return 1;
-      a.stg_j = t->d_stg_j; a.stg_n = t->d_stg_n; a.int_slot = t->d_int_slot; a.int_glob = t->d_int_glob;
-      a.order = t->d_order; a.has_ghost = t->d_has_ghost;
-      EMD_CUDA(cudaMemsetAsync(t->d_flags + 4, 0, 4 * sizeof(int), ctx->stream));
-      EMD_LAUNCH(ctx, tiles_tables_kernel, t->ntiles, kFilterThreads, 0, a);
-      // the force kernel's copy of the adjacency: bank-conflict-free columns (tiles_schedule_kernel)
-      if (ensure_bytes((void **)&t->d_nell_s, &t->nell_s_cap, (size_t)t->ntiles * a.stride * sizeof(int))) return 1;
-      a.nell_s = t->d_nell_s;
-      // EMD_TILES_SCHED = full | rot | none (measurement switch; default below)
-      int mode = SCHED_ROT;
-      if (const char *e = getenv("EMD_TILES_SCHED")) mode = !strcmp(e, "full") ? SCHED_FULL : !strcmp(e, "none") ? SCHED_NONE : SCHED_ROT;
-      if (a.maxrow > kSchedMaxRow) mode = SCHED_NONE;
-      int maxrow_s = a.maxrow + 8;
-      const long long warps = (long long)t->ntiles * (a.stride / 32);
-      const int sgrid = (int)((warps + kSchedWarps - 1) / kSchedWarps);
-      for (int sa = 0; sa < 4; sa++) {
-        a.maxrow_s = maxrow_s;
-        if (ensure_bytes((void **)&t->d_ell_s, &t->ell_s_cap, (size_t)t->ntiles * a.maxrow_s * a.stride * sizeof(unsigned short))) return 1;
-        a.ell_s = t->d_ell_s;
-        const size_t wsm = sched_warp_smem(a.maxrow, a.maxrow_s), ssm = wsm * kSchedWarps;
-        if (ssm > (size_t)t->max_smem_optin) return 3;
-        EMD_CUDA(cudaMemsetAsync(t->d_flags, 0, 4 * sizeof(int), ctx->stream));
-        EMD_LAUNCH(ctx, tiles_order_kernel, 1, 1024, 0, a, t->ntiles); // writes flags[2]
-#define EMD_SCHED(M)                                                                                                        \
-  do {                                                                                                                     \
-    if (set_smem(tiles_schedule_kernel<M>, ssm)) return 1;                                                                 \
-    EMD_LAUNCH(ctx, tiles_schedule_kernel<M>, sgrid, 32 * kSchedWarps, ssm, a, t->ntiles, (unsigned)wsm);                  \
-  } while (0)
-        if (mode == SCHED_ROT) {
-          const size_t rwsm = rot_warp_smem(a.maxrow), rsm = rwsm * kRotWarps;
-          if (set_smem(tiles_rotate_kernel, rsm)) return 1;
-          EMD_LAUNCH(ctx, tiles_rotate_kernel, (int)((warps + kRotWarps - 1) / kRotWarps), 32 * kRotWarps, rsm, a, t->ntiles, (unsigned)rwsm);
-        } else if (mode == SCHED_FULL) EMD_SCHED(SCHED_FULL);
-        else EMD_SCHED(SCHED_NONE);
-#undef EMD_SCHED
-        EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        EMD_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (!(ctx->h_pinned[0] & 8)) {
-          t->n_free_tiles = ctx->h_pinned[2];
-          t->all_owned_have_rows = ctx->h_pinned[4] == n_local;
-          t->valid = true;
-          return 0;
-        }
-        maxrow_s = (ctx->h_pinned[1] + ctx->h_pinned[1] / 8 + 15) / 8 * 8;
-      }
-      return 3;
-    }
-    if (bits & 2) { (void)need_int; return 3; } // a tile holds more atoms than threads: density far from the estimate
-    if (bits & 1) {
-      if (need_cap > cap_max || need_cap > 65535) return 3;
-      a.cap = (need_cap + need_cap / 16 + 31) / 32 * 32;
-      if (a.cap > cap_max) a.cap = cap_max;
-    }
-    if (bits & 4) maxrow = (need_row + need_row / 8 + 7) / 8 * 8;
-  }
-  return 3;
+  return launch_search(ctx, t);
 }
 
 int emd_neigh_tiles_count(emd_ctx *ctx, emd_tiles *t, int half, int newton, int *d_row_map, int *h_total) {
   if (!t || !t->valid) { set_error("emd_neigh_tiles_count: tiles not built"); return 1; }
-  TileArgs &a = t->a;
-  EmitArgs e;
-  memset(&e, 0, sizeof e);
-  e.cutsq = t->neigh_cut * t->neigh_cut; e.newton = newton; e.counts = d_row_map;
-  EMD_CUDA(cudaMemsetAsync(d_row_map, 0, sizeof(int) * ((size_t)a.n_local + 1), ctx->stream));
-  const size_t smem = emit_smem(a.cap, a.stride);
-  if (half) { if (set_smem(tiles_emit_kernel<true, EMIT_COUNT>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<true, EMIT_COUNT>), t->ntiles, a.stride, smem, a, e); }
-  else { if (set_smem(tiles_emit_kernel<false, EMIT_COUNT>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<false, EMIT_COUNT>), t->ntiles, a.stride, smem, a, e); }
-  if (exclusive_scan_int(ctx, d_row_map, d_row_map, a.n_local + 1, nullptr)) return 1;
-  if (h_total) {
-    EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_row_map + a.n_local, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    EMD_CUDA(cudaStreamSynchronize(ctx->stream));
-    *h_total = ctx->h_pinned[0];
-    if (*h_total < 0) { set_error("emd_neigh_tiles_count: neighbor count overflows 32-bit row_map"); return 2; }
+  for (int attempt = 0; attempt < 5; attempt++) {
+    TileArgs &a = t->a;
+    EMD_CUDA(cudaMemsetAsync(d_row_map, 0, sizeof(int) * ((size_t)a.n_local + 1), ctx->stream));
+    if (!t->valid) { const int rc = launch_search(ctx, t); if (rc) return rc; }
+    const int key = (half ? 1 : 0) | (newton ? 2 : 0);
+    if (!t->rows_ready || t->exact_key != key) { const int rc = launch_lists(ctx, t, true, half, newton, d_row_map); if (rc) return rc; }
+    else EMD_LAUNCH(ctx, tiles_counts_kernel, t->ntiles, kRowThreads, 0, a, d_row_map);
+    if (exclusive_scan_int(ctx, d_row_map, d_row_map, a.n_local + 1, nullptr)) return 1;
+    int total = 0;
+    const int rc = check_flags(ctx, t, a.n_local, d_row_map + a.n_local, &total);
+    if (rc == 2) continue; // a capacity grew: search and lists again
+    if (rc) return rc;
+    if (h_total) *h_total = total;
+    if (total < 0) { set_error("emd_neigh_tiles_count: neighbor count overflows 32-bit row_map"); return 2; }
+    return 0;
   }
-  return 0;
+  return 3;
 }
 
 int emd_neigh_tiles_fill_csr(emd_ctx *ctx, emd_tiles *t, int half, int newton, const int *d_row_map, int *d_entries) {
   if (!t || !t->valid) { set_error("emd_neigh_tiles_fill_csr: tiles not built"); return 1; }
-  TileArgs &a = t->a;
-  EmitArgs e;
+  const int rc = ensure_lists(ctx, t, true, half, newton, nullptr);
+  if (rc) { if (rc == 3) set_error("emd_neigh_tiles_fill_csr: tile lists not available"); return rc; }
+  FillArgs e;
   memset(&e, 0, sizeof e);
-  e.cutsq = t->neigh_cut * t->neigh_cut; e.newton = newton; e.row_map = d_row_map; e.entries = d_entries;
-  const size_t smem = emit_smem(a.cap, a.stride);
-  if (half) { if (set_smem(tiles_emit_kernel<true, EMIT_CSR>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<true, EMIT_CSR>), t->ntiles, a.stride, smem, a, e); }
-  else { if (set_smem(tiles_emit_kernel<false, EMIT_CSR>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<false, EMIT_CSR>), t->ntiles, a.stride, smem, a, e); }
+  e.row_map = d_row_map; e.entries = d_entries;
+  EMD_LAUNCH(ctx, tiles_fill_kernel<FILL_CSR>, t->ntiles, kRowThreads, 0, t->a, e);
   return 0;
 }
 
 int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half, int newton, int maxneighs, int *d_num_neighs, int *d_neighs,
                             int *h_max_count) {
   if (!t || !t->valid) { set_error("emd_neigh_tiles_fill_2d: tiles not built"); return 1; }
+  const int rc = ensure_lists(ctx, t, true, half, newton, nullptr);
+  if (rc) { if (rc == 3) set_error("emd_neigh_tiles_fill_2d: tile lists not available"); return rc; }
   TileArgs &a = t->a;
-  EmitArgs e;
+  FillArgs e;
   memset(&e, 0, sizeof e);
-  e.cutsq = t->neigh_cut * t->neigh_cut; e.newton = newton; e.counts = d_num_neighs; e.entries = d_neighs; e.maxneighs = maxneighs;
-  e.max_count = t->d_flags + 1;
-  EMD_CUDA(cudaMemsetAsync(e.max_count, 0, sizeof(int), ctx->stream));
+  e.entries = d_neighs; e.num_neighs = d_num_neighs; e.maxneighs = maxneighs;
+  EMD_CUDA(cudaMemsetAsync(t->d_flags + FL_MAX2D, 0, sizeof(int), ctx->stream));
   EMD_CUDA(cudaMemsetAsync(d_num_neighs, 0, sizeof(int) * ((size_t)a.n_local + 1), ctx->stream));
-  const size_t smem = emit_smem(a.cap, a.stride);
-  if (half) { if (set_smem(tiles_emit_kernel<true, EMIT_2D>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<true, EMIT_2D>), t->ntiles, a.stride, smem, a, e); }
-  else { if (set_smem(tiles_emit_kernel<false, EMIT_2D>, smem)) return 1; EMD_LAUNCH(ctx, (tiles_emit_kernel<false, EMIT_2D>), t->ntiles, a.stride, smem, a, e); }
+  EMD_LAUNCH(ctx, tiles_fill_kernel<FILL_2D>, t->ntiles, kRowThreads, 0, a, e);
   if (h_max_count) {
-    EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, e.max_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, t->d_flags + FL_MAX2D, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     EMD_CUDA(cudaStreamSynchronize(ctx->stream));
     *h_max_count = ctx->h_pinned[0];
   }
   return 0;
 }
 
+} // extern "C"
+
 // ForceLJNeigh::compute / compute_energy on the tile lists.  d_x/d_type are the CURRENT arrays
 // (atoms keep their indices between rebuilds; the binning arrays captured at build time must
 // still be alive).  With h_pe != NULL only the energy is computed (forces untouched).
 // part: 0 = every tile; 1 = only the tiles that do not read the halo (their forces are final before the halo exchange of
 // this step has landed); 2 = the rest.  reserve_ctas > 0 leaves that many CTA slots of the persistent grid free, so that
-// the pack and NCCL kernels of a concurrent halo exchange find room on the SMs.
+// the pack and transport kernels of a concurrent halo exchange find room on the SMs.
 static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe, int part,
                            int reserve_ctas, const NveFuse *fuse = nullptr) {
   if (!t || !t->valid) { set_error("emd_force_lj_compute_tiles: tiles not built"); return 1; }
   if (ctx->lj.ntypes == 0) { set_error("emd_force_lj_compute_tiles: parameters not set"); return 1; }
   if (part < 0 || part > 2 || (h_pe && part != 0)) { set_error("emd_force_lj_compute_tiles: bad part"); return 1; }
   if (fuse && h_pe) { set_error("emd_force_lj_compute_tiles: the energy launch cannot carry the integrator"); return 1; }
+  if (!t->rows_ready || !t->checked) { // a build that nobody asked a CSR / 2D list of
+    const int rc = ensure_lists(ctx, t, false, 0, 0, nullptr);
+    if (rc) { if (rc == 3) set_error("emd_force_lj_compute_tiles: tile lists not available"); return rc == 3 ? 1 : rc; }
+  }
+  // an owned atom outside the interior bins has no row (the reference leaves it without neighbors, neighbor_csr.h:184):
+  // its force is the zero of the reference's deep_copy(f, 0)
+  if (!t->all_owned_have_rows && !h_pe && part == 0) EMD_CUDA(cudaMemsetAsync(d_f, 0, sizeof(double) * 3 * (size_t)t->a.n_local, ctx->stream));
   const NveFuse nve = fuse ? *fuse : NveFuse{nullptr, nullptr, nullptr, 0.0, 0.0};
   TileArgs a = t->a;
   a.x = d_x; a.type = d_type;
   const bool one = ctx->lj.ntypes == 1;
-  LJOne p1 = {ctx->lj.lj1[0], ctx->lj.lj2[0], ctx->lj.cutsq[0]};
-  if (!one) {
-    LJTab h;
-    h.ntypes = ctx->lj.ntypes;
-    memcpy(h.lj1, ctx->lj.lj1, sizeof h.lj1); memcpy(h.lj2, ctx->lj.lj2, sizeof h.lj2); memcpy(h.cutsq, ctx->lj.cutsq, sizeof h.cutsq);
-    EMD_CUDA(cudaMemcpyAsync(t->d_tab, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
-    EMD_CUDA(cudaStreamSynchronize(ctx->stream)); // h is a stack object
+  LJOne p1 = {ctx->lj.lj1[0], ctx->lj.lj2[0], ctx->lj.cutsq[0], 0.0, 0.0, 0.0};
+  lj_energy_consts(p1.lj1, p1.lj2, p1.cutsq, p1.e1, p1.e2, p1.eshift);
+  if (!one && t->tab_version != ctx->lj_version) { // the pair table travels once per emd_force_lj_set_params
+    LJTab *h = t->h_tab;
+    h->ntypes = ctx->lj.ntypes;
+    memcpy(h->lj1, ctx->lj.lj1, sizeof h->lj1); memcpy(h->lj2, ctx->lj.lj2, sizeof h->lj2); memcpy(h->cutsq, ctx->lj.cutsq, sizeof h->cutsq);
+    for (int k = 0; k < h->ntypes * h->ntypes; k++) lj_energy_consts(h->lj1[k], h->lj2[k], h->cutsq[k], h->e1[k], h->e2[k], h->eshift[k]);
+    EMD_CUDA(cudaMemcpyAsync(t->d_tab, h, sizeof *h, cudaMemcpyHostToDevice, ctx->stream));
+    EMD_CUDA(cudaStreamSynchronize(ctx->stream));
+    t->tab_version = ctx->lj_version;
   }
-  const size_t base_smem = force_smem(a.cap, !one);
-  if (base_smem > (size_t)t->max_smem_optin) { set_error("emd_force_lj_compute_tiles: tile does not fit in shared memory"); return 1; }
-  // the ELL ring (16 bytes per thread) only if two CTAs still fit on one SM (1 KB per CTA is reserved by the system).
-  // Measured at 2 M atoms (gpurun r01t): the ring halves the long-scoreboard stalls (18 % -> 10 % of samples) but the
-  // per-iteration cp.async wait and the extra LDS.128 cost more than that buys: 0.386 ms against 0.367 ms with the L1
-  // prefetch.  Off unless EMD_TILES_RING=1.
-  const bool ring_allowed = getenv("EMD_TILES_RING") && atoi(getenv("EMD_TILES_RING"));
-  const size_t ring_smem = base_smem + (size_t)kForceThreads * sizeof(uint4);
-  const bool ring = !fuse && ring_allowed && 2 * (ring_smem + 1024) <= (size_t)t->max_smem_sm && 2 * (base_smem + 1024) <= (size_t)t->max_smem_sm;
-  const size_t smem = ring ? ring_smem : base_smem;
+  // three coordinate buffers if two CTAs still fit on one SM (1 KB per CTA is reserved by the system), else two
+  int nbuf = kMaxBuf;
+  if (2 * (force_smem(a.fcap, !one, 3) + 1024) > (size_t)t->max_smem_sm) nbuf = 2;
+  const size_t smem = force_smem(a.fcap, !one, nbuf);
+  if (smem > (size_t)t->max_smem_optin) { set_error("emd_force_lj_compute_tiles: tile does not fit in shared memory"); return 1; }
   const int first = part == 2 ? t->n_free_tiles : 0;
   const int count = part == 0 ? t->ntiles : part == 1 ? t->n_free_tiles : t->ntiles - t->n_free_tiles;
   if (count <= 0) return 0;
@@ -1285,21 +1204,20 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
     if (ctx->s_c.ensure(sizeof(double) * ((size_t)grid + 8))) return 1;
     partial = ctx->s_c.as<double>() + 8;
   }
-#define EMD_LJ_TILES(ONE, EN, RG, FU)                                                                                      \
+#define EMD_LJ_TILES(ONE, MD)                                                                                              \
   do {                                                                                                                     \
-    if (set_smem(lj_tiles_kernel<ONE, EN, RG, FU>, smem)) return 1;                                                        \
-    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, EN, RG, FU>), grid, kForceThreads, smem, a, first, count, p1, t->d_tab, d_f,     \
-               partial, (unsigned)base_smem, nve);                                                                         \
+    if (set_smem(lj_tiles_kernel<ONE, MD>, smem)) return 1;                                                                \
+    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, MD>), grid, kForceThreads, smem, a, first, count, nbuf, p1, t->d_tab, d_f, partial, nve); \
   } while (0)
-#define EMD_LJ_TILES2(ONE, EN) do { if (ring) EMD_LJ_TILES(ONE, EN, true, false); else EMD_LJ_TILES(ONE, EN, false, false); } while (0)
-  if (fuse) { if (one) EMD_LJ_TILES(true, false, false, true); else EMD_LJ_TILES(false, false, false, true); }
-  else if (h_pe) { if (one) EMD_LJ_TILES2(true, true); else EMD_LJ_TILES2(false, true); }
-  else { if (one) EMD_LJ_TILES2(true, false); else EMD_LJ_TILES2(false, false); }
-#undef EMD_LJ_TILES2
+  if (fuse) { if (one) EMD_LJ_TILES(true, MODE_NVE); else EMD_LJ_TILES(false, MODE_NVE); }
+  else if (h_pe) { if (one) EMD_LJ_TILES(true, MODE_ENERGY); else EMD_LJ_TILES(false, MODE_ENERGY); }
+  else { if (one) EMD_LJ_TILES(true, MODE_FORCE); else EMD_LJ_TILES(false, MODE_FORCE); }
 #undef EMD_LJ_TILES
   if (h_pe) return device_sum_partials(ctx, partial, grid, h_pe);
   return 0;
 }
+
+extern "C" {
 
 int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe) {
   return lj_tiles_launch(ctx, t, d_x, d_type, d_f, h_pe, 0, 0);
@@ -1312,7 +1230,7 @@ int emd_force_lj_compute_tiles_part(emd_ctx *ctx, emd_tiles *t, const double *d_
 
 int emd_force_lj_compute_tiles_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *d_v,
                                    double *d_x_new, const double *d_mass, double dtf, double dtv) {
-  if (t && t->valid && !t->all_owned_have_rows) return 3; // an owned atom has no row: its position would not be advanced
+  if (t && t->valid && t->checked && !t->all_owned_have_rows) return 3; // an owned atom has no row: its position would not be advanced
   if (!d_v || !d_x_new || !d_mass || d_x_new == d_x) { set_error("emd_force_lj_compute_tiles_nve: v, mass and a second position array are required"); return 1; }
   const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv};
   return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, 0, 0, &nve);
@@ -1320,22 +1238,33 @@ int emd_force_lj_compute_tiles_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x
 
 int emd_force_lj_compute_tiles_part_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, int part,
                                         int reserve_ctas, double *d_v, double *d_x_new, const double *d_mass, double dtf, double dtv) {
-  if (t && t->valid && !t->all_owned_have_rows) return 3;
+  if (t && t->valid && t->checked && !t->all_owned_have_rows) return 3;
   if (!d_v || !d_x_new || !d_mass || d_x_new == d_x) { set_error("emd_force_lj_compute_tiles_part_nve: v, mass and a second position array are required"); return 1; }
   const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv};
   return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, part, reserve_ctas, &nve);
 }
 
+// the build is asynchronous: the first question about its outcome makes the force rows and reads the flags back
+static int settle(const emd_tiles *tc, const char *who) {
+  emd_tiles *t = const_cast<emd_tiles *>(tc);
+  if (!t || !t->valid) { set_error("%s: tiles not built", who); return 1; }
+  if (t->checked && t->rows_ready) return 0;
+  const int rc = ensure_lists(t->ctx, t, false, 0, 0, nullptr);
+  if (rc == 3) set_error("%s: tile lists not available", who);
+  return rc ? 1 : 0;
+}
+
 int emd_tiles_complete(const emd_tiles *t, int *all_owned_have_rows) {
-  if (!t || !t->valid) { set_error("emd_tiles_complete: tiles not built"); return 1; }
+  if (settle(t, "emd_tiles_complete")) return 1;
   if (all_owned_have_rows) *all_owned_have_rows = t->all_owned_have_rows ? 1 : 0;
   return 0;
 }
 
 int emd_tiles_halo_split(const emd_tiles *t, int *n_free, int *n_halo) {
-  if (!t || !t->valid) { set_error("emd_tiles_halo_split: tiles not built"); return 1; }
-  if (n_free) *n_free = t->n_free_tiles;
-  if (n_halo) *n_halo = t->ntiles - t->n_free_tiles;
+  if (settle(t, "emd_tiles_halo_split")) return 1;
+  // an incomplete build is not split: the single launch zeroes the rows that no tile writes
+  if (n_free) *n_free = t->all_owned_have_rows ? t->n_free_tiles : 0;
+  if (n_halo) *n_halo = t->all_owned_have_rows ? t->ntiles - t->n_free_tiles : t->ntiles;
   return 0;
 }
 

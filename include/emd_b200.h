@@ -153,13 +153,15 @@ int emd_force_lj_energy(emd_ctx *ctx, const double *d_x, const int *d_type, int 
 
 /* ---- tile lists: the B200 fast path of the neighbor build + LJ force (kernels/tiles.cu) -------
  * An emd_tiles object holds a tile-local FULL adjacency (shared-memory slot numbers, ELL layout)
- * built from the same inputs as the reference lists.  The reference-visible CSR / 2D lists are
- * emitted FROM it with the reference's exact FP64 inclusion rules, so they are bit-identical to
- * emd_neigh_csr_count/fill and emd_neigh_2d_fill; the LJ force then runs on the tile lists with
- * every x[j] served from shared memory and no atomics (each pair is evaluated from both sides).
- * emd_neigh_tiles_build returns 0 on success and 3 when the fast path does not apply to this
- * configuration (bins narrower than the list radius, a tile that does not fit in shared memory):
- * the caller then uses the generic entry points above.  The binning arrays passed to build must
+ * built from the same inputs as the reference lists: an FP32 search leaves one bit per stencil
+ * candidate; the reference-visible CSR / 2D lists are made FROM those bits with the reference's
+ * exact FP64 inclusion rules, so they are bit-identical to emd_neigh_csr_count/fill and
+ * emd_neigh_2d_fill; the LJ force then runs on the tile lists with every x[j] served from shared
+ * memory and no atomics (each pair is evaluated from both sides).
+ * emd_neigh_tiles_build / _count return 0 on success and 3 when the fast path does not apply to
+ * this configuration (bins narrower than the list radius, a tile that does not fit in shared
+ * memory): the caller then uses the generic entry points above.  A re-neighboring synchronises
+ * with the host once (the row total of emd_neigh_tiles_count, read back with the overflow flags).  The binning arrays passed to build must
  * stay alive and unchanged until the next build (they are re-read by every later call). */
 typedef struct emd_tiles emd_tiles;
 int emd_tiles_create(emd_tiles **out);
@@ -167,13 +169,14 @@ void emd_tiles_destroy(emd_tiles *t);
 int emd_tiles_valid(const emd_tiles *t);
 void emd_tiles_invalidate(emd_tiles *t);
 int emd_tiles_info(const emd_tiles *t, int *tile_dims3, int *ntiles, int *stride, int *maxrow, int *cap);
-/* Device pointers of the two copies of the tile adjacency (inspection / tests): the list-order rows the
- * CSR/2D lists are emitted from (ell: [ntiles][maxrow/8][stride][8] uint16 staged-slot numbers, nell:
- * [ntiles][stride] row lengths) and the force kernel's copy, re-ordered into shared-memory
- * bank-conflict-free columns (ell_s, nell_s, capacity maxrow_s; bit 15 of an entry marks padding);
- * int_slot: [ntiles][stride] staged slot of the row's own atom.  Any pointer argument may be NULL. */
-int emd_tiles_lists(const emd_tiles *t, const unsigned short **d_ell, const int **d_nell, int *maxrow_s,
-                    const unsigned short **d_ell_s, const int **d_nell_s, const unsigned short **d_int_slot);
+/* Device pointers of the tile lists (inspection / tests).  csr16 / ncsr: the EXACT rows of the list type last asked for
+ * (emd_neigh_tiles_count / fill_*), in the reference's order, as staged-slot numbers ([ntiles][maxrow/8][stride][8] uint16,
+ * row lengths [ntiles][stride]); NULL if no exact list was made of this build.  ell_s / nell_s: the force kernel's rows, a
+ * conservative FP32 superset of the full list re-ordered into shared-memory bank-conflict-free columns; an entry is the byte
+ * offset 24*(16 + slot) of the neighbor's staged coordinates, entries < 24*16 are padding (16 dummy atoms lead the buffer).  int_slot: [ntiles][stride] staged
+ * slot of the row's own atom; stg_j: [ntiles][cap] atom index of every staged slot.  Any pointer argument may be NULL. */
+int emd_tiles_lists(const emd_tiles *t, const unsigned short **d_csr16, const int **d_ncsr, const unsigned short **d_ell_s,
+                    const int **d_nell_s, const unsigned short **d_int_slot, const int **d_stg_j);
 int emd_neigh_tiles_build(emd_ctx *ctx, emd_tiles *t, const double *d_x, int n_local, int n_all,
                           const emd_bin_geom *geom, const int *d_bincount, const int *d_binoffsets,
                           const int *d_permute, double neigh_cut);

@@ -105,31 +105,37 @@ class Tiles:
         return {"dims": tuple(d), "ntiles": nt.value, "stride": st.value, "maxrow": mr.value, "cap": cap.value}
 
     def lists(self):
-        """host copies of both adjacency layouts as [ntiles][words][stride][8] uint16 arrays (+ row lengths, own slots)"""
+        """host copies of the tile lists: exact rows (csr16/ncsr, None before a CSR/2D list was asked for) and the force
+        kernel's rows (ell_s/nell_s), both [ntiles][words][stride][8] uint16, + own slots and the slot -> atom table"""
         inf = self.info()
-        ell, nell, ell_s, nell_s, islot = P(), P(), P(), P(), P()
-        mrs = C.c_int()
-        emd.check(emd.lib().emd_tiles_lists(self.h, C.byref(ell), C.byref(nell), C.byref(mrs), C.byref(ell_s), C.byref(nell_s), C.byref(islot)))
-        nt, st = inf["ntiles"], inf["stride"]
+        csr16, ncsr, ell_s, nell_s, islot, stgj = P(), P(), P(), P(), P(), P()
+        emd.check(emd.lib().emd_tiles_lists(self.h, C.byref(csr16), C.byref(ncsr), C.byref(ell_s), C.byref(nell_s), C.byref(islot), C.byref(stgj)))
+        nt, st, mr, cap = inf["ntiles"], inf["stride"], inf["maxrow"], inf["cap"]
 
         def grab(p, count, dtype):
             h = np.empty(count, dtype=dtype)
             emd.check(emd.lib().emd_memcpy_d2h(self.ctx.handle, h.ctypes.data_as(P), p, h.nbytes), "emd_memcpy_d2h")
             return h
 
-        out = {"maxrow": inf["maxrow"], "maxrow_s": mrs.value, "stride": st, "ntiles": nt}
-        out["ell"] = grab(ell, nt * inf["maxrow"] * st, np.uint16).reshape(nt, inf["maxrow"] // 8, st, 8)
-        out["nell"] = grab(nell, nt * st, np.int32).reshape(nt, st)
-        out["ell_s"] = grab(ell_s, nt * mrs.value * st, np.uint16).reshape(nt, mrs.value // 8, st, 8)
+        out = {"maxrow": mr, "stride": st, "ntiles": nt, "cap": cap}
+        if csr16:
+            out["csr16"] = grab(csr16, nt * mr * st, np.uint16).reshape(nt, mr // 8, st, 8)
+            out["ncsr"] = grab(ncsr, nt * st, np.int32).reshape(nt, st)
+        out["ell_s"] = grab(ell_s, nt * mr * st, np.uint16).reshape(nt, mr // 8, st, 8)
         out["nell_s"] = grab(nell_s, nt * st, np.int32).reshape(nt, st)
         out["int_slot"] = grab(islot, nt * st, np.uint16).reshape(nt, st)
+        out["stg_j"] = grab(stgj, nt * cap, np.int32).reshape(nt, cap)
         return out
 
     def csr(self, half, newton):
         L = emd.lib()
         rm = torch.empty(self.n_local + 1, dtype=torch.int32, device="cuda")
         total = C.c_int()
-        emd.check(L.emd_neigh_tiles_count(self.ctx.handle, self.h, half, newton, ptr(rm), C.byref(total)), "tiles_count")
+        rc = L.emd_neigh_tiles_count(self.ctx.handle, self.h, half, newton, ptr(rm), C.byref(total))
+        if rc == 3:  # the build is asynchronous: "fast path not applicable" may only show when the flags are read back
+            self.rc = 3
+            return None, None, -1
+        emd.check(rc, "tiles_count")
         ent = torch.empty(max(total.value, 1), dtype=torch.int32, device="cuda")
         emd.check(L.emd_neigh_tiles_fill_csr(self.ctx.handle, self.h, half, newton, ptr(rm), ptr(ent)), "tiles_fill_csr")
         return rm, ent[: total.value], total.value

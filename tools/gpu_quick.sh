@@ -10,7 +10,7 @@ else
   (time timeout 900 python -m pytest tests -m gpu -x -q) > $out/pytest_gpu.log 2>&1
 fi
 tail -15 $out/pytest_gpu.log
-(time timeout 600 python bench.py --steps 100 --warmup 20 --no-cpu-baseline --no-snap) > $out/bench.json 2> $out/bench.err
+(time timeout 600 python bench.py --steps 100 --warmup 20 --no-cpu-baseline --no-extra) > $out/bench.json 2> $out/bench.err
 tail -c 2500 $out/bench.json; tail -3 $out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_bench.csv \
-   python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-snap > $out/ncu_bench.log 2>&1
+   python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_bench.log 2>&1
