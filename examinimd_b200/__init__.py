@@ -106,6 +106,7 @@ _SIGS = {
     "emd_neigh_tiles_fill_csr": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "emd_neigh_tiles_fill_2d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "emd_force_lj_compute_tiles": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
+    "emd_force_lj_compute_tiles_with_energy": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
     "emd_force_lj_compute_tiles_part": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "emd_force_lj_compute_tiles_nve": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double]),
     "emd_force_lj_compute_tiles_part_nve": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_double, C.c_double]),

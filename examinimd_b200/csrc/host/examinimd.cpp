@@ -158,7 +158,7 @@ void ExaMiniMD::thermo(T_FLOAT *T, T_FLOAT *PE, T_FLOAT *KE) {
   *KE = kine.compute(system) / system->N;
 }
 
-void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
+void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next, bool observed) {
   const T_F_FLOAT neigh_cutoff = input->force_cutoff + input->neighbor_skin;
   static const bool overlap_halo = !(getenv("EMD_NO_OVERLAP") && atoi(getenv("EMD_NO_OVERLAP")));
   static const bool comm_first = !(getenv("EMD_OVERLAP_ORDER") && atoi(getenv("EMD_OVERLAP_ORDER")) == 0);
@@ -183,7 +183,7 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
   } else {
     // decomposed run: the share of the force that reads no ghost atom starts now, on the side stream, and overlaps the
     // halo exchange (the reference's blocking sequence update_halo -> compute, examinimd.cpp:226-235, otherwise)
-    split = overlap_halo && comm->num_processes() > 1 && force->can_split(system, neighbor);
+    split = overlap_halo && !observed && comm->num_processes() > 1 && force->can_split(system, neighbor);
     // the split force can take the integrator kick along like the single launch (Force::compute_with_nve)
     split_kick = split && fuse_next && fuse_nve && !input->comm_newton && integrator->step_factors(&nve_factors[0], &nve_factors[1]) &&
                  force->can_kick(system, neighbor);
@@ -215,6 +215,7 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next) {
     if (!kicked) {
       if (!force->zeroes_forces())
         emd_memset_zero(system->ctx, system->f, sizeof(T_F_FLOAT) * 3 * (size_t)system->N_max);
+      force->expect_energy(observed); // thermo follows this step (run / run_quiet): one pass over the pairs may serve both
       force->compute(system, binning, neighbor);
     }
   }
@@ -240,7 +241,7 @@ void ExaMiniMD::run_quiet(int nsteps, T_FLOAT *last_thermo3) {
   for (int s = 1; s <= nsteps; s++) {
     const int step = ++current_step;
     const bool observed = input->thermo_rate > 0 && step % input->thermo_rate == 0;
-    step_once(step, nullptr, s < nsteps && !observed);
+    step_once(step, nullptr, s < nsteps && !observed, observed);
     if (observed) {
       T_FLOAT T, PE, KE;
       thermo(&T, &PE, &KE);
@@ -259,7 +260,7 @@ void ExaMiniMD::run(int nsteps) {
     const int step = ++current_step;
     // thermo output, dumps and the correctness check read x, v, f between two steps: no fusion across them
     const bool observed = (input->thermo_rate > 0 && step % input->thermo_rate == 0) || input->dumpbinaryflag || input->correctnessflag;
-    step_once(step, &tm, s < nsteps && !observed);
+    step_once(step, &tm, s < nsteps && !observed, input->thermo_rate > 0 && step % input->thermo_rate == 0);
 
     if (input->thermo_rate > 0 && step % input->thermo_rate == 0) {
       T_FLOAT T, PE, KE;

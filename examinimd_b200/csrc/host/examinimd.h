@@ -53,7 +53,8 @@ public:
   // one timestep of the loop body of run() (examinimd.cpp:192-250), without output
   // fuse_next: the next step follows with nothing observing the state in between, so this step ends with
   // Integrator::final_initial_integrate() and the next one skips its initial_integrate()
-  void step_once(int step, PhaseTimers *timers, bool fuse_next = false);
+  // observed: thermo output follows this step (the force module may evaluate the energy in the same pass, Force::expect_energy)
+  void step_once(int step, PhaseTimers *timers, bool fuse_next = false, bool observed = false);
   bool initial_done = false; // the pending step's initial_integrate has already been applied
   // advance `nsteps` steps continuing the global step counter (rebuild cadence preserved)
   void advance(int nsteps);

@@ -13,6 +13,10 @@ public:
   virtual void init_coeff(int nargs, char **args) {}
   virtual void compute(System *system, Binning *binning, Neighbor *neigh) {}
   virtual T_F_FLOAT compute_energy(System *system, Binning *binning, Neighbor *neigh) { return 0.0; } // thermo only
+  // Optional (not in the reference): the driver announces that compute_energy() follows the next compute() on unchanged
+  // positions (a thermo step, src/examinimd.cpp:252-267); a module may then evaluate both in one pass over the pairs and
+  // answer compute_energy() from that pass.  The default ignores the hint.
+  virtual void expect_energy(bool) {}
   // true when compute() zeroes/overwrites f itself, so the driver may skip deep_copy(f,0)
   // (src/examinimd.cpp:232); a foreign Force plugin simply inherits `false`
   virtual bool zeroes_forces() const { return false; }

@@ -40,7 +40,11 @@ void ForceLJNeigh::compute(System *system, Binning *, Neighbor *neighbor) {
   if (t && !(half_neigh && comm_newton)) {
     if (comm_newton && system->N_ghost > 0) // ghost rows stay zero, as after the reference's deep_copy(f,0)
       emd_memset_zero(system->ctx, system->f + 3 * (size_t)system->N_local, sizeof(T_F_FLOAT) * 3 * (size_t)system->N_ghost);
-    if (emd_force_lj_compute_tiles(system->ctx, t, system->x, system->type, system->f, nullptr)) fail("compute (tiles)");
+    pe_cached = false;
+    if (want_energy) { // a thermo step: forces and energy in one pass over the pairs
+      if (emd_force_lj_compute_tiles_with_energy(system->ctx, t, system->x, system->type, system->f, &pe_cache)) fail("compute + energy (tiles)");
+      pe_cached = true;
+    } else if (emd_force_lj_compute_tiles(system->ctx, t, system->x, system->type, system->f, nullptr)) fail("compute (tiles)");
     return;
   }
   const emd_neigh_list l = neighbor->list_view();
@@ -55,6 +59,7 @@ bool ForceLJNeigh::compute_with_nve(System *system, Binning *, Neighbor *neighbo
   static const bool off = getenv("EMD_NO_FUSED_FORCE_NVE") && atoi(getenv("EMD_NO_FUSED_FORCE_NVE"));
   emd_tiles *t = neighbor->tiles();
   if (off || !t || comm_newton || !system->x_alt) return false;
+  pe_cached = false;
   const int rc = emd_force_lj_compute_tiles_nve(system->ctx, t, system->x, system->type, system->f, system->v, system->x_alt, system->mass,
                                                 dtf, dtv);
   if (rc == 3) return false; // an owned atom without a row: separate kernels
@@ -81,6 +86,7 @@ bool ForceLJNeigh::can_kick(System *system, Neighbor *neighbor) {
 void ForceLJNeigh::compute_part(System *system, Binning *, Neighbor *neighbor, int part, const T_V_FLOAT *nve) {
   static const int reserve = getenv("EMD_OVERLAP_RESERVE") ? atoi(getenv("EMD_OVERLAP_RESERVE")) : 0;
   // part 1 runs on the side stream's SM partition (ctx.cu); EMD_OVERLAP_RESERVE additionally leaves CTA slots free
+  pe_cached = false;
   if (nve) {
     if (emd_force_lj_compute_tiles_part_nve(system->ctx, neighbor->tiles(), system->x, system->type, system->f, part, part == 1 ? reserve : 0,
                                             system->v, system->x_alt, system->mass, nve[0], nve[1]))
@@ -96,6 +102,7 @@ void ForceLJNeigh::compute_part(System *system, Binning *, Neighbor *neighbor, i
 T_F_FLOAT ForceLJNeigh::compute_energy(System *system, Binning *, Neighbor *neighbor) {
   double pe = 0.0;
   emd_tiles *t = neighbor->tiles();
+  if (pe_cached) return pe_cache; // evaluated by the compute() of this step (expect_energy), positions unchanged since
   if (t && !(half_neigh && comm_newton)) {
     if (emd_force_lj_compute_tiles(system->ctx, t, system->x, system->type, system->f, &pe)) fail("energy (tiles)");
     return pe;

@@ -24,12 +24,15 @@ private:
   bool use_stackparams;
   std::vector<T_F_FLOAT> lj1, lj2, cutsq; // [ntypes][ntypes] host tables, pushed into the context
   System *sys;
+  bool want_energy = false, pe_cached = false; // expect_energy(): the next compute() also evaluates the energy
+  T_F_FLOAT pe_cache = 0.0;
 
 public:
   ForceLJNeigh(char **args, System *system, bool half_neigh_);
   void init_coeff(int nargs, char **args);
   void compute(System *system, Binning *binning, Neighbor *neighbor);
   T_F_FLOAT compute_energy(System *system, Binning *binning, Neighbor *neighbor);
+  void expect_energy(bool on) { want_energy = on; if (!on) pe_cached = false; }
   bool zeroes_forces() const { return true; }
   bool compute_with_nve(System *system, Binning *binning, Neighbor *neighbor, T_V_FLOAT dtf, T_V_FLOAT dtv);
   bool can_split(System *system, Neighbor *neighbor);

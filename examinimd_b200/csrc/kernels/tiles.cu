@@ -343,7 +343,7 @@ struct ListArgs {
 // lane is done after n columns.  In list order the 16 rows of a half-warp hit ~2.5 words per bank pair and the
 // shared-memory pipe, not FP64, bounds the force kernel (profiles/r01e); with these columns every bank pair is hit by the
 // two lanes l, l+16 except where a hole was filled (test_tiles_force_rows_are_a_conflict_light_permutation).
-constexpr int kExcessRoom = 40; // bank-sorted row + its excess entries (typically < 25)
+constexpr int kExcessRoom = 40; // excess entries of a row (typically < 25)
 
 template <bool EXACT>
 __global__ void __launch_bounds__(kRowThreads, 2) tiles_lists_kernel(TileArgs a, ListArgs e, unsigned coords_bytes, int rowcap) {
@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) tiles_lists_kernel(TileArgs a,
   // region A: FP64 coordinates + global indices while the exact rows are made, then the bank-sorted rows
   double *sx = reinterpret_cast<double *>(dyn);                 // [cap][3]
   int *sj = reinterpret_cast<int *>(dyn + (size_t)a.cap * 24);  // [cap]
-  unsigned short *srow = reinterpret_cast<unsigned short *>(dyn) + threadIdx.x;                  // srow[pos * kRowThreads]
+  unsigned char *srow = reinterpret_cast<unsigned char *>(dyn) + threadIdx.x;                    // srow[pos * kRowThreads]: slot >> 4 (the bucket is the bank)
+  unsigned short *sexc = reinterpret_cast<unsigned short *>(dyn + (size_t)a.maxrow * kRowThreads) + threadIdx.x; // sexc[k * kRowThreads]: excess entries (slots)
   unsigned short *state = reinterpret_cast<unsigned short *>(dyn + coords_bytes) + threadIdx.x;  // state[bank * kRowThreads]
   TileCtx t;
   tile_setup(a, t, s_start, s_goff, s_ibase);
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) tiles_lists_kernel(TileArgs a,
         if (c * 8 + k < n) {
           const unsigned slot = (w4[k >> 1] >> (16 * (k & 1))) & 0xffffu;
           const unsigned st = state[(slot & 15u) * kRowThreads];
-          srow[(st & 0xffu) * kRowThreads] = (unsigned short)slot;
+          srow[(st & 0xffu) * kRowThreads] = (unsigned char)(slot >> 4);
           state[(slot & 15u) * kRowThreads] = (unsigned short)(st + 1u);
         }
       }
@@ -491,18 +492,18 @@ __global__ void __launch_bounds__(kRowThreads, 2) tiles_lists_kernel(TileArgs a,
     const int fe = T - ((((b - hl) & 15) >= last) ? 1 : 0); // first round of this bank that has no column
     nexc += max(0, c - fe);
   }
-  const bool plain = n + nexc > rowcap; // (pathological rows: bank-sorted order as it is)
+  const bool plain = nexc > rowcap; // (pathological rows: bank-sorted order as it is)
   if (!plain && nexc > 0) {
-    int k = n;
+    int k = 0;
 #pragma unroll
     for (int b = 0; b < 16; b++) {
       const unsigned st = state[b * kRowThreads];
       const int S = st & 0xffu, c = st >> 8;
       const int fe = T - ((((b - hl) & 15) >= last) ? 1 : 0);
-      for (int tt = fe; tt < c; tt++) srow[(k++) * kRowThreads] = srow[(S + tt) * kRowThreads];
+      for (int tt = fe; tt < c; tt++) sexc[(k++) * kRowThreads] = (unsigned short)(((unsigned)srow[(S + tt) * kRowThreads] << 4) | (unsigned)b);
     }
   }
-  int cursor = n;
+  int cursor = 0, pb = 0; // next excess entry; plain rows: the bucket that holds position q
   const int c8 = (nmax + 7) & ~7;
   uint4 *dst = reinterpret_cast<uint4 *>(a.ell_s) + ((size_t)t.tile * (a.maxrow >> 3)) * a.stride + ts;
   for (int q0 = 0; q0 < c8; q0 += 8) {
@@ -513,13 +514,17 @@ __global__ void __launch_bounds__(kRowThreads, 2) tiles_lists_kernel(TileArgs a,
       const unsigned b = (unsigned)(q + hl) & 15u;
       unsigned ent = b * 24u; // padding: the dummy atom of this lane's bank in this column
       if (q < n) {
-        int idx = q;
+        unsigned slot;
         if (!plain) {
           const unsigned st = state[b * kRowThreads];
           const int tt = q >> 4;
-          idx = tt < (int)(st >> 8) ? (int)(st & 0xffu) + tt : cursor++;
+          if (tt < (int)(st >> 8)) slot = ((unsigned)srow[((st & 0xffu) + tt) * kRowThreads] << 4) | b;
+          else slot = sexc[(cursor++) * kRowThreads];
+        } else {
+          while (q >= (int)((state[pb * kRowThreads] & 0xffu) + (state[pb * kRowThreads] >> 8))) pb++;
+          slot = ((unsigned)srow[q * kRowThreads] << 4) | (unsigned)pb;
         }
-        ent = ((unsigned)srow[idx * kRowThreads] + kDummySlots) * 24u;
+        ent = (slot + kDummySlots) * 24u;
       }
       wv[k >> 1] |= ent << (16 * (k & 1));
     }
@@ -686,12 +691,12 @@ constexpr int kMaxBuf = 3;
 // bit-identical to the separate kernels): v is updated in place, the new position goes to a SECOND position array because
 // other CTAs still stage the old coordinates (the host swaps the two arrays after the launch).
 struct NveFuse { double *v; double *x_new; const double *mass; double dtf, dtv; };
-enum { MODE_FORCE = 0, MODE_ENERGY = 1, MODE_NVE = 2 };
+enum { MODE_FORCE = 0, MODE_ENERGY = 1, MODE_NVE = 2, MODE_FORCE_ENERGY = 3 };
 
 template <bool ONETYPE, int MODE>
 __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, int nbuf, LJOne one, const LJTab *__restrict__ tab,
                                                                    double *__restrict__ f, double *__restrict__ pe_partial, NveFuse nve) {
-  constexpr bool ENERGY = MODE == MODE_ENERGY;
+  constexpr bool ENERGY = MODE == MODE_ENERGY || MODE == MODE_FORCE_ENERGY;
   __shared__ double s_red[kForceWarps];
   __shared__ unsigned long long s_full[kMaxBuf], s_empty[kMaxBuf];
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -756,19 +761,28 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
       n_nxt = a.nell_s[rb];
     }
   };
+  // The row words (16 bytes = 8 entries per thread and step) are read once per step.  At this register budget ptxas places
+  // the load of word c+1 at the END of iteration c, next to its first use; an L1 prefetch two words ahead holds no register
+  // and makes that late load an L1 hit.  Measured alternatives (2 M atoms, profiles/README.md, round 2): a per-warp ring of
+  // 512-byte cp.async.bulk copies with one mbarrier per slot removes the long-scoreboard stalls (4.9 -> 1.6 warps per issue)
+  // but costs 30 % more instructions and the shared memory of the second CTA (depth 3: 0.42 ms; depth 2: 0.37 ms); a
+  // two-word register look-ahead 0.329 ms; this form 0.320 ms.
   auto row_of_tile = [&](int tl) { return reinterpret_cast<const uint4 *>(a.ell_s) + ((size_t)tl * (a.maxrow >> 3)) * a.stride + ts; };
   load_desc(0);
   double pe = 0.0;
   int b = 0;
   unsigned parity = 0u;
+  const double dtfm1 = (MODE == MODE_NVE && ONETYPE) ? nve.dtf / nve.mass[0] : 0.0; // integrator_nve.cpp:67,106 (one type: one mass)
   for (int k = 0; k < my_tiles; k++) {
     const int i_cur = i_nxt, own_cur = own_nxt, n_cur = n_nxt, tile = tile_nxt;
     const bool has_row = i_cur < a.n_local;
-    const uint4 *row = row_of_tile(tile);
     const int nchunk = n_cur >> 3;
+    const uint4 *row = row_of_tile(tile);
+    const size_t rstep = (size_t)a.stride;
     uint4 cur = make_uint4(0, 0, 0, 0);
     if (has_row && nchunk > 0) cur = ldg_nc_v4(row); // in flight while the warp waits for the coordinates
-    if (has_row && nchunk > 1) prefetch_l1(row + a.stride);
+    if (has_row && nchunk > 1) prefetch_l1(row + rstep);
+    load_desc(k + 1);
     if (MODE == MODE_NVE && has_row) { prefetch_l1(nve.v + 3 * (size_t)i_cur); prefetch_l1(nve.v + 3 * (size_t)i_cur + 2); } // the epilogue's v
     if (producer) {
       // buffer (k + nbuf - 1) mod nbuf held tile k - 1
@@ -778,17 +792,15 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
       }
       produce(k + nbuf - 1);
     }
-    load_desc(k + 1);
     mbar_wait(&s_full[b], parity);
     const unsigned char *spb = dyn + (size_t)b * buf_bytes;
     const int *st = st0 + (size_t)b * tstride;
+    const double *me = reinterpret_cast<const double *>(spb) + 3 * (own_cur + kDummySlots);
+    const double x_i = me[0], y_i = me[1], z_i = me[2];
+    const int type_i = ONETYPE ? 0 : st[own_cur + kDummySlots];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    // one 16-byte word = 8 columns of the warp's schedule (n_cur is the same multiple of 8 in every lane of the warp)
     if (has_row) {
-      const double *me = reinterpret_cast<const double *>(spb) + 3 * (own_cur + kDummySlots);
-      const double x_i = me[0], y_i = me[1], z_i = me[2];
-      const int type_i = ONETYPE ? 0 : st[own_cur + kDummySlots];
-      double fx = 0.0, fy = 0.0, fz = 0.0;
-      // one 16-byte word = 8 columns of the warp's schedule (n_cur is the same multiple of 8 in every lane of the warp)
-      const size_t rstep = (size_t)a.stride;
       for (int c = 0; c < nchunk; c++, row += rstep) {
         if (c + 2 < nchunk) prefetch_l1(row + 2 * rstep);
         uint4 nxt = make_uint4(0, 0, 0, 0);
@@ -797,9 +809,11 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
         lj_quad<ONETYPE, ENERGY>(spb, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
         cur = nxt;
       }
-      if (!ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
+    }
+    if (has_row) {
+      if (MODE != MODE_ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
       if (MODE == MODE_NVE) {
-        const double dtfm = nve.dtf / nve.mass[ONETYPE ? a.type[i_cur] : type_i]; // integrator_nve.cpp:67,106
+        const double dtfm = ONETYPE ? dtfm1 : nve.dtf / nve.mass[type_i];
         double *vp = nve.v + 3 * (size_t)i_cur, *xp = nve.x_new + 3 * (size_t)i_cur;
         const double fi[3] = {fx, fy, fz}, xi[3] = {x_i, y_i, z_i};
 #pragma unroll
@@ -831,7 +845,7 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
 }
 
 size_t lists_coords_bytes(int cap, int maxrow) { // region A of tiles_lists_kernel
-  const size_t coords = (size_t)cap * 28, rows = (size_t)(maxrow + kExcessRoom) * kRowThreads * sizeof(unsigned short);
+  const size_t coords = (size_t)cap * 28, rows = (size_t)maxrow * kRowThreads + (size_t)kExcessRoom * kRowThreads * sizeof(unsigned short);
   return (std::max(coords, rows) + 15) / 16 * 16;
 }
 size_t lists_smem(int cap, int maxrow) { return lists_coords_bytes(cap, maxrow) + (size_t)16 * kRowThreads * sizeof(unsigned short); }
@@ -930,8 +944,8 @@ int launch_lists(emd_ctx *ctx, emd_tiles *t, bool exact, int half, int newton, i
   e.cutsq = t->neigh_cut * t->neigh_cut; e.half = half; e.newton = newton; e.counts = d_counts;
   const size_t cb = lists_coords_bytes(a.cap, a.maxrow), smem = lists_smem(a.cap, a.maxrow);
   if (smem > (size_t)t->max_smem_optin) return 3;
-  if (exact) { if (set_smem(tiles_lists_kernel<true>, smem)) return 1; EMD_LAUNCH(ctx, tiles_lists_kernel<true>, t->ntiles, kRowThreads, smem, a, e, (unsigned)cb, a.maxrow + kExcessRoom); }
-  else { if (set_smem(tiles_lists_kernel<false>, smem)) return 1; EMD_LAUNCH(ctx, tiles_lists_kernel<false>, t->ntiles, kRowThreads, smem, a, e, (unsigned)cb, a.maxrow + kExcessRoom); }
+  if (exact) { if (set_smem(tiles_lists_kernel<true>, smem)) return 1; EMD_LAUNCH(ctx, tiles_lists_kernel<true>, t->ntiles, kRowThreads, smem, a, e, (unsigned)cb, kExcessRoom); }
+  else { if (set_smem(tiles_lists_kernel<false>, smem)) return 1; EMD_LAUNCH(ctx, tiles_lists_kernel<false>, t->ntiles, kRowThreads, smem, a, e, (unsigned)cb, kExcessRoom); }
   t->rows_ready = true;
   if (exact) t->exact_key = (half ? 1 : 0) | (newton ? 2 : 0);
   return 0;
@@ -1163,7 +1177,7 @@ int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half, int newton, in
 // this step has landed); 2 = the rest.  reserve_ctas > 0 leaves that many CTA slots of the persistent grid free, so that
 // the pack and transport kernels of a concurrent halo exchange find room on the SMs.
 static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe, int part,
-                           int reserve_ctas, const NveFuse *fuse = nullptr) {
+                           int reserve_ctas, const NveFuse *fuse = nullptr, bool force_too = false) {
   if (!t || !t->valid) { set_error("emd_force_lj_compute_tiles: tiles not built"); return 1; }
   if (ctx->lj.ntypes == 0) { set_error("emd_force_lj_compute_tiles: parameters not set"); return 1; }
   if (part < 0 || part > 2 || (h_pe && part != 0)) { set_error("emd_force_lj_compute_tiles: bad part"); return 1; }
@@ -1174,7 +1188,7 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
   }
   // an owned atom outside the interior bins has no row (the reference leaves it without neighbors, neighbor_csr.h:184):
   // its force is the zero of the reference's deep_copy(f, 0)
-  if (!t->all_owned_have_rows && !h_pe && part == 0) EMD_CUDA(cudaMemsetAsync(d_f, 0, sizeof(double) * 3 * (size_t)t->a.n_local, ctx->stream));
+  if (!t->all_owned_have_rows && (!h_pe || force_too) && part == 0) EMD_CUDA(cudaMemsetAsync(d_f, 0, sizeof(double) * 3 * (size_t)t->a.n_local, ctx->stream));
   const NveFuse nve = fuse ? *fuse : NveFuse{nullptr, nullptr, nullptr, 0.0, 0.0};
   TileArgs a = t->a;
   a.x = d_x; a.type = d_type;
@@ -1210,6 +1224,7 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
     EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, MD>), grid, kForceThreads, smem, a, first, count, nbuf, p1, t->d_tab, d_f, partial, nve); \
   } while (0)
   if (fuse) { if (one) EMD_LJ_TILES(true, MODE_NVE); else EMD_LJ_TILES(false, MODE_NVE); }
+  else if (h_pe && force_too) { if (one) EMD_LJ_TILES(true, MODE_FORCE_ENERGY); else EMD_LJ_TILES(false, MODE_FORCE_ENERGY); }
   else if (h_pe) { if (one) EMD_LJ_TILES(true, MODE_ENERGY); else EMD_LJ_TILES(false, MODE_ENERGY); }
   else { if (one) EMD_LJ_TILES(true, MODE_FORCE); else EMD_LJ_TILES(false, MODE_FORCE); }
 #undef EMD_LJ_TILES
@@ -1221,6 +1236,11 @@ extern "C" {
 
 int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe) {
   return lj_tiles_launch(ctx, t, d_x, d_type, d_f, h_pe, 0, 0);
+}
+
+int emd_force_lj_compute_tiles_with_energy(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe) {
+  if (!h_pe) { set_error("emd_force_lj_compute_tiles_with_energy: h_pe == NULL"); return 1; }
+  return lj_tiles_launch(ctx, t, d_x, d_type, d_f, h_pe, 0, 0, nullptr, true);
 }
 
 int emd_force_lj_compute_tiles_part(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, int part,

@@ -192,6 +192,10 @@ int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half_neigh, int comm
  * Valid for full lists and for half lists with newton off (same forces on owned atoms). */
 int emd_force_lj_compute_tiles(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type,
                                double *d_f, double *h_pe);
+/* ::compute and ::compute_energy in ONE pass over the pairs (the driver asks for it on the steps whose thermo output follows:
+ * src/examinimd.cpp:232-235 then :252-267 evaluate the same pairs twice): d_f as by compute, *h_pe as by compute_energy. */
+int emd_force_lj_compute_tiles_with_energy(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type,
+                                           double *d_f, double *h_pe);
 /* The same force in two launches, for a decomposed run (CommMPI): part 1 = the tiles whose staged cells hold only owned
  * atoms (no dependence on this step's halo exchange, src/comm_types/comm_mpi.cpp:382-423), part 2 = the tiles that read
  * ghosts; part 0 = all.  The two parts write disjoint rows of d_f.  reserve_ctas leaves CTA slots of the persistent grid
