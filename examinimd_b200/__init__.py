@@ -153,6 +153,17 @@ _SIGS = {
     "emd_net_allreduce": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "emd_net_scan_int": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "emd_net_barrier": (C.c_int, [_P]),
+    "emd_net_allgather_bytes": (C.c_int, [_P, _P, C.c_int, _P]),
+    "emd_peer_create": (C.c_int, [C.POINTER(_P), _P, _P, C.c_int, C.c_int]),
+    "emd_peer_destroy": (None, [_P]),
+    "emd_peer_publish": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int)]),
+    "emd_peer_ready": (C.c_int, [_P]),
+    "emd_peer_begin_update": (C.c_int, [_P, _P, _P]),
+    "emd_peer_update_dim": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int]),
+    "emd_peer_wait_all": (C.c_int, [_P]),
+    "emd_ctx_set_halo_gate": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "emd_ctx_halo_gate_wait": (C.c_int, [_P]),
+    "emd_ctx_halo_gate_pending": (C.c_int, [_P]),
     "emd_reduce_mv2": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(C.c_double)]),
     # session API (include/emd_b200_app.h)
     "emd_app_create": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(C.c_char_p), C.c_int, _P]),

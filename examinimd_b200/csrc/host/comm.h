@@ -16,6 +16,9 @@ public:
   virtual void exchange() {}       // move atoms that left the sub-domain / wrap periodic images
   virtual void exchange_halo() {}  // (re)create ghost atoms
   virtual void update_halo() {}    // refresh ghost positions
+  // Optional (not in the reference): the same refresh, but the stream is not made to wait for the neighbours' data; the
+  // consumer named by Force::gates_halo waits itself.  false: not available, nothing was done (call update_halo()).
+  virtual bool update_halo_deferred() { return false; }
   virtual void update_force() {}   // reverse: fold ghost forces back (newton on)
   virtual void reduce_float(T_FLOAT *values, T_INT N) {}
   virtual void reduce_int(T_INT *values, T_INT N) {}

@@ -5,7 +5,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static double g_t_exchange = 0.0, g_t_halo = 0.0, g_t_publish = 0.0;
+static int g_n_rebuild = 0, g_n_calls = 0;
 static const size_t kParticleBytes = 72; // sizeof(Particle), src/system.h:43-55
 
 static int env_int(const char *a, const char *b, const char *c, int dflt) {
@@ -16,17 +20,26 @@ static int env_int(const char *a, const char *b, const char *c, int dflt) {
   return dflt;
 }
 
-CommMPI::CommMPI(System *s, T_X_FLOAT comm_depth_) : Comm(s, comm_depth_), net(nullptr) {
+CommMPI::CommMPI(System *s, T_X_FLOAT comm_depth_) : Comm(s, comm_depth_), net(nullptr), peer(nullptr) {
   proc_rank = env_int("RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", 0);
   proc_size = env_int("WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", 1);
   if (proc_size < 1) proc_size = 1;
   memset(&dec, 0, sizeof dec);
   for (int p = 0; p < 6; p++) proc_num_send[p] = proc_num_recv[p] = num_ghost[p] = ghost_offsets[p] = 0;
   if (proc_size > 1 && emd_net_create(&net, system->ctx, proc_size, proc_rank, nullptr)) fail("emd_net_create");
+  // EMD_HALO_TRANSPORT=nccl keeps the send/recv groups for the per-step refresh (measurement switch); default: peer stores
+  const char *tr = getenv("EMD_HALO_TRANSPORT");
+  if (net && !(tr && !strcmp(tr, "nccl")) && emd_peer_create(&peer, net, system->ctx, proc_size, proc_rank)) fail("emd_peer_create");
   system->do_print = system->do_print && proc_rank == 0; // src/system.cpp:61-67: only rank 0 prints
 }
 
-CommMPI::~CommMPI() { if (net) emd_net_destroy(net); }
+CommMPI::~CommMPI() {
+  if (getenv("EMD_PEER_DEBUG") && g_n_rebuild)
+    fprintf(stderr, "CommMPI[rank %d]: per re-neighboring (host wall, synchronised): exchange %.0f us, exchange_halo %.0f us, peer publish %.0f us (%d)\n", proc_rank,
+            1e6 * g_t_exchange / g_n_rebuild, 1e6 * g_t_halo / g_n_rebuild, 1e6 * g_t_publish / g_n_rebuild, g_n_rebuild);
+  if (peer) emd_peer_destroy(peer);
+  if (net) emd_net_destroy(net);
+}
 
 void CommMPI::init() {}
 
@@ -52,6 +65,9 @@ void CommMPI::create_domain_decomposition() {
 // src/comm_types/comm_mpi.cpp:193-289
 void CommMPI::exchange() {
   emd_ctx *ctx = system->ctx;
+  static const bool dbg = getenv("EMD_PEER_DEBUG") != nullptr;
+  double t0 = 0.0;
+  if (dbg) { emd_ctx_sync(ctx); t0 = now_s(); }
   const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
   T_INT N_local = system->N_local, N_ghost = 0;
   const int wrap[3] = {dec.grid[0] == 1, dec.grid[1] == 1, dec.grid[2] == 1};
@@ -89,11 +105,15 @@ void CommMPI::exchange() {
     fail("compact");
   system->N_local = N_local;
   system->N_ghost = 0;
+  if (dbg) { emd_ctx_sync(ctx); if (g_n_calls++ >= 5) g_t_exchange += now_s() - t0; }
 }
 
 // src/comm_types/comm_mpi.cpp:291-380
 void CommMPI::exchange_halo() {
   emd_ctx *ctx = system->ctx;
+  static const bool dbg = getenv("EMD_PEER_DEBUG") != nullptr;
+  double t0 = 0.0, t1 = 0.0;
+  if (dbg) { emd_ctx_sync(ctx); t0 = now_s(); }
   const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
   const T_INT N_local = system->N_local;
   T_INT N_ghost = 0;
@@ -150,20 +170,60 @@ void CommMPI::exchange_halo() {
     most = std::max(most, (size_t)std::max(proc_num_send[2 * d] + proc_num_send[2 * d + 1], proc_num_recv[2 * d] + proc_num_recv[2 * d + 1]));
   ensure_bytes(pack_buffer, most * kParticleBytes);
   ensure_bytes(unpack_buffer, most * kParticleBytes);
+  // leading dimensions without decomposition: one resolved refresh kernel instead of two phase kernels per dimension
+  local_dims = 0;
+  while (local_dims < 3 && !decomposed(2 * local_dims)) local_dims++;
+  local_ghosts = 0;
+  for (int phase = 0; phase < 2 * local_dims; phase++) local_ghosts += proc_num_recv[phase];
+  if (local_dims > 0 && local_ghosts > 0) {
+    if (local_root.extent() < (size_t)local_ghosts) {
+      if (!local_root.alloc((size_t)local_ghosts + local_ghosts / 8) || !local_shift.alloc(3 * ((size_t)local_ghosts + local_ghosts / 8))) fail("alloc local roots");
+    }
+    const int *lists[6];
+    int counts[6];
+    for (int p = 0; p < 6; p++) { lists[p] = pack_indicies[p].ptr; counts[p] = p < 2 * local_dims ? proc_num_send[p] : 0; }
+    if (emd_comm_halo_resolve(ctx, lists, counts, N_local, L, local_root.ptr, local_shift.ptr)) fail("halo_resolve");
+  }
+  if (dbg) { emd_ctx_sync(ctx); t1 = now_s(); if (g_n_calls > 5) { g_t_halo += t1 - t0; g_n_rebuild++; } }
+  if (peer) { // the neighbours learn where my ghost rows of each phase start (and my position arrays, if they were reallocated)
+    int ghost_begin[6];
+    T_INT g = 0;
+    for (int phase = 0; phase < 6; phase++) { ghost_begin[phase] = system->N_local + g; g += proc_num_recv[phase]; }
+    if (!system->x_alt) { emd_peer_destroy(peer); peer = nullptr; }
+    else if (emd_peer_publish(peer, &dec, system->x, system->x_alt, ghost_begin)) fail("peer publish");
+  }
+  if (dbg) { emd_ctx_sync(ctx); if (g_n_calls > 5) g_t_publish += now_s() - t1; }
 }
 
 // src/comm_types/comm_mpi.cpp:382-423: no host synchronisation anywhere in here.  The two phases of a dimension do not
 // depend on each other (phase 2d+1 never replays ghosts received in phase 2d, :306), so a decomposed dimension packs
 // both directions, ships them as ONE NCCL group and unpacks both: three exchanges per step instead of six.
-void CommMPI::update_halo() {
+void CommMPI::update_halo() { refresh(false); }
+
+// the peer-store refresh without the wait for the neighbours' stores (the force kernel named by Force::gates_halo waits)
+bool CommMPI::update_halo_deferred() {
+  if (!(peer && emd_peer_ready(peer))) return false;
+  refresh(true);
+  return true;
+}
+
+void CommMPI::refresh(bool defer) {
   emd_ctx *ctx = system->ctx;
   const double L[3] = {system->domain_x, system->domain_y, system->domain_z};
   T_INT ghost_begin[6];
   T_INT N_ghost = 0;
   for (int phase = 0; phase < 6; phase++) { ghost_begin[phase] = system->N_local + N_ghost; N_ghost += proc_num_recv[phase]; }
-  for (int dim = 0; dim < 3; dim++) {
+  const bool by_peer = peer && emd_peer_ready(peer);
+  if (by_peer && emd_peer_begin_update(peer, &dec, system->x)) fail("peer begin_update");
+  if (local_dims > 0 && local_ghosts > 0 && emd_comm_halo_refresh(ctx, system->x, system->N_local, local_ghosts, local_root.ptr, local_shift.ptr))
+    fail("halo_refresh");
+  for (int dim = local_dims; dim < 3; dim++) {
     const int pa = 2 * dim, pb = 2 * dim + 1;
-    if (decomposed(pa)) {
+    if (decomposed(pa) && by_peer) {
+      // the pack kernel stores into the neighbours' ghost rows; the stream then waits for their stores into mine
+      if (emd_peer_update_dim(peer, &dec, L, dim, system->x, pack_indicies[pa].ptr, proc_num_send[pa], pack_indicies[pb].ptr, proc_num_send[pb], defer ? 1 : 0))
+        fail("peer update_dim");
+    } else if (decomposed(pa)) {
       double *send_a = (double *)pack_buffer.ptr, *send_b = send_a + 3 * (size_t)proc_num_send[pa];
       // a refresh message is exactly the ghost rows of x (3 doubles per ghost, in ghost order): receive in place, no unpack
       double *recv_a = system->x + 3 * (size_t)ghost_begin[pa], *recv_b = system->x + 3 * (size_t)ghost_begin[pb];
@@ -176,6 +236,7 @@ void CommMPI::update_halo() {
           emd_net_group_end(net))
         fail("sendrecv");
     } else {
+      if (by_peer && emd_peer_wait_all(peer)) fail("peer wait"); // this dimension forwards the ghosts of the earlier ones
       for (int phase = pa; phase <= pb; phase++)
         if (emd_comm_halo_update_phase(ctx, phase, system->x, system->v, system->q, system->id, system->type, pack_indicies[phase].ptr,
                                        proc_num_send[phase], ghost_begin[phase], L))

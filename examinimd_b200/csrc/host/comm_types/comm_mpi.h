@@ -18,16 +18,24 @@
 
 class CommMPI : public Comm {
   emd_net *net;
+  emd_peer *peer; // per-step halo refresh by peer stores over NVLink (kernels/comm_peer.cu); nullptr: NCCL send/recv
   emd_decomp dec;
   int proc_rank, proc_size;
   T_INT proc_num_send[6], proc_num_recv[6]; // atoms shipped / received per phase by the last exchange_halo
   T_INT num_ghost[6], ghost_offsets[6];
   DeviceArray<T_INT> pack_indicies[6];      // pack_indicies_all(phase, :)
   DeviceArray<char> pack_buffer, unpack_buffer;
+  // the leading dimensions that are not decomposed: every ghost of theirs resolved to its owned root atom + total periodic
+  // shift once per ghost build, so that their refresh is one kernel (as in CommSerial)
+  DeviceArray<T_INT> local_root;
+  DeviceArray<T_X_FLOAT> local_shift;
+  int local_dims = 0;       // dims [0, local_dims) are handled by that kernel
+  T_INT local_ghosts = 0;
 
   bool decomposed(int phase) const { return dec.grid[phase / 2] > 1; }
   void ensure_bytes(DeviceArray<char> &b, size_t bytes);
   void fail(const char *what);
+  void refresh(bool defer);
 
 public:
   CommMPI(System *s, T_X_FLOAT comm_depth_);
@@ -37,6 +45,7 @@ public:
   void exchange();
   void exchange_halo();
   void update_halo();
+  bool update_halo_deferred();
   void update_force();
   void reduce_float(T_FLOAT *values, T_INT N);
   void reduce_int(T_INT *values, T_INT N);

@@ -183,7 +183,10 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next, bool observ
   } else {
     // decomposed run: the share of the force that reads no ghost atom starts now, on the side stream, and overlaps the
     // halo exchange (the reference's blocking sequence update_halo -> compute, examinimd.cpp:226-235, otherwise)
-    split = overlap_halo && !observed && comm->num_processes() > 1 && force->can_split(system, neighbor);
+    // peer-store transport + a force kernel that waits for the ghosts itself: nothing to overlap by hand, the refresh costs
+    // its pack kernels and the neighbours' stores land while the ghost-free tiles are computed
+    const bool gated = comm->num_processes() > 1 && force->gates_halo(system, neighbor) && comm->update_halo_deferred();
+    split = !gated && overlap_halo && !observed && comm->num_processes() > 1 && force->can_split(system, neighbor);
     // the split force can take the integrator kick along like the single launch (Force::compute_with_nve)
     split_kick = split && fuse_next && fuse_nve && !input->comm_newton && integrator->step_factors(&nve_factors[0], &nve_factors[1]) &&
                  force->can_kick(system, neighbor);
@@ -194,7 +197,7 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next, bool observ
       force->compute_part(system, binning, neighbor, 1, split_kick ? nve_factors : nullptr);
       if (emd_ctx_side_end(system->ctx)) comm->error(emd_last_error());
     }
-    comm->update_halo();
+    if (!gated) comm->update_halo();
     if (split && comm_first) {
       if (emd_ctx_side_begin(system->ctx)) comm->error(emd_last_error());
       force->compute_part(system, binning, neighbor, 1, split_kick ? nve_factors : nullptr);

@@ -32,6 +32,10 @@ public:
   // can_kick() said so); part 2 then publishes the new positions
   virtual void compute_part(System *system, Binning *binning, Neighbor *neigh, int part, const T_V_FLOAT *nve = nullptr) {}
   virtual bool can_kick(System *system, Neighbor *neigh) { return false; }
+  // Optional: the next compute() / compute_with_nve() waits for the neighbours' ghost stores of this step itself (only before
+  // the first pair that reads a ghost), so the driver may ask the Comm module for a refresh that does not block the stream
+  // (Comm::update_halo_deferred).  A module that inherits `false` always sees a completed Comm::update_halo().
+  virtual bool gates_halo(System *system, Neighbor *neigh) { return false; }
   virtual const char *name() { return "ForceNone"; }
 };
 

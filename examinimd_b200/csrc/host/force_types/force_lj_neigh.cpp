@@ -47,6 +47,7 @@ void ForceLJNeigh::compute(System *system, Binning *, Neighbor *neighbor) {
     } else if (emd_force_lj_compute_tiles(system->ctx, t, system->x, system->type, system->f, nullptr)) fail("compute (tiles)");
     return;
   }
+  emd_ctx_halo_gate_wait(system->ctx);
   const emd_neigh_list l = neighbor->list_view();
   if (emd_force_lj_compute(system->ctx, system->x, system->type, system->f, system->N_local,
                            system->N_local + system->N_ghost, &l, half_neigh, /*zero_f=*/1))
@@ -83,6 +84,14 @@ bool ForceLJNeigh::can_kick(System *system, Neighbor *neighbor) {
   return !off && t && !comm_newton && system->x_alt && !emd_tiles_complete(t, &lists_complete) && lists_complete;
 }
 
+// the tile kernel waits for the ghosts itself (tiles.cu: halo gate); the generic kernels below wait on the stream first
+bool ForceLJNeigh::gates_halo(System *, Neighbor *neighbor) {
+  // Measured on 2 and 8 B200s (profiles/r02_halo_transport.md): the split launch on the side stream still hides more (the
+  // re-neighboring steps' exchanges dominate what is left), so the gate is opt-in.
+  static const bool on = getenv("EMD_HALO_GATE") && atoi(getenv("EMD_HALO_GATE"));
+  return on && neighbor->tiles() && !(half_neigh && comm_newton);
+}
+
 void ForceLJNeigh::compute_part(System *system, Binning *, Neighbor *neighbor, int part, const T_V_FLOAT *nve) {
   static const int reserve = getenv("EMD_OVERLAP_RESERVE") ? atoi(getenv("EMD_OVERLAP_RESERVE")) : 0;
   // part 1 runs on the side stream's SM partition (ctx.cu); EMD_OVERLAP_RESERVE additionally leaves CTA slots free
@@ -103,6 +112,7 @@ T_F_FLOAT ForceLJNeigh::compute_energy(System *system, Binning *, Neighbor *neig
   double pe = 0.0;
   emd_tiles *t = neighbor->tiles();
   if (pe_cached) return pe_cache; // evaluated by the compute() of this step (expect_energy), positions unchanged since
+  emd_ctx_halo_gate_wait(system->ctx);
   if (t && !(half_neigh && comm_newton)) {
     if (emd_force_lj_compute_tiles(system->ctx, t, system->x, system->type, system->f, &pe)) fail("energy (tiles)");
     return pe;

@@ -38,6 +38,7 @@ public:
   bool can_split(System *system, Neighbor *neighbor);
   void compute_part(System *system, Binning *binning, Neighbor *neighbor, int part, const T_V_FLOAT *nve = nullptr);
   bool can_kick(System *system, Neighbor *neighbor);
+  bool gates_halo(System *system, Neighbor *neighbor);
   const char *name();
 };
 #endif

@@ -259,6 +259,7 @@ struct emd_net {
   int nranks = 1, rank = 0;
   int *d_small = nullptr; // 64 ints / 32 doubles of device staging for counts and scalar reductions
   bool in_group = false;  // between emd_net_group_begin / _end: message pairs join one NCCL group
+  char *d_gather = nullptr; size_t gather_cap = 0; // emd_net_allgather_bytes staging
 };
 
 extern "C" {
@@ -422,6 +423,7 @@ void emd_net_destroy(emd_net *n) {
   if (!n) return;
   if (n->comm) g_nccl.CommDestroy(n->comm);
   if (n->d_small) cudaFree(n->d_small);
+  if (n->d_gather) cudaFree(n->d_gather);
   delete n;
 }
 
@@ -504,6 +506,25 @@ int emd_net_scan_int(emd_net *n, int *h_value) {
   int s = 0;
   for (int r = 0; r <= n->rank; r++) s += stage[r];
   *h_value = s;
+  return 0;
+}
+
+// MPI_Allgather of a small record per rank (host memory in, host memory out); synchronises
+int emd_net_allgather_bytes(emd_net *n, const void *h_in, int nbytes, void *h_out_all) {
+  if (!n || nbytes <= 0 || (nbytes & 3)) { set_error("emd_net_allgather_bytes: bad arguments"); return 1; }
+  emd_ctx *c = n->ctx;
+  const size_t need = (size_t)nbytes * ((size_t)n->nranks + 1);
+  if (need > n->gather_cap) {
+    if (n->d_gather) cudaFree(n->d_gather);
+    n->d_gather = nullptr; n->gather_cap = 0;
+    EMD_CUDA(cudaMalloc((void **)&n->d_gather, need));
+    n->gather_cap = need;
+  }
+  char *dsend = n->d_gather, *dall = n->d_gather + nbytes;
+  EMD_CUDA(cudaMemcpyAsync(dsend, h_in, (size_t)nbytes, cudaMemcpyHostToDevice, c->stream));
+  EMD_NCCL(g_nccl.AllGather(dsend, dall, (size_t)nbytes, ncclChar, n->comm, c->stream));
+  EMD_CUDA(cudaMemcpyAsync(h_out_all, dall, (size_t)nbytes * (size_t)n->nranks, cudaMemcpyDeviceToHost, c->stream));
+  EMD_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -64,6 +64,12 @@ struct emd_ctx {
   // LJ parameters
   emd::LJParams lj;
   unsigned long long lj_version = 0; // bumped by emd_force_lj_set_params (device copies of the table are uploaded once per version)
+  // Halo gate (comm_peer.cu): the neighbours' stores into my ghost rows are announced by sequence flags; a kernel that can
+  // wait for them itself (the LJ tile force: only before its first tile that reads a ghost) takes the gate along, every
+  // other consumer calls emd_ctx_halo_gate_wait first.
+  const int *gate_flags = nullptr; // [6] arrived flags, by phase
+  int gate_seq = 0, gate_mask = 0; // wanted sequence number; phases that count
+  bool gate_pending = false;
   double *d_lj_tables = nullptr; // for ntypes > 12: [3][ntypes][ntypes]
   int lj_tables_ntypes = 0;
 };

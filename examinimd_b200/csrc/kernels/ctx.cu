@@ -201,6 +201,28 @@ void emd_ctx_destroy(emd_ctx *c) {
 
 void *emd_ctx_stream(emd_ctx *c) { return (void *)c->stream; }
 int emd_ctx_sync(emd_ctx *c) { EMD_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+
+namespace {
+__global__ void halo_gate_wait_kernel(const int *flags, int seq, int mask) {
+  const int p = threadIdx.x;
+  if (p < 6 && ((mask >> p) & 1)) {
+    int v;
+    do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory"); if (v < seq) __nanosleep(200); } while (v < seq);
+  }
+  __threadfence_system();
+}
+} // namespace
+int emd_ctx_set_halo_gate(emd_ctx *c, const int *d_arrived6, int seq, int phase_mask) {
+  c->gate_flags = d_arrived6; c->gate_seq = seq; c->gate_mask = phase_mask; c->gate_pending = d_arrived6 && phase_mask;
+  return 0;
+}
+int emd_ctx_halo_gate_wait(emd_ctx *c) {
+  if (!c->gate_pending) return 0;
+  c->gate_pending = false;
+  EMD_LAUNCH(c, halo_gate_wait_kernel, 1, 32, 0, c->gate_flags, c->gate_seq, c->gate_mask);
+  return 0;
+}
+int emd_ctx_halo_gate_pending(const emd_ctx *c) { return c->gate_pending ? 1 : 0; }
 unsigned long long emd_ctx_launch_count(emd_ctx *c) { return c->launches; }
 // The side stream lives in a GREEN CONTEXT that owns all but a few SMs (driver API, CUDA >= 12.4, resolved at run time so the
 // library has no link-time dependency on libcuda): the persistent force kernel launched on it fills ITS SMs, and the pack and

@@ -693,9 +693,11 @@ constexpr int kMaxBuf = 3;
 struct NveFuse { double *v; double *x_new; const double *mass; double dtf, dtv; };
 enum { MODE_FORCE = 0, MODE_ENERGY = 1, MODE_NVE = 2, MODE_FORCE_ENERGY = 3 };
 
+struct HaloGate { const int *flags; int seq, mask; }; // common.cuh: the neighbours' ghost stores of this step (comm_peer.cu)
+
 template <bool ONETYPE, int MODE>
 __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, int nbuf, LJOne one, const LJTab *__restrict__ tab,
-                                                                   double *__restrict__ f, double *__restrict__ pe_partial, NveFuse nve) {
+                                                                   double *__restrict__ f, double *__restrict__ pe_partial, NveFuse nve, HaloGate gate) {
   constexpr bool ENERGY = MODE == MODE_ENERGY || MODE == MODE_FORCE_ENERGY;
   __shared__ double s_red[kForceWarps];
   __shared__ unsigned long long s_full[kMaxBuf], s_empty[kMaxBuf];
@@ -720,10 +722,22 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
   const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + G - 1) / G : 0;
   auto tile_of = [&](int k) { return a.order[first + blockIdx.x + k * G]; };
   // producer: copies of the CTA's kk-th tile (the caller has made sure that its buffer is free)
+  bool halo_ok = gate.mask == 0; // producer warp: the ghost rows of this step have landed
   auto produce = [&](int kk) {
     const int b = kk % nbuf;
     if (kk < my_tiles) {
       const int tl = tile_of(kk);
+      if (!halo_ok && a.has_ghost[tl]) {
+        // The tiles that read no ghost come first in a.order, so the neighbours' stores (issued before this launch began) have
+        // normally landed long before the first tile that needs them: the wait costs one flag read per phase, once per CTA.
+        if (lane < 6 && ((gate.mask >> lane) & 1)) {
+          int v;
+          do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(gate.flags + lane) : "memory"); if (v < gate.seq) __nanosleep(100); } while (v < gate.seq);
+        }
+        __threadfence_system();
+        __syncwarp();
+        halo_ok = true;
+      }
       const int n = a.stg_n[tl];
       const int *__restrict__ src = a.stg_j + (size_t)tl * a.cap;
       double *dstb = reinterpret_cast<double *>(dyn + (size_t)b * buf_bytes) + 3 * kDummySlots;
@@ -1209,6 +1223,10 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
   if (2 * (force_smem(a.fcap, !one, 3) + 1024) > (size_t)t->max_smem_sm) nbuf = 2;
   const size_t smem = force_smem(a.fcap, !one, nbuf);
   if (smem > (size_t)t->max_smem_optin) { set_error("emd_force_lj_compute_tiles: tile does not fit in shared memory"); return 1; }
+  // a pending halo gate travels with the single launch; part 1 reads no ghost; part 2 has to wait on the stream first
+  HaloGate gate = {nullptr, 0, 0};
+  if (ctx->gate_pending && part == 0) { gate.flags = ctx->gate_flags; gate.seq = ctx->gate_seq; gate.mask = ctx->gate_mask; ctx->gate_pending = false; }
+  else if (ctx->gate_pending && part == 2) { if (emd_ctx_halo_gate_wait(ctx)) return 1; }
   const int first = part == 2 ? t->n_free_tiles : 0;
   const int count = part == 0 ? t->ntiles : part == 1 ? t->n_free_tiles : t->ntiles - t->n_free_tiles;
   if (count <= 0) return 0;
@@ -1221,7 +1239,7 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
 #define EMD_LJ_TILES(ONE, MD)                                                                                              \
   do {                                                                                                                     \
     if (set_smem(lj_tiles_kernel<ONE, MD>, smem)) return 1;                                                                \
-    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, MD>), grid, kForceThreads, smem, a, first, count, nbuf, p1, t->d_tab, d_f, partial, nve); \
+    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, MD>), grid, kForceThreads, smem, a, first, count, nbuf, p1, t->d_tab, d_f, partial, nve, gate); \
   } while (0)
   if (fuse) { if (one) EMD_LJ_TILES(true, MODE_NVE); else EMD_LJ_TILES(false, MODE_NVE); }
   else if (h_pe && force_too) { if (one) EMD_LJ_TILES(true, MODE_FORCE_ENERGY); else EMD_LJ_TILES(false, MODE_FORCE_ENERGY); }

@@ -28,6 +28,12 @@ int emd_ctx_create(emd_ctx **out, int device, void *stream);
 void emd_ctx_destroy(emd_ctx *ctx);
 void *emd_ctx_stream(emd_ctx *ctx);
 int emd_ctx_sync(emd_ctx *ctx);                 /* replaces Kokkos::fence() */
+/* Halo gate: emd_peer_update_dim(..., defer_wait = 1) leaves the wait for the neighbours' ghost stores to the consumer.
+ * The LJ tile force launches take a pending gate along (they wait only before their first tile that reads a ghost);
+ * every other consumer of ghost positions calls emd_ctx_halo_gate_wait first (a one-warp wait kernel on the stream). */
+int emd_ctx_set_halo_gate(emd_ctx *ctx, const int *d_arrived6, int seq, int phase_mask);
+int emd_ctx_halo_gate_wait(emd_ctx *ctx);
+int emd_ctx_halo_gate_pending(const emd_ctx *ctx);
 /* measurement aid (bench.py): FP64 FMA peak of the device in TFLOP/s, DFMA loop on every SM, `reps` launches after two
  * warm-ups -- best and mean.  The SNAP roofline's denominator (MEASURED_PEAKS.json holds HBM and bf16 only). */
 int emd_microbench_fp64(emd_ctx *ctx, int reps, double *h_tflops_best, double *h_tflops_mean);
@@ -346,6 +352,25 @@ int emd_net_sendrecv(emd_net *n, const void *d_send, unsigned long long send_byt
 /* message pairs issued between begin and end travel as one NCCL group (one fused send/recv kernel on the stream) */
 int emd_net_group_begin(emd_net *n);
 int emd_net_group_end(emd_net *n);
+/* MPI_Allgather of one small record per rank, host memory to host memory (nbytes a multiple of 4); synchronises */
+int emd_net_allgather_bytes(emd_net *n, const void *h_in, int nbytes, void *h_out_all);
+/* ---- CommMPI::update_halo (comm_mpi.cpp:382-423) by peer stores over NVLink (kernels/comm_peer.cu): the pack kernel of a
+ * phase writes the shifted positions straight into the neighbour's ghost rows through CUDA IPC mappings and raises a
+ * sequence flag there; no transport library on the per-step path.  emd_peer_publish is collective and follows every
+ * exchange_halo (it ships the IPC handles of the two position arrays and the first ghost row of each phase);
+ * per refresh: emd_peer_begin_update once, then emd_peer_update_dim for every decomposed dimension in order 0,1,2
+ * (the dimensions that are not decomposed use emd_comm_halo_update_phase in between, as before). */
+typedef struct emd_peer emd_peer;
+int emd_peer_create(emd_peer **out, emd_net *net, emd_ctx *ctx, int nranks, int rank);
+void emd_peer_destroy(emd_peer *p);
+int emd_peer_publish(emd_peer *p, const emd_decomp *dec, double *d_x0, double *d_x1, const int ghost_begin[6]);
+int emd_peer_ready(const emd_peer *p);
+int emd_peer_begin_update(emd_peer *p, const emd_decomp *dec, const double *d_x_current);
+int emd_peer_update_dim(emd_peer *p, const emd_decomp *dec, const double domain[3], int dim, const double *d_x,
+                        const int *d_pack_idx_a, int count_a, const int *d_pack_idx_b, int count_b, int defer_wait);
+/* blocks the stream until every message of the refresh in progress has landed (needed before a dimension that is not
+ * decomposed forwards ghosts of an earlier, decomposed one) */
+int emd_peer_wait_all(emd_peer *p);
 /* the count handshake of a phase (comm_mpi.cpp:235-238, 325-328); synchronises */
 int emd_net_exchange_count(emd_net *n, int send_count, int peer_send, int peer_recv, int *h_recv_count);
 /* MPI_Allreduce(IN_PLACE) / MPI_Scan on HOST scalars (comm_mpi.cpp:150-191): is_double 0 int / 1 double, op 0 sum / 1 max */
