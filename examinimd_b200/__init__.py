@@ -94,6 +94,11 @@ _SIGS = {
     "emd_force_lj_compute": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NeighList), C.c_int, C.c_int]),
     "emd_force_lj_idial_compute": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NeighList), C.c_int, C.c_int, _P]),
     "emd_force_lj_energy": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(NeighList), C.c_int, C.POINTER(C.c_double)]),
+    "emd_lattice_count": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "emd_lattice_fill": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "emd_velocity_sums": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "emd_velocity_shift": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_double, C.c_double]),
+    "emd_velocity_scale": (C.c_int, [_P, _P, C.c_int, C.c_double]),
     "emd_tiles_create": (C.c_int, [C.POINTER(_P)]),
     "emd_tiles_destroy": (None, [_P]),
     "emd_tiles_valid": (C.c_int, [_P]),

@@ -340,12 +340,61 @@ void for_each_site(const Input &in, const System &s, Visit visit) {
 }
 } // namespace
 
+void Input::create_lattice_device(Comm *comm) {
+  System &s = *system;
+  emd_lattice lat;
+  // index ranges exactly as the host loops compute them (truncation of the double expressions, :485-490 / :604-609)
+  const T_INT ix0 = s.sub_domain_lo_x / s.domain_x * lattice_nx - 0.5, ix1 = s.sub_domain_hi_x / s.domain_x * lattice_nx + 0.5;
+  const T_INT iy0 = s.sub_domain_lo_y / s.domain_y * lattice_ny - 0.5, iy1 = s.sub_domain_hi_y / s.domain_y * lattice_ny + 0.5;
+  const T_INT iz0 = s.sub_domain_lo_z / s.domain_z * lattice_nz - 0.5, iz1 = s.sub_domain_hi_z / s.domain_z * lattice_nz + 0.5;
+  lat.i0[0] = ix0; lat.i0[1] = iy0; lat.i0[2] = iz0;
+  lat.n[0] = ix1 - ix0 + 1; lat.n[1] = iy1 - iy0 + 1; lat.n[2] = iz1 - iz0 + 1;
+  lat.fcc = lattice_style == LATTICE_FCC ? 1 : 0;
+  lat.a = lattice_constant;
+  lat.offset[0] = lattice_offset_x; lat.offset[1] = lattice_offset_y; lat.offset[2] = lattice_offset_z;
+  lat.lo[0] = s.sub_domain_lo_x; lat.lo[1] = s.sub_domain_lo_y; lat.lo[2] = s.sub_domain_lo_z;
+  lat.hi[0] = s.sub_domain_hi_x; lat.hi[1] = s.sub_domain_hi_y; lat.hi[2] = s.sub_domain_hi_z;
+  auto die = [&](const char *what) { fprintf(stderr, "Input::create_lattice: %s: %s\n", what, emd_last_error()); emd_host_exit(1); };
+  int n = 0;
+  if (emd_lattice_count(s.ctx, &lat, &n)) die("count");
+  s.N_local = n;
+  s.N = n;
+  s.grow(n + n / 4 + 16); // head-room for ghosts (the reference ends up with 2n, :497-534)
+  // global atom count and globally unique ids (:578-584 / :714-721)
+  T_INT N_local_offset = n;
+  comm->scan_int(&N_local_offset, 1);
+  comm->reduce_int(&s.N, 1);
+  if (s.do_print) printf("Atoms: %i %i\n", s.N, s.N_local);
+  if (emd_lattice_fill(s.ctx, &lat, temperature_seed, N_local_offset - n, s.mass, s.x, s.v, s.q, s.type, s.id)) die("fill");
+  if (emd_memset_zero(s.ctx, s.f, sizeof(T_F_FLOAT) * 3 * (size_t)n)) die("zero f");
+  // centre-of-mass velocity out, then rescale to the target temperature (:731-785); sums in atom order
+  double m4[4];
+  if (emd_velocity_sums(s.ctx, s.v, s.type, s.mass, n, 0, m4)) die("momentum sums");
+  T_FLOAT total_mass = m4[0], px = m4[1], py = m4[2], pz = m4[3];
+  comm->reduce_float(&px, 1);
+  comm->reduce_float(&py, 1);
+  comm->reduce_float(&pz, 1);
+  comm->reduce_float(&total_mass, 1);
+  if (emd_velocity_shift(s.ctx, s.v, n, px / total_mass, py / total_mass, pz / total_mass)) die("shift");
+  if (emd_velocity_sums(s.ctx, s.v, s.type, s.mass, n, 1, m4)) die("temperature sum");
+  T_V_FLOAT T = m4[0];
+  comm->reduce_float(&T, 1);
+  const T_INT dof = 3 * s.N - 3;
+  T *= s.mvv2e / (1.0 * dof * s.boltz);
+  if (emd_velocity_scale(s.ctx, s.v, n, sqrt(temperature_target / T))) die("scale");
+}
+
 void Input::create_lattice(Comm *comm) {
   system->set_mass(system->h_mass);
   system->domain_x = lattice_constant * lattice_nx;
   system->domain_y = lattice_constant * lattice_ny;
   system->domain_z = lattice_constant * lattice_nz;
   comm->create_domain_decomposition();
+
+  // one atom type: everything below runs on the device, bit-identical (kernels/lattice.cu); more types need the
+  // sequential libc rand() stream of the reference for the type draw and keep the host loops
+  const bool host_only = getenv("EMD_HOST_LATTICE") && atoi(getenv("EMD_HOST_LATTICE")); // (read at every call: the tests compare both paths)
+  if (system->ntypes == 1 && !host_only) { create_lattice_device(comm); return; }
 
   T_INT n = 0;
   for_each_site(*this, *system, [&](const Site &) { n++; });

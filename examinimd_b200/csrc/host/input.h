@@ -68,4 +68,5 @@ public:
   void read_lammps_file(const char *filename);
   void check_lammps_command(int line);
   void create_lattice(Comm *comm);
+  void create_lattice_device(Comm *comm); // the same on the device (one atom type), kernels/lattice.cu
 };

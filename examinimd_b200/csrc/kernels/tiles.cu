@@ -679,6 +679,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 constexpr int kForceThreads = kRowThreads;
 constexpr int kForceWarps = kForceThreads / 32;
 constexpr int kMaxBuf = 3;
+constexpr int kProdUnroll = 16;
 
 // Persistent CTAs (2 per SM), each walking the tiles a.order[first + blockIdx.x], [first + blockIdx.x + gridDim.x], ...
 // below first + ntiles.  NBUF coordinate buffers; tile k of the CTA lives in buffer k mod NBUF.
@@ -742,12 +743,13 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
       const int *__restrict__ src = a.stg_j + (size_t)tl * a.cap;
       double *dstb = reinterpret_cast<double *>(dyn + (size_t)b * buf_bytes) + 3 * kDummySlots;
       int *dstt = st0 + (size_t)b * tstride + kDummySlots;
-      for (int s0 = 0; s0 < n; s0 += 32 * 8) {
-        int j[8];
+      // 16 staging indices per lane are in flight at a time: the copies of a tile are 4-5 dependent rounds of global latency
+      for (int s0 = 0; s0 < n; s0 += 32 * kProdUnroll) {
+        int j[kProdUnroll];
 #pragma unroll
-        for (int u = 0; u < 8; u++) { const int s = s0 + u * 32 + lane; j[u] = s < n ? __ldg(src + s) : -1; }
+        for (int u = 0; u < kProdUnroll; u++) { const int s = s0 + u * 32 + lane; j[u] = s < n ? __ldg(src + s) : -1; }
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < kProdUnroll; u++) {
           if (j[u] >= 0) {
             const int s = s0 + u * 32 + lane;
             const double *g = a.x + 3 * (size_t)j[u];

@@ -157,6 +157,25 @@ int emd_force_lj_idial_compute(emd_ctx *ctx, const double *d_x, const int *d_typ
 int emd_force_lj_energy(emd_ctx *ctx, const double *d_x, const int *d_type, int n_local,
                         const emd_neigh_list *list, int half_neigh, double *h_pe);
 
+/* ---- Input::create_lattice / create_velocities on the device (src/input.cpp:460-792, src/input.h:66-133), bit-identical
+ * to the host loops: sites in the reference's loop order (z, y, x, basis) that lie in the brick [lo, hi); velocities from the
+ * per-position hashed Park-Miller stream; momentum / temperature sums in atom order (one thread). */
+typedef struct emd_lattice {
+  long long i0[3];   /* first lattice index per dimension (input.cpp:485-490 / 604-609) */
+  int n[3];          /* number of indices per dimension (inclusive ranges of the reference) */
+  int fcc;           /* 1: fcc (4-atom basis, a*(1.0*i + basis + offset)); 0: sc (a*(i + offset)) */
+  double a, offset[3];
+  double lo[3], hi[3];
+} emd_lattice;
+int emd_lattice_count(emd_ctx *ctx, const emd_lattice *lat, int *h_n);
+/* follows emd_lattice_count of the same lattice; one atom type (type 0); id = row + 1 + id_offset; q = 0; v = (u - 0.5)/sqrt(m) */
+int emd_lattice_fill(emd_ctx *ctx, const emd_lattice *lat, int seed, int id_offset, const double *d_mass, double *d_x, double *d_v,
+                     double *d_q, int *d_type, int *d_id);
+/* mode 0: {sum m, sum m vx, sum m vy, sum m vz} (input.cpp:750-753); mode 1: {sum m |v|^2} (property_temperature.cpp:49) */
+int emd_velocity_sums(emd_ctx *ctx, const double *d_v, const int *d_type, const double *d_mass, int n, int mode, double *h_out4);
+int emd_velocity_shift(emd_ctx *ctx, double *d_v, int n, double sx, double sy, double sz);   /* input.cpp:763-767 */
+int emd_velocity_scale(emd_ctx *ctx, double *d_v, int n, double s);                          /* input.cpp:781-785 */
+
 /* ---- tile lists: the B200 fast path of the neighbor build + LJ force (kernels/tiles.cu) -------
  * An emd_tiles object holds a tile-local FULL adjacency (shared-memory slot numbers, ELL layout)
  * built from the same inputs as the reference lists: an FP32 search leaves one bit per stencil

@@ -149,3 +149,25 @@ def test_full_size_invariants(emd):
     total = app.get("total_neighs")
     assert total >= 39 * n * 0.9
     app.close()
+
+
+@pytest.mark.parametrize("deck,region", [(DECK, (12, 10, 14)), (REPO / "input" / "snap" / "in.snap.W", (5, 6, 7))])
+def test_device_lattice_is_bit_identical_to_the_host_loops(emd, deck, region, monkeypatch):
+    """Input::create_lattice / create_velocities on the device (kernels/lattice.cu) against the host loops they replace
+    (src/input.cpp:460-792): atom order, positions, ids, types and velocities bit for bit"""
+    import os
+    cwd = os.getcwd()
+    os.chdir(deck.parent)  # the SNAP deck names its coefficient files relative to the working directory
+    try:
+        states = []
+        for host in ("1", "0"):
+            monkeypatch.setenv("EMD_HOST_LATTICE", host)
+            app = emd.App(["-il", str(deck), "--comm-type", "SERIAL", "--region", *map(str, region)])
+            states.append(app.download())
+            app.close()
+    finally:
+        os.chdir(cwd)
+    a, b = states
+    assert a["x"].shape[0] > 0
+    for k in ("id", "type", "x", "v"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
