@@ -251,6 +251,7 @@ def lj_throughput(env, app, K, W):
     n_atoms = app.get("N")
     rate = app.get("exchange_rate")
     app.run(W)
+    app.thermo()  # (warm-up also meets the thermo kernels: CUDA loads a kernel at its first launch, ~1 ms)
     app.advance((rate - 1 - app.get("step")) % rate)
     t_ms, launches = timed(env, app, lambda: app.run(K))
     app.advance((rate - 1 - app.get("step")) % rate)
@@ -330,7 +331,7 @@ def main_section(env, args):
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": force_bytes,
                 "kernel": "lj_tiles_kernel" if tiles else "lj_force_kernel<half> + zero_rows_kernel", "kernel_ms": force_ms, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_atom": force_bytes / n_local, "nbar": nbar, "g": g,
-                "note": "the kernel is FP64-issue-bound, not HBM-bound (DESIGN.md 4.3); the HBM fraction is what BASELINE.json's metric asks for",
+                "note": "the kernel is bound by the FP64 pipe (0.146 ms floor) and the shared-memory pipe, not by HBM (DESIGN.md 4.3); the HBM fraction is what BASELINE.json's metric asks for",
                 "whole_step": {"B_LJ_bytes_per_atom_step": b_lj, "achieved_gbs": b_lj * per_gpu / 1e9, "frac": b_lj * per_gpu / 1e9 / peak,
                                "frac_no_thermo": b_lj * thr["value_no_thermo"] / world / 1e9 / peak}}
 

@@ -1023,8 +1023,26 @@ int ensure_lists(emd_ctx *ctx, emd_tiles *t, bool exact, int half, int newton, i
 
 extern "C" {
 
+// CUDA loads a kernel lazily at its first launch (~1 ms each): the variants that a run meets late (the thermo step's force +
+// energy launch, the split launches of a decomposed run) are loaded here instead of inside somebody's timed region
+static void warm_kernels() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncAttributes at;
+#define EMD_WARM(K) (void)cudaFuncGetAttributes(&at, K)
+  EMD_WARM((lj_tiles_kernel<true, MODE_FORCE>)); EMD_WARM((lj_tiles_kernel<true, MODE_ENERGY>)); EMD_WARM((lj_tiles_kernel<true, MODE_NVE>));
+  EMD_WARM((lj_tiles_kernel<true, MODE_FORCE_ENERGY>)); EMD_WARM((lj_tiles_kernel<false, MODE_FORCE>)); EMD_WARM((lj_tiles_kernel<false, MODE_ENERGY>));
+  EMD_WARM((lj_tiles_kernel<false, MODE_NVE>)); EMD_WARM((lj_tiles_kernel<false, MODE_FORCE_ENERGY>));
+  EMD_WARM(tiles_search_kernel); EMD_WARM(tiles_order_kernel); EMD_WARM(tiles_lists_kernel<true>); EMD_WARM(tiles_lists_kernel<false>);
+  EMD_WARM(tiles_counts_kernel); EMD_WARM(tiles_fill_kernel<FILL_CSR>); EMD_WARM(tiles_fill_kernel<FILL_2D>);
+#undef EMD_WARM
+  (void)cudaGetLastError();
+}
+
 int emd_tiles_create(emd_tiles **out) {
   if (!out) { set_error("emd_tiles_create: out == NULL"); return 1; }
+  warm_kernels();
   emd_tiles *t = new emd_tiles();
   memset(&t->a, 0, sizeof t->a);
   EMD_CUDA(cudaMalloc((void **)&t->d_flags, FL_COUNT * sizeof(int)));
