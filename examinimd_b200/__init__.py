@@ -159,6 +159,7 @@ _SIGS = {
     "emd_net_scan_int": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "emd_net_barrier": (C.c_int, [_P]),
     "emd_net_allgather_bytes": (C.c_int, [_P, _P, C.c_int, _P]),
+    "emd_net_exchange_counts2": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "emd_peer_create": (C.c_int, [C.POINTER(_P), _P, _P, C.c_int, C.c_int]),
     "emd_peer_destroy": (None, [_P]),
     "emd_peer_publish": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int)]),

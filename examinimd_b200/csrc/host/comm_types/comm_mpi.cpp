@@ -73,31 +73,43 @@ void CommMPI::exchange() {
   const int wrap[3] = {dec.grid[0] == 1, dec.grid[1] == 1, dec.grid[2] == 1};
   if (emd_comm_wrap_dims(ctx, system->x, N_local, L, wrap)) fail("wrap");
   T_INT N_total_recv = 0, N_total_send = 0;
-  for (int phase = 0; phase < 6; phase++) {
-    T_INT send = 0, recv = 0;
-    if (decomposed(phase)) {
+  // The two phases of a dimension do not depend on each other (an atom that arrives from -d in the even phase lies inside
+  // the brick in d and cannot be selected by the odd one; packed atoms are marked and skipped): both are packed first,
+  // their counts travel as one handshake and their atoms as one message group -- half the synchronisations and groups
+  // of the phase-by-phase sequence (:219-256), same atoms, same order.
+  for (int dim = 0; dim < 3; dim++) {
+    const int pa = 2 * dim;
+    if (!decomposed(pa)) continue;
+    DeviceArray<char> *pk[2] = {&pack_buffer, &pack_buffer2}, *up[2] = {&unpack_buffer, &unpack_buffer2};
+    int send[2] = {0, 0}, recv[2] = {0, 0};
+    for (int k = 0; k < 2; k++) {
       for (int attempt = 0; attempt < 2; attempt++) {
-        const int cap = (int)(pack_buffer.extent() / kParticleBytes);
+        const int cap = (int)(pk[k]->extent() / kParticleBytes);
         int count = 0;
-        if (emd_comm_exchange_pack(ctx, phase, &dec, L, system->x, system->v, system->q, system->id, system->type, N_local + N_ghost,
-                                   pack_buffer.ptr, cap, &count))
+        if (emd_comm_exchange_pack(ctx, pa + k, &dec, L, system->x, system->v, system->q, system->id, system->type, N_local + N_ghost,
+                                   pk[k]->ptr, cap, &count))
           fail("exchange_pack");
-        send = count;
+        send[k] = count;
         if (count <= cap) break;
-        ensure_bytes(pack_buffer, (size_t)(count * 1.1 + 16) * kParticleBytes); // :230-238
+        ensure_bytes(*pk[k], (size_t)(count * 1.1 + 16) * kParticleBytes); // :230-238
       }
-      if (emd_net_exchange_count(net, send, dec.neighbor_send[phase], dec.neighbor_recv[phase], &recv)) fail("count handshake");
-      ensure_bytes(unpack_buffer, (size_t)recv * kParticleBytes);
-      if (N_local + N_ghost + recv > system->N_max) system->grow(N_local + N_ghost + recv + recv / 4 + 16);
-      if (emd_net_sendrecv(net, pack_buffer.ptr, (size_t)send * kParticleBytes, dec.neighbor_send[phase], unpack_buffer.ptr,
-                           (size_t)recv * kParticleBytes, dec.neighbor_recv[phase]))
-        fail("sendrecv");
-      if (emd_comm_unpack(ctx, unpack_buffer.ptr, recv, N_local + N_ghost, system->x, system->v, system->q, system->id, system->type))
-        fail("unpack");
     }
-    N_ghost += recv;
-    N_total_recv += recv;
-    N_total_send += send;
+    const int peer_send[2] = {dec.neighbor_send[pa], dec.neighbor_send[pa + 1]}, peer_recv[2] = {dec.neighbor_recv[pa], dec.neighbor_recv[pa + 1]};
+    if (emd_net_exchange_counts2(net, send, peer_send, peer_recv, recv)) fail("count handshake");
+    for (int k = 0; k < 2; k++) ensure_bytes(*up[k], (size_t)recv[k] * kParticleBytes);
+    const T_INT need = N_local + N_ghost + recv[0] + recv[1];
+    if (need > system->N_max) system->grow(need + (recv[0] + recv[1]) / 4 + 16);
+    if (emd_net_group_begin(net)) fail("group");
+    for (int k = 0; k < 2; k++)
+      if (emd_net_sendrecv(net, pk[k]->ptr, (size_t)send[k] * kParticleBytes, peer_send[k], up[k]->ptr, (size_t)recv[k] * kParticleBytes, peer_recv[k]))
+        fail("sendrecv");
+    if (emd_net_group_end(net)) fail("group");
+    for (int k = 0; k < 2; k++) {
+      if (emd_comm_unpack(ctx, up[k]->ptr, recv[k], N_local + N_ghost, system->x, system->v, system->q, system->id, system->type)) fail("unpack");
+      N_ghost += recv[k];
+      N_total_recv += recv[k];
+      N_total_send += send[k];
+    }
   }
   const T_INT N_local_start = N_local, N_exchange = N_ghost;
   N_local = N_local + N_total_recv - N_total_send; // :259
@@ -121,28 +133,40 @@ void CommMPI::exchange_halo() {
     // an odd phase does not re-scan the ghosts its even twin just received (:306,:346)
     const T_INT nparticles = N_local + N_ghost - ((phase % 2 == 1) ? proc_num_recv[phase - 1] : 0);
     int count = 0;
-    if (decomposed(phase)) {
-      for (int attempt = 0; attempt < 2; attempt++) {
-        const int cap = (int)std::min(pack_buffer.extent() / kParticleBytes, pack_indicies[phase].extent());
-        if (emd_comm_halo_pack(ctx, phase, &dec, L, comm_depth, system->x, system->v, system->q, system->id, system->type, nparticles,
-                               pack_indicies[phase].ptr, pack_buffer.ptr, cap, &count))
-          fail("halo_pack");
-        if (count <= cap) break;
-        ensure_bytes(pack_buffer, (size_t)(count * 1.1 + 16) * kParticleBytes); // :319-327
-        if ((size_t)count > pack_indicies[phase].extent() && !pack_indicies[phase].alloc((size_t)(count * 1.1) + 16)) fail("alloc pack_indicies");
+    if (decomposed(phase) && phase % 2 == 1) {
+      count = proc_num_recv[phase]; // shipped together with its even twin below
+    } else if (decomposed(phase)) {
+      // both phases of the dimension scan the same atoms [0, nparticles): packed first, one count handshake, one message group
+      DeviceArray<char> *pk[2] = {&pack_buffer, &pack_buffer2}, *up[2] = {&unpack_buffer, &unpack_buffer2};
+      int send[2] = {0, 0}, recv[2] = {0, 0};
+      for (int k = 0; k < 2; k++) {
+        const int ph = phase + k;
+        for (int attempt = 0; attempt < 2; attempt++) {
+          const int cap = (int)std::min(pk[k]->extent() / kParticleBytes, pack_indicies[ph].extent());
+          if (emd_comm_halo_pack(ctx, ph, &dec, L, comm_depth, system->x, system->v, system->q, system->id, system->type, nparticles,
+                                 pack_indicies[ph].ptr, pk[k]->ptr, cap, &send[k]))
+            fail("halo_pack");
+          if (send[k] <= cap) break;
+          ensure_bytes(*pk[k], (size_t)(send[k] * 1.1 + 16) * kParticleBytes); // :319-327
+          if ((size_t)send[k] > pack_indicies[ph].extent() && !pack_indicies[ph].alloc((size_t)(send[k] * 1.1) + 16)) fail("alloc pack_indicies");
+        }
+        proc_num_send[ph] = send[k];
       }
-      proc_num_send[phase] = count;
-      int recv = 0;
-      if (emd_net_exchange_count(net, count, dec.neighbor_send[phase], dec.neighbor_recv[phase], &recv)) fail("count handshake");
-      proc_num_recv[phase] = recv;
-      ensure_bytes(unpack_buffer, (size_t)recv * kParticleBytes);
-      if (N_local + N_ghost + recv > system->N_max) system->grow(N_local + N_ghost + recv + recv / 4 + 16);
-      if (emd_net_sendrecv(net, pack_buffer.ptr, (size_t)count * kParticleBytes, dec.neighbor_send[phase], unpack_buffer.ptr,
-                           (size_t)recv * kParticleBytes, dec.neighbor_recv[phase]))
-        fail("sendrecv");
-      if (emd_comm_unpack(ctx, unpack_buffer.ptr, recv, N_local + N_ghost, system->x, system->v, system->q, system->id, system->type))
+      const int peer_send[2] = {dec.neighbor_send[phase], dec.neighbor_send[phase + 1]}, peer_recv[2] = {dec.neighbor_recv[phase], dec.neighbor_recv[phase + 1]};
+      if (emd_net_exchange_counts2(net, send, peer_send, peer_recv, recv)) fail("count handshake");
+      proc_num_recv[phase] = recv[0]; proc_num_recv[phase + 1] = recv[1];
+      for (int k = 0; k < 2; k++) ensure_bytes(*up[k], (size_t)recv[k] * kParticleBytes);
+      const T_INT need = N_local + N_ghost + recv[0] + recv[1];
+      if (need > system->N_max) system->grow(need + (recv[0] + recv[1]) / 4 + 16);
+      if (emd_net_group_begin(net)) fail("group");
+      for (int k = 0; k < 2; k++)
+        if (emd_net_sendrecv(net, pk[k]->ptr, (size_t)send[k] * kParticleBytes, peer_send[k], up[k]->ptr, (size_t)recv[k] * kParticleBytes, peer_recv[k]))
+          fail("sendrecv");
+      if (emd_net_group_end(net)) fail("group");
+      if (emd_comm_unpack(ctx, up[0]->ptr, recv[0], N_local + N_ghost, system->x, system->v, system->q, system->id, system->type) ||
+          emd_comm_unpack(ctx, up[1]->ptr, recv[1], N_local + N_ghost + recv[0], system->x, system->v, system->q, system->id, system->type))
         fail("unpack");
-      count = recv;
+      count = recv[0];
     } else { // the in-process twin of the phase, same kernels as CommSerial (:344-371)
       const double lo[3] = {system->sub_domain_lo_x, system->sub_domain_lo_y, system->sub_domain_lo_z};
       const double hi[3] = {system->sub_domain_hi_x, system->sub_domain_hi_y, system->sub_domain_hi_z};

@@ -25,6 +25,7 @@ class CommMPI : public Comm {
   T_INT num_ghost[6], ghost_offsets[6];
   DeviceArray<T_INT> pack_indicies[6];      // pack_indicies_all(phase, :)
   DeviceArray<char> pack_buffer, unpack_buffer;
+  DeviceArray<char> pack_buffer2, unpack_buffer2; // the odd phase of a dimension (both phases of a dimension travel together)
   // the leading dimensions that are not decomposed: every ghost of theirs resolved to its owned root atom + total periodic
   // shift once per ghost build, so that their refresh is one kernel (as in CommSerial)
   DeviceArray<T_INT> local_root;

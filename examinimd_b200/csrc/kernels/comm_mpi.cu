@@ -473,6 +473,24 @@ int emd_net_exchange_count(emd_net *n, int send_count, int peer_send, int peer_r
   return 0;
 }
 
+// the count handshakes of the two phases of one dimension as ONE message group and ONE synchronisation
+int emd_net_exchange_counts2(emd_net *n, const int send_count[2], const int peer_send[2], const int peer_recv[2], int h_recv_count[2]) {
+  if (!n) { set_error("emd_net_exchange_counts2: no transport"); return 1; }
+  emd_ctx *c = n->ctx;
+  c->h_pinned[8] = send_count[0]; c->h_pinned[9] = send_count[1];
+  EMD_CUDA(cudaMemcpyAsync(n->d_small, c->h_pinned + 8, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  EMD_NCCL(g_nccl.GroupStart());
+  for (int k = 0; k < 2; k++) {
+    EMD_NCCL(g_nccl.Recv(n->d_small + 2 + k, 1, ncclInt, peer_recv[k], n->comm, c->stream));
+    EMD_NCCL(g_nccl.Send(n->d_small + k, 1, ncclInt, peer_send[k], n->comm, c->stream));
+  }
+  EMD_NCCL(g_nccl.GroupEnd());
+  EMD_CUDA(cudaMemcpyAsync(c->h_pinned + 10, n->d_small + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  EMD_CUDA(cudaStreamSynchronize(c->stream));
+  h_recv_count[0] = c->h_pinned[10]; h_recv_count[1] = c->h_pinned[11];
+  return 0;
+}
+
 // MPI_Allreduce(IN_PLACE) on HOST values (comm_mpi.cpp:156-191): is_double 0 = int, 1 = double; op 0 = sum, 1 = max
 int emd_net_allreduce(emd_net *n, void *h_values, int count, int is_double, int op) {
   if (!n) { set_error("emd_net_allreduce: no transport"); return 1; }

@@ -371,6 +371,8 @@ int emd_net_sendrecv(emd_net *n, const void *d_send, unsigned long long send_byt
 /* message pairs issued between begin and end travel as one NCCL group (one fused send/recv kernel on the stream) */
 int emd_net_group_begin(emd_net *n);
 int emd_net_group_end(emd_net *n);
+/* the handshakes of the two phases of one dimension (which do not depend on each other) in one group; synchronises */
+int emd_net_exchange_counts2(emd_net *n, const int send_count[2], const int peer_send[2], const int peer_recv[2], int h_recv_count[2]);
 /* MPI_Allgather of one small record per rank, host memory to host memory (nbytes a multiple of 4); synchronises */
 int emd_net_allgather_bytes(emd_net *n, const void *h_in, int nbytes, void *h_out_all);
 /* ---- CommMPI::update_halo (comm_mpi.cpp:382-423) by peer stores over NVLink (kernels/comm_peer.cu): the pack kernel of a
