@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # load all kernels with the module, not at their first launch (if CUDA is not up yet)
 from pathlib import Path
 
 _ROOT = Path(__file__).resolve().parent

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 int main(int argc, char *argv[]) {
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0); // load every kernel with its module, not at its first launch inside the run loop
   int device = 0;
   if (const char *lr = getenv("LOCAL_RANK")) device = atoi(lr);
   ExaMiniMD examinimd(device);
