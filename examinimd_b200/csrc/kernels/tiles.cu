@@ -50,6 +50,7 @@ namespace {
 
 constexpr int kMaxStagedCells = 400;
 constexpr int kMaxInteriorCells = 128;
+constexpr int kMaxStagedRows = 36; // (tx+2)(ty+2) of the largest tile shape
 constexpr int kSearchThreads = 256;
 constexpr int kRowThreads = 384;  // dense atom slots (rows) per tile = threads of the lists / fill / force kernels
 constexpr int kRowWarps = kRowThreads / 32;
@@ -89,6 +90,9 @@ struct TileArgs {
   // per-tile staging tables, so that the per-step force kernel needs no cell arithmetic
   int *stg_j;                // [ntiles][cap]  global index of every staged slot
   int *stg_n;                // [ntiles]  staged atoms
+  // staged z-rows ((tz+2) z-adjacent bins = one contiguous slot range): {first slot, first atom index or -1, atoms, 0}.  Owned atoms
+  // are cell-sorted, so a row without ghosts is one contiguous piece of x and is copied without the slot -> atom table
+  int4 *rowdesc;             // [ntiles][kMaxStagedRows]
   unsigned short *int_slot;  // [ntiles][stride]  staged slot of the row's own atom
   int *int_glob;             // [ntiles][stride]  its global index (>= n_local or 0x7fffffff: no row)
   // tiles whose staged cells hold only owned atoms come first in `order` (their forces do not depend on the halo, so a
@@ -208,6 +212,15 @@ __global__ void __launch_bounds__(kSearchThreads) tiles_search_kernel(TileArgs a
   }
   ghost = __syncthreads_or(ghost);
   if (threadIdx.x == 0) a.has_ghost[t.tile] = ghost ? 1 : 0;
+  for (int r = warp; r < t.sxn * t.syn; r += nwarps) { // row descriptors: is the row one run of consecutive atom indices?
+    const int c0 = r * t.szn;
+    const int sb = s_start[c0], n = s_start[c0 + t.szn] - sb;
+    const int j0 = n > 0 ? a.stg_j[(size_t)t.tile * a.cap + sb] : -1; // (written above by this CTA; visible after the barrier)
+    bool ok = j0 >= 0 && j0 + n <= a.n_local;
+    for (int k = lane; k < n && ok; k += 32) ok = a.stg_j[(size_t)t.tile * a.cap + sb + k] == j0 + k;
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) a.rowdesc[(size_t)t.tile * kMaxStagedRows + r] = make_int4(sb, ok ? j0 : -1, n, 0);
+  }
   for (int k = t.n_int + threadIdx.x; k < a.stride; k += blockDim.x) {
     a.nell[(size_t)t.tile * a.stride + k] = 0;
     a.int_slot[(size_t)t.tile * a.stride + k] = 0;
@@ -648,6 +661,12 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) 
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 ldg_nc_v4(const uint4 *p) {
   uint4 v;
@@ -697,7 +716,7 @@ enum { MODE_FORCE = 0, MODE_ENERGY = 1, MODE_NVE = 2, MODE_FORCE_ENERGY = 3 };
 struct HaloGate { const int *flags; int seq, mask; }; // common.cuh: the neighbours' ghost stores of this step (comm_peer.cu)
 
 template <bool ONETYPE, int MODE>
-__global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, int nbuf, LJOne one, const LJTab *__restrict__ tab,
+__global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, int nbuf, unsigned ring_off, LJOne one, const LJTab *__restrict__ tab,
                                                                    double *__restrict__ f, double *__restrict__ pe_partial, NveFuse nve, HaloGate gate) {
   constexpr bool ENERGY = MODE == MODE_ENERGY || MODE == MODE_FORCE_ENERGY;
   __shared__ double s_red[kForceWarps];
@@ -739,22 +758,40 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
         __syncwarp();
         halo_ok = true;
       }
-      const int n = a.stg_n[tl];
       const int *__restrict__ src = a.stg_j + (size_t)tl * a.cap;
       double *dstb = reinterpret_cast<double *>(dyn + (size_t)b * buf_bytes) + 3 * kDummySlots;
       int *dstt = st0 + (size_t)b * tstride + kDummySlots;
-      // 16 staging indices per lane are in flight at a time: the copies of a tile are 4-5 dependent rounds of global latency
-      for (int s0 = 0; s0 < n; s0 += 32 * kProdUnroll) {
-        int j[kProdUnroll];
+      // One descriptor per staged z-row, read with one coalesced load: in a tile without ghosts every row is a run of
+      // consecutive atoms of x (owned atoms are cell-sorted) and is copied as consecutive doubles: one round of global latency
+      // for the whole tile.  A tile that stages a ghost (or has one inside an interior bin) goes through the slot -> atom
+      // table: dependent rounds of 16 indices per lane.
+      const int nrows = (a.tx + 2) * (a.ty + 2);
+      const int4 mine = lane < nrows ? a.rowdesc[(size_t)tl * kMaxStagedRows + lane] : make_int4(0, 0, 0, 0);
+      const int4 mine2 = lane + 32 < nrows ? a.rowdesc[(size_t)tl * kMaxStagedRows + 32 + lane] : make_int4(0, 0, 0, 0);
+      if (!__any_sync(0xffffffffu, (mine.z > 0 && mine.y < 0) || (mine2.z > 0 && mine2.y < 0))) {
+        for (int r = 0; r < nrows; r++) {
+          const int sl = r & 31;
+          const int sb = __shfl_sync(0xffffffffu, r < 32 ? mine.x : mine2.x, sl), j0 = __shfl_sync(0xffffffffu, r < 32 ? mine.y : mine2.y, sl),
+                    n = __shfl_sync(0xffffffffu, r < 32 ? mine.z : mine2.z, sl);
+          const double *g = a.x + 3 * (size_t)j0;
+          double *d = dstb + 3 * sb;
+          for (int e = lane; e < 3 * n; e += 32) cp_async8(d + e, g + e);
+          if (!ONETYPE) for (int e = lane; e < n; e += 32) cp_async4(dstt + sb + e, a.type + j0 + e);
+        }
+      } else {
+        const int n = a.stg_n[tl];
+        for (int s0 = 0; s0 < n; s0 += 32 * kProdUnroll) {
+          int j[kProdUnroll];
 #pragma unroll
-        for (int u = 0; u < kProdUnroll; u++) { const int s = s0 + u * 32 + lane; j[u] = s < n ? __ldg(src + s) : -1; }
+          for (int u = 0; u < kProdUnroll; u++) { const int s = s0 + u * 32 + lane; j[u] = s < n ? __ldg(src + s) : -1; }
 #pragma unroll
-        for (int u = 0; u < kProdUnroll; u++) {
-          if (j[u] >= 0) {
-            const int s = s0 + u * 32 + lane;
-            const double *g = a.x + 3 * (size_t)j[u];
-            cp_async8(dstb + 3 * s, g); cp_async8(dstb + 3 * s + 1, g + 1); cp_async8(dstb + 3 * s + 2, g + 2);
-            if (!ONETYPE) cp_async4(dstt + s, a.type + j[u]);
+          for (int u = 0; u < kProdUnroll; u++) {
+            if (j[u] >= 0) {
+              const int s = s0 + u * 32 + lane;
+              const double *g = a.x + 3 * (size_t)j[u];
+              cp_async8(dstb + 3 * s, g); cp_async8(dstb + 3 * s + 1, g + 1); cp_async8(dstb + 3 * s + 2, g + 2);
+              if (!ONETYPE) cp_async4(dstt + s, a.type + j[u]);
+            }
           }
         }
       }
@@ -777,13 +814,16 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
       n_nxt = a.nell_s[rb];
     }
   };
-  // The row words (16 bytes = 8 entries per thread and step) are read once per step.  At this register budget ptxas places
-  // the load of word c+1 at the END of iteration c, next to its first use; an L1 prefetch two words ahead holds no register
-  // and makes that late load an L1 hit.  Measured alternatives (2 M atoms, profiles/README.md, round 2): a per-warp ring of
-  // 512-byte cp.async.bulk copies with one mbarrier per slot removes the long-scoreboard stalls (4.9 -> 1.6 warps per issue)
-  // but costs 30 % more instructions and the shared memory of the second CTA (depth 3: 0.42 ms; depth 2: 0.37 ms); a
-  // two-word register look-ahead 0.329 ms; this form 0.320 ms.
+  // The row words (16 bytes = 8 entries per thread and step) are read once per step, through two 16-byte shared-memory slots
+  // per thread filled by cp.async (LDGSTS): word c+2 is requested right after word c was taken, no register is held while it
+  // is in flight (at this register budget ptxas sinks a register load to the end of the loop body, next to its use), and
+  // cp.async.wait_group 1 leaves word c+1 in flight.  Measured (2 M atoms, profiles/README.md, round 2): register load +
+  // L1 prefetch two words ahead 0.320 ms (17 % of the stall samples on the first use of the word; only 47 % of those loads
+  // hit the 23 KB of L1 left next to the coordinate buffers); two-word register look-ahead 0.329 ms; a per-warp ring of
+  // 512-byte cp.async.bulk copies with one mbarrier per slot 0.42 ms at depth 3 (one CTA per SM) / 0.37 ms at depth 2
+  // (+30 % instructions: elected-lane issue, try_wait, __syncwarp); this per-thread ring 0.316 ms (long-scoreboard 4.9 -> 2.8).
   auto row_of_tile = [&](int tl) { return reinterpret_cast<const uint4 *>(a.ell_s) + ((size_t)tl * (a.maxrow >> 3)) * a.stride + ts; };
+  uint4 *const ering = reinterpret_cast<uint4 *>(dyn + ring_off) + ts; // two 16-byte slots per thread: ering[0], ering[kForceThreads]
   load_desc(0);
   double pe = 0.0;
   int b = 0;
@@ -795,9 +835,13 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
     const int nchunk = n_cur >> 3;
     const uint4 *row = row_of_tile(tile);
     const size_t rstep = (size_t)a.stride;
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (has_row && nchunk > 0) cur = ldg_nc_v4(row); // in flight while the warp waits for the coordinates
-    if (has_row && nchunk > 1) prefetch_l1(row + rstep);
+    // row words 0 and 1 are in flight while the warp waits for the coordinates
+    if (has_row) {
+      if (nchunk > 0) cp_async16(ering, row);
+      cp_async_commit();
+      if (nchunk > 1) cp_async16(ering + kForceThreads, row + rstep);
+      cp_async_commit();
+    }
     load_desc(k + 1);
     if (MODE == MODE_NVE && has_row) { prefetch_l1(nve.v + 3 * (size_t)i_cur); prefetch_l1(nve.v + 3 * (size_t)i_cur + 2); } // the epilogue's v
     if (producer) {
@@ -818,12 +862,13 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
     // one 16-byte word = 8 columns of the warp's schedule (n_cur is the same multiple of 8 in every lane of the warp)
     if (has_row) {
       for (int c = 0; c < nchunk; c++, row += rstep) {
-        if (c + 2 < nchunk) prefetch_l1(row + 2 * rstep);
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (c + 1 < nchunk) nxt = ldg_nc_v4(row + rstep);
+        cp_async_wait_1(); // word c has landed (word c+1 may still be in flight)
+        uint4 *slot = ering + (c & 1) * kForceThreads;
+        const uint4 cur = *slot;
+        if (c + 2 < nchunk) cp_async16(slot, row + 2 * rstep); // same thread: the read above precedes the asynchronous write
+        cp_async_commit();
         lj_quad<ONETYPE, ENERGY>(spb, st, cur.x, cur.y, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
         lj_quad<ONETYPE, ENERGY>(spb, st, cur.z, cur.w, x_i, y_i, z_i, type_i, one, tab, fx, fy, fz, pe);
-        cur = nxt;
       }
     }
     if (has_row) {
@@ -865,7 +910,8 @@ size_t lists_coords_bytes(int cap, int maxrow) { // region A of tiles_lists_kern
   return (std::max(coords, rows) + 15) / 16 * 16;
 }
 size_t lists_smem(int cap, int maxrow) { return lists_coords_bytes(cap, maxrow) + (size_t)16 * kRowThreads * sizeof(unsigned short); }
-size_t force_smem(int fcap, bool types, int nbuf) { return (size_t)nbuf * ((size_t)(fcap + kDummySlots) * 24 + (types ? (size_t)(fcap + kDummySlots) * sizeof(int) : 0)); }
+size_t force_coord_smem(int fcap, bool types, int nbuf) { return ((size_t)nbuf * ((size_t)(fcap + kDummySlots) * 24 + (types ? (size_t)(fcap + kDummySlots) * sizeof(int) : 0)) + 127) / 128 * 128; }
+size_t force_smem(int fcap, bool types, int nbuf) { return force_coord_smem(fcap, types, nbuf) + (size_t)2 * kForceThreads * sizeof(uint4); }
 
 } // namespace
 
@@ -886,6 +932,7 @@ struct emd_tiles {
   int *d_nell_s = nullptr; size_t nell_s_cap = 0;
   int *d_stg_j = nullptr; size_t stg_j_cap = 0;
   int *d_stg_n = nullptr; size_t stg_n_cap = 0;
+  int4 *d_rowdesc = nullptr; size_t rowdesc_cap = 0;
   unsigned short *d_int_slot = nullptr; size_t int_slot_cap = 0;
   int *d_int_glob = nullptr; size_t int_glob_cap = 0;
   int *d_order = nullptr; size_t order_cap = 0;
@@ -937,12 +984,13 @@ int launch_search(emd_ctx *ctx, emd_tiles *t) {
   if (ensure_bytes((void **)&t->d_nell_s, &t->nell_s_cap, rows * sizeof(int))) return 1;
   if (ensure_bytes((void **)&t->d_stg_j, &t->stg_j_cap, (size_t)t->ntiles * a.cap * sizeof(int))) return 1;
   if (ensure_bytes((void **)&t->d_stg_n, &t->stg_n_cap, (size_t)t->ntiles * sizeof(int))) return 1;
+  if (ensure_bytes((void **)&t->d_rowdesc, &t->rowdesc_cap, (size_t)t->ntiles * kMaxStagedRows * sizeof(int4))) return 1;
   if (ensure_bytes((void **)&t->d_int_slot, &t->int_slot_cap, rows * sizeof(unsigned short))) return 1;
   if (ensure_bytes((void **)&t->d_int_glob, &t->int_glob_cap, rows * sizeof(int))) return 1;
   if (ensure_bytes((void **)&t->d_order, &t->order_cap, (size_t)t->ntiles * sizeof(int))) return 1;
   if (ensure_bytes((void **)&t->d_has_ghost, &t->has_ghost_cap, (size_t)t->ntiles * sizeof(int))) return 1;
   a.ell = t->d_ell; a.nell = t->d_nell; a.csr16 = t->d_csr16; a.ncsr = t->d_ncsr; a.ell_s = t->d_ell_s; a.nell_s = t->d_nell_s;
-  a.stg_j = t->d_stg_j; a.stg_n = t->d_stg_n; a.int_slot = t->d_int_slot; a.int_glob = t->d_int_glob;
+  a.stg_j = t->d_stg_j; a.stg_n = t->d_stg_n; a.rowdesc = t->d_rowdesc; a.int_slot = t->d_int_slot; a.int_glob = t->d_int_glob;
   a.order = t->d_order; a.has_ghost = t->d_has_ghost; a.flags = t->d_flags;
   EMD_CUDA(cudaMemsetAsync(t->d_flags, 0, FL_COUNT * sizeof(int), ctx->stream));
   const size_t smem = (size_t)a.cap * sizeof(float4);
@@ -1059,7 +1107,7 @@ int emd_tiles_create(emd_tiles **out) {
 
 void emd_tiles_destroy(emd_tiles *t) {
   if (!t) return;
-  void *bufs[] = {t->d_ell, t->d_nell, t->d_csr16, t->d_ncsr, t->d_ell_s, t->d_nell_s, t->d_stg_j, t->d_stg_n, t->d_int_slot, t->d_int_glob,
+  void *bufs[] = {t->d_ell, t->d_nell, t->d_csr16, t->d_ncsr, t->d_ell_s, t->d_nell_s, t->d_stg_j, t->d_stg_n, t->d_rowdesc, t->d_int_slot, t->d_int_glob,
                   t->d_order, t->d_has_ghost, t->d_flags, t->d_tab};
   for (void *p : bufs) if (p) cudaFree(p);
   if (t->h_tab) cudaFreeHost(t->h_tab);
@@ -1259,7 +1307,7 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
 #define EMD_LJ_TILES(ONE, MD)                                                                                              \
   do {                                                                                                                     \
     if (set_smem(lj_tiles_kernel<ONE, MD>, smem)) return 1;                                                                \
-    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, MD>), grid, kForceThreads, smem, a, first, count, nbuf, p1, t->d_tab, d_f, partial, nve, gate); \
+    EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, MD>), grid, kForceThreads, smem, a, first, count, nbuf, (unsigned)force_coord_smem(a.fcap, !one, nbuf), p1, t->d_tab, d_f, partial, nve, gate); \
   } while (0)
   if (fuse) { if (one) EMD_LJ_TILES(true, MODE_NVE); else EMD_LJ_TILES(false, MODE_NVE); }
   else if (h_pe && force_too) { if (one) EMD_LJ_TILES(true, MODE_FORCE_ENERGY); else EMD_LJ_TILES(false, MODE_FORCE_ENERGY); }
