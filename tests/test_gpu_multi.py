@@ -16,8 +16,8 @@ def _ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def run(n, *args, port=29701):
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+def run(n, *args, port=29701, extra_env=None):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", **(extra_env or {}))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
                         "--master-port", str(port), "tests/mgpu_check.py", *map(str, args)], capture_output=True, text=True, env=env, cwd=REPO,
                        timeout=600)
@@ -30,3 +30,12 @@ def test_decomposed_run_matches_single_rank_oracle(emd, oracle_lib, n, args):
     if _ngpus() < n:
         pytest.skip(f"needs {n} GPUs")
     run(n, *args, port=29701 + n)
+
+
+@pytest.mark.parametrize("env", [{"EMD_HALO_GATE": "1"}, {"EMD_HALO_TRANSPORT": "nccl"}, {"EMD_NO_OVERLAP": "1"}])
+def test_decomposed_run_other_halo_schedules(emd, oracle_lib, env):
+    """the same parity bar for the schedules that are not the default: the force kernel waiting for the neighbours' arrival flags
+    itself (halo gate), NCCL send/recv groups instead of peer stores, and the blocking (not overlapped) refresh"""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    run(2, "lj", 12, 14, 14, 45, "half", port=29731, extra_env=env)
