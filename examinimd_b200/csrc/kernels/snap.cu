@@ -58,6 +58,7 @@ struct SnapTab {
   Triple triple[kMaxTriples];         // sorted by j
   int tri_begin[kMaxJ + 2];           // blocks of output level j: [tri_begin[j], tri_begin[j+1]) (twojmax = 8 list)
   short strip_j[kMaxStrips], strip_ma[kMaxStrips]; // output strips, most expensive first
+  int strip_seg[kMaxStrips + 1];                   // segments (YiSeg) of strip s: [strip_seg[s], strip_seg[s+1])
   int elem_of_type[kMaxTypesConst];
   double radelem[kMaxTypesConst], wjelem[kMaxTypesConst];
 };
@@ -99,6 +100,9 @@ struct emd_snap {
   SnapTab h;              // host copy of the tables
   SnapTab *d_tab = nullptr;
   double *d_betaj = nullptr;  // [nelements][ntriples]
+  int4 *d_segs = nullptr;     // YiSeg descriptors of snap_yi, strip after strip
+  double *d_steptab = nullptr; // Clebsch-Gordan factors of snap_yi's steps: [block][mb2][k], rows padded to an even length
+  int ntab = 0;
   int ncoeff = 0;
   // work arrays (grow-only)
   Scratch ulist, ylist, cnt, pair_i, pair_j, queue;
@@ -286,103 +290,114 @@ __global__ void __launch_bounds__(32 * kMaxCol) snap_ui_kernel(const SnapTab *__
 }
 
 // ------------------------------------------------------------------------------------ snap_yi
-// block = 32 atoms (lanes) x W warps.  Dynamic shared memory: sU [nuf][32] double2 (full U_tot of the batch).
+// block = 32 atoms (lanes) x W warps.  Dynamic shared memory: [front pad][sU [nuf][32] double2 = full U_tot of the batch][back
+// pad][step table of Clebsch-Gordan factors].
 //
 // Register tiling of compute_zi's inner loop (sna_impl.hpp:248-262).  A warp takes an output STRIP (j, ma) = all
-// NMB = j/2+1 values of mb at once.  For one row pair (ma1, ma2) of a block (j1,j2,j) the products are
-//     z(mb) += cg(mb1, mb2) u_j1(ma1, mb1) u_j2(ma2, mb2),   mb2 = mb + C - mb1,  C = (j1+j2-j)/2,
-// so while mb1 walks up its row, the NMB elements of the other row that the strip needs form a WINDOW that slides
-// down by one element per step: one new element of each row is read from shared memory per step and feeds NMB
-// products (2 LDS.128 per 6*NMB FP64 instructions instead of 2 per 6), the Clebsch-Gordan factors are consecutive
-// constant-memory words fetched through the uniform datapath.  Measured history at 250 000 atoms: plain loop nest
-// 14.5 ms (shared-memory bound, 60 % LSU / 23 % FP64 pipe); fully unrolled per-block code (125 template
-// instantiations, 380 KB of SASS) 24 ms free-running and 13.5 ms with the warps held on one block by barriers
-// (instruction-fetch bound: 18 no-instruction stalls per issue); this generic sliding window: see profiles/.
+// NMB = j/2+1 values of mb at once.  For one row pair (ma1, ma2) of a block (j1,j2,j), j1 >= j2, the products are
+//     y(mb) += [beta cg(ma1,ma2)] cg(mb1, mb2) u_j1(ma1, mb1) u_j2(ma2, mb2),   mb1 = mb + C - mb2,  C = (j1+j2-j)/2.
+// The SHORT row (j2) is the one that is stepped through: mb2 = 0 .. min(j2, C+NMB-1); the NMB elements of the long row
+// that the strip needs at one step form a WINDOW that slides down by one element per step (a ring of NMB registers, the
+// step loop unrolled NMB-fold so that every slot index is a compile-time constant).  Per step: one new element of each
+// row (2 LDS.128), the NMB coefficients of the step as one aligned row of the step table (ceil(NMB/2) broadcast LDS.128;
+// a coefficient of an (mb1, mb2) outside the block is stored as 0, so the window is filled without range tests: what it
+// reads outside its row is some other finite element of sU or the zeroed pad), 2 + 6 NMB FP64 instructions.  The factor
+// beta*cg(ma1,ma2) of the row pair is folded into the stepped element, so the strip accumulates straight into its NMB
+// outputs.  Everything that depends only on (strip, block) -- row offsets, strides, trip counts, table offset -- comes from
+// a segment descriptor built at emd_snap_create (32 bytes, warp-uniform, fetched one segment ahead).
+//
+// History at 250 000 atoms (profiles/): plain loop nest 14.5 ms (shared-memory bound); fully unrolled per-block code (125
+// instantiations, 380 KB of SASS) 13.5-24 ms (instruction-fetch bound); round 1's sliding window over the long row with
+// the coefficients as indexed constant loads 10.7 ms: FP64 pipe 42 % busy, every term waited for its own LDC (one
+// register pair for c at the 128-register cap) and a third of the executed terms were zero padding of the union range.
+// Stepping the short row executes 45 656 instead of 51 476 terms per atom (38 358 are non-zero).
 constexpr int kYiWarps = 16;
 constexpr int kNumCg = 4098; // see snap_triples.inc
-constexpr int kCgPad = 8;    // zero words before and after the table: a strip's window may look up to 4 words outside a block row
+constexpr int kCgPad = 8;
 __constant__ double c_cg[kNumCg + 2 * kCgPad]; // compact Clebsch-Gordan blocks for twojmax = 8 (a 2J = 6 run uses a subset)
+constexpr int kYiFrontPad = 16, kYiBackPad = 8; // elements ([32] double2 each) before / after sU
+
+struct __align__(16) YiSeg {
+  int a_off;       // long row: element index (in sU) of the window's slot 0 at step 0, (j1, ma1lo, mb1 = C)
+  int w_off;       // short row: element index of (j2, ma2 of ma1lo, mb2 = 0)
+  int tab_off;     // step table: index (in doubles) of the block's row of step 0
+  int cga_idx;     // c_cg index of cg(ma1lo, ma2)
+  short a_stride;  // j1 + 1: next ma1
+  short w_stride;  // -(j2 + 1): ma2 decreases as ma1 increases
+  short cga_stride; // j2
+  short tab_stride; // doubles per step row (NMB of the block's j rounded up to even)
+  short nrows, nsteps, tr, pad;
+};
+static_assert(sizeof(YiSeg) == 32, "YiSeg is read as two 16-byte words");
 
 template <int NMB>
-__device__ __forceinline__ void z_block(const double2 *__restrict__ U, const SnapTab &t, int tr, int J, int ma, double bj,
-                                        double (&yr)[kMaxCol], double (&yi)[kMaxCol]) {
-  const int j1 = t.triple[tr].j1, j2 = t.triple[tr].j2, cgoff = t.triple[tr].cgoff + kCgPad;
-  const int C = (j1 + j2 - J) / 2;
-  const int lo1 = max(0, C - j2), hi1 = min(j1, C + NMB - 1); // union of the mb1 ranges of the strip's outputs
-  const int ma1lo = max(0, (2 * ma - J - j2 + j1) / 2), ma1hi = min(j1, (2 * ma - J + j2 + j1) / 2);
-  double zr[NMB], zi[NMB];
-#pragma unroll
-  for (int k = 0; k < NMB; k++) { zr[k] = 0.0; zi[k] = 0.0; }
-  for (int ma1 = ma1lo; ma1 <= ma1hi; ma1++) {
-    const int ma2 = (2 * ma - J - (2 * ma1 - j1) + j2) / 2;
-    const double2 *r1 = U + (size_t)(t.uf_block[j1] + ma1 * (j1 + 1) + lo1) * 32; // next element of row 1 (walks up)
-    const double2 *r2 = U + (size_t)(t.uf_block[j2] + ma2 * (j2 + 1)) * 32;
-    const double cga = c_cg[cgoff + ma1 * (j2 + 1) + ma2];
-    // The window is a ring of NMB registers: at step s = mb1 - lo1 output k reads slot (k - s) mod NMB, which holds
-    // u_j2(ma2, k + C - mb1); elements outside 0..j2 are zero (their products vanish).  The mb1 loop is unrolled NMB-fold
-    // so every slot index is a compile-time constant and nothing is ever moved.
+__device__ __forceinline__ void z_segment(const double2 *__restrict__ U, const double *__restrict__ s_tab, const YiSeg &g, double bj,
+                                          double (&yr)[kMaxCol], double (&yi)[kMaxCol]) {
+  constexpr int NC2 = (NMB + 1) / 2;
+  const double2 *arow = U + (size_t)g.a_off * 32;
+  const double2 *wrow = U + (size_t)g.w_off * 32;
+  int cga_idx = g.cga_idx;
+  for (int row = 0; row < g.nrows; row++) {
+    double sc = bj * c_cg[cga_idx];
+    asm volatile("" : "+d"(sc)); // keep it in its register (the compiler would re-load and re-multiply it in every step)
     double2 w[NMB];
 #pragma unroll
-    for (int k = 0; k < NMB; k++) {
-      const int mb2 = k + C - lo1;
-      w[k] = (mb2 >= 0 && mb2 <= j2) ? r2[mb2 * 32] : make_double2(0.0, 0.0);
-    }
-    int nb2 = C - lo1 - 1;                      // row-2 index entering the window after the current step
-    const double2 *r2n = r2 + nb2 * 32;
-    const double *pc = c_cg + cgoff + lo1 * j2 + C; // cg(mb1, k + C - mb1), k = 0..NMB-1: consecutive words; advances by j2 per step
-    double sr[NMB], si[NMB];
+    for (int k = 0; k < NMB; k++) w[k] = arow[k * 32];
+    const double2 *an = arow - 32;   // element entering the window after the current step
+    const double2 *wp = wrow;
+    const double2 *tp = reinterpret_cast<const double2 *>(s_tab + g.tab_off);
+    // operands of a step are fetched one step ahead (the fetch past the last step lands in a pad or a neighbouring row)
+    double2 e_next = *wp, a_next = *an, c_next[NC2];
 #pragma unroll
-    for (int k = 0; k < NMB; k++) { sr[k] = 0.0; si[k] = 0.0; }
-    // ncu (profiles/r01e_snap_ncu.csv, source page) puts 20 % of the kernel's stall samples on `pc += j2` (short scoreboard:
-    // the bump waits until the indexed constant loads of the step before have read their address register) and 8 % on the
-    // first use of `a`.  One address register per unrolled step (pcs[r], bumped once per group of NMB steps) and a one-step
-    // look-ahead for `a` (the element after the last one of a row is read and never used; sU carries a pad for the very
-    // last row) bought only 1.5 % (10.83 -> 10.67 ms at 250 000 atoms, gpurun r01v): the stall moves, the 4 warps per
-    // scheduler that 146 KB of U_tot and 128 registers allow cannot hide it.
-    double2 a_next = *r1;
-    for (int mb1 = lo1; mb1 <= hi1; mb1 += NMB) {
-      const double *pcs[NMB];
-#pragma unroll
-      for (int r = 0; r < NMB; r++) pcs[r] = pc + r * j2;
+    for (int q = 0; q < NC2; q++) c_next[q] = tp[q];
+    for (int s0 = 0; s0 < g.nsteps; s0 += NMB) {
 #pragma unroll
       for (int r = 0; r < NMB; r++) {
-        if (mb1 + r <= hi1) {
-          const double2 a = a_next;
-          r1 += 32;
-          a_next = *r1;
+        if (s0 + r < g.nsteps) {
+          double2 c2[NC2];
+#pragma unroll
+          for (int q = 0; q < NC2; q++) c2[q] = c_next[q];
+          const double2 a_new = a_next;
+          const double2 e = make_double2(sc * e_next.x, sc * e_next.y);
+          wp += 32; an -= 32;
+          tp = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(tp) + g.tab_stride);
+          e_next = *wp; a_next = *an;
+#pragma unroll
+          for (int q = 0; q < NC2; q++) c_next[q] = tp[q];
 #pragma unroll
           for (int k = 0; k < NMB; k++) {
-            const double2 wk = w[(k - r + NMB) % NMB];
-            const double c = pcs[r][k];
-            sr[k] += c * (a.x * wk.x - a.y * wk.y);
-            si[k] += c * (a.x * wk.y + a.y * wk.x);
+            const double2 a = w[(k - r + NMB) % NMB];
+            const double c = (k & 1) ? c2[k >> 1].y : c2[k >> 1].x;
+            yr[k] += c * (e.x * a.x - e.y * a.y);
+            yi[k] += c * (e.x * a.y + e.y * a.x);
           }
-          // the slot of output NMB-1 is free now: it receives the element output 0 needs at the next step
-          w[(NMB - 1 - r + NMB) % NMB] = (nb2 >= 0 && nb2 <= j2) ? *r2n : make_double2(0.0, 0.0);
-          r2n -= 32; nb2--;
+          w[(NMB - 1 - r + NMB) % NMB] = a_new; // the slot of output NMB-1 is free: it receives what output 0 needs next
         }
       }
-      pc += NMB * j2;
     }
-#pragma unroll
-    for (int k = 0; k < NMB; k++) { zr[k] += cga * sr[k]; zi[k] += cga * si[k]; }
+    arow += g.a_stride * 32;
+    wrow += g.w_stride * 32;
+    cga_idx += g.cga_stride;
   }
-#pragma unroll
-  for (int k = 0; k < NMB; k++) { yr[k] += bj * zr[k]; yi[k] += bj * zi[k]; }
 }
 
 __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ betaj,
+                                                                const int4 *__restrict__ segs, const double *__restrict__ steptab, int ntab,
                                                                 const int *__restrict__ type, int n_local, const double2 *__restrict__ ulist,
                                                                 int ustride, double2 *__restrict__ ylist) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_next;
   const SnapTab &t = *tab;
-  double2 *sU = reinterpret_cast<double2 *>(dyn);
+  double2 *sU = reinterpret_cast<double2 *>(dyn) + kYiFrontPad * 32;
+  double *s_tab = reinterpret_cast<double *>(sU + ((size_t)t.nuf + kYiBackPad) * 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const bool valid = i < n_local;
   const int twojmax = t.twojmax;
   if (threadIdx.x == 0) s_next = 0;
+  for (int k = threadIdx.x; k < kYiFrontPad * 32; k += blockDim.x) sU[k - kYiFrontPad * 32] = make_double2(0.0, 0.0);
+  for (int k = threadIdx.x; k < kYiBackPad * 32; k += blockDim.x) sU[(size_t)t.nuf * 32 + k] = make_double2(0.0, 0.0);
+  for (int k = threadIdx.x; k < ntab; k += blockDim.x) s_tab[k] = steptab[k];
   // expand the half range to the full (ma,mb) range with the inversion symmetry
   for (int j = 0; j <= twojmax; j++) {
     const int nhalf = (j / 2 + 1) * (j + 1);
@@ -407,21 +422,33 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
     s = __shfl_sync(0xffffffffu, s, 0);
     if (s >= t.nstrips) break;
     const int J = t.strip_j[s], ma = t.strip_ma[s];
+    // even J, ma below the diagonal of the middle column: that output has weight 0 in the contraction, leave it out
+    const int nmb = J / 2 + 1 - ((J % 2 == 0 && ma > J / 2) ? 1 : 0);
     double yr[kMaxCol], yi[kMaxCol];
 #pragma unroll
     for (int mb = 0; mb < kMaxCol; mb++) { yr[mb] = 0.0; yi[mb] = 0.0; }
-    for (int tr = t.tri_begin[J]; tr < t.tri_begin[J + 1]; tr++) {
-      if (t.triple[tr].j1 > twojmax) continue; // blocks of the 2J = 8 table that a smaller twojmax does not have
-      const double bj = beta_i[tr];
-      // even J, ma below the diagonal of the middle column: that output has weight 0 in the contraction, leave it out
-      switch (J / 2 + 1 - ((J % 2 == 0 && ma > J / 2) ? 1 : 0)) {
-        case 0: break;
-        case 1: z_block<1>(U, t, tr, J, ma, bj, yr, yi); break;
-        case 2: z_block<2>(U, t, tr, J, ma, bj, yr, yi); break;
-        case 3: z_block<3>(U, t, tr, J, ma, bj, yr, yi); break;
-        case 4: z_block<4>(U, t, tr, J, ma, bj, yr, yi); break;
-        default: z_block<5>(U, t, tr, J, ma, bj, yr, yi); break;
+    const int sbeg = t.strip_seg[s], send = t.strip_seg[s + 1];
+    YiSeg g;
+    if (sbeg < send) {
+      reinterpret_cast<int4 *>(&g)[0] = __ldg(segs + 2 * sbeg);
+      reinterpret_cast<int4 *>(&g)[1] = __ldg(segs + 2 * sbeg + 1);
+    }
+    for (int q = sbeg; q < send; q++) {
+      YiSeg gn = g;
+      if (q + 1 < send) { // the next descriptor travels while this segment runs
+        reinterpret_cast<int4 *>(&gn)[0] = __ldg(segs + 2 * (q + 1));
+        reinterpret_cast<int4 *>(&gn)[1] = __ldg(segs + 2 * (q + 1) + 1);
       }
+      const double bj = beta_i[g.tr];
+      switch (nmb) {
+        case 0: break;
+        case 1: z_segment<1>(U, s_tab, g, bj, yr, yi); break;
+        case 2: z_segment<2>(U, s_tab, g, bj, yr, yi); break;
+        case 3: z_segment<3>(U, s_tab, g, bj, yr, yi); break;
+        case 4: z_segment<4>(U, s_tab, g, bj, yr, yi); break;
+        default: z_segment<5>(U, s_tab, g, bj, yr, yi); break;
+      }
+      g = gn;
     }
     if (valid) {
       double2 *Y = ylist + (size_t)i * t.nuh + t.uh_block[J] + ma;
@@ -587,7 +614,7 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
 }
 
 size_t ui_smem(const SnapTab &h) { return ((size_t)h.nuh * 32 + (size_t)kMaxJ * 32 * h.ncol) * sizeof(double2); }
-size_t yi_smem(const SnapTab &h) { return ((size_t)h.nuf + 8) * 32 * sizeof(double2); } // + pad: z_block prefetches one element past a row
+size_t yi_smem(const SnapTab &h, int ntab) { return ((size_t)h.nuf + kYiFrontPad + kYiBackPad) * 32 * sizeof(double2) + sizeof(double) * (size_t)ntab; }
 size_t de_smem(const SnapTab &h) { return ((size_t)kMaxJ * 4 * kDeThreads + (size_t)kDeStageAtoms * h.nuh) * sizeof(double2); }
 
 } // namespace
@@ -679,26 +706,60 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
       bj[t3] += b * ((j + 1) / (j2 + 1.0));
     }
   }
-  // output strips (j, ma) sorted by their Clebsch-Gordan term count, most expensive first
-  struct Strip { int j, ma; long cost; };
+  // snap_yi's step table: for block tI, step mb2 and output k the factor cg(mb1 = C + k - mb2, mb2), 0 outside the block
+  std::vector<double> steptab;
+  std::vector<int> tab_off(kMaxTriples, 0), tab_stride(kMaxTriples, 0);
+  for (int tI = 0; tI < kMaxTriples; tI++) {
+    const int j1 = full[tI].j1, j2 = full[tI].j2, j = full[tI].j, C = (j1 + j2 - j) / 2;
+    const int nk = (j / 2 + 1 + 1) / 2 * 2;
+    tab_off[tI] = (int)steptab.size(); tab_stride[tI] = nk;
+    for (int mb2 = 0; mb2 <= j2; mb2++)
+      for (int k = 0; k < nk; k++) {
+        const int mb1 = C + k - mb2;
+        steptab.push_back((k <= j / 2 && mb1 >= 0 && mb1 <= j1) ? cg[kTri[tI].cgoff + mb1 * (j2 + 1) + mb2] : 0.0);
+      }
+  }
+  for (int k = 0; k < 8; k++) steptab.push_back(0.0); // a step row is fetched whole
+  // output strips (j, ma) with their segments (one per block of level j that this twojmax has and that reaches row ma),
+  // sorted by FP64 instruction count, most expensive first
+  struct Strip { int j, ma; long cost; std::vector<YiSeg> segs; };
   std::vector<Strip> strips;
   for (int j = 0; j <= J2; j++)
     for (int ma = 0; ma <= j; ma++) {
-      long cost = 0;
-      for (int tI = h.tri_begin[j]; tI < h.tri_begin[j + 1]; tI++) {
-        const int j1 = full[tI].j1, j2 = full[tI].j2;
+      Strip st{j, ma, 0, {}};
+      const int nmb = j / 2 + 1 - ((j % 2 == 0 && ma > j / 2) ? 1 : 0);
+      for (int tI = h.tri_begin[j]; tI < h.tri_begin[j + 1] && nmb > 0; tI++) {
+        const int j1 = full[tI].j1, j2 = full[tI].j2, C = (j1 + j2 - j) / 2;
         if (j1 > J2) continue;
-        const long na = imin(j1, (2 * ma - j + j2 + j1) / 2) - imax(0, (2 * ma - j - j2 + j1) / 2) + 1;
-        for (int mb = 0; 2 * mb <= j; mb++) {
-          const long nb = imin(j1, (2 * mb - j + j2 + j1) / 2) - imax(0, (2 * mb - j - j2 + j1) / 2) + 1;
-          cost += na * nb + na;
-        }
+        const int ma1lo = imax(0, ma + C - j2), ma1hi = imin(j1, ma + C); // 0 <= ma2 = ma + C - ma1 <= j2
+        if (ma1hi < ma1lo) continue;
+        const int ma2 = ma + C - ma1lo;
+        YiSeg g;
+        g.a_off = h.uf_block[j1] + ma1lo * (j1 + 1) + C;
+        g.w_off = h.uf_block[j2] + ma2 * (j2 + 1);
+        g.tab_off = tab_off[tI];
+        g.cga_idx = kCgPad + kTri[tI].cgoff + ma1lo * (j2 + 1) + ma2;
+        g.a_stride = (short)(j1 + 1); g.w_stride = (short)-(j2 + 1); g.cga_stride = (short)j2; g.tab_stride = (short)tab_stride[tI];
+        g.nrows = (short)(ma1hi - ma1lo + 1); g.nsteps = (short)(imin(j2, C + nmb - 1) + 1); g.tr = (short)tI; g.pad = 0;
+        st.cost += (long)g.nrows * (g.nsteps * (6 * nmb + 2) + 12) + 20;
+        st.segs.push_back(g);
       }
-      strips.push_back({j, ma, cost});
+      strips.push_back(st);
     }
   std::stable_sort(strips.begin(), strips.end(), [](const Strip &a, const Strip &b) { return a.cost > b.cost; });
   h.nstrips = (int)strips.size();
-  for (int k = 0; k < h.nstrips; k++) { h.strip_j[k] = (short)strips[k].j; h.strip_ma[k] = (short)strips[k].ma; }
+  std::vector<YiSeg> segs;
+  for (int k = 0; k < h.nstrips; k++) {
+    h.strip_j[k] = (short)strips[k].j; h.strip_ma[k] = (short)strips[k].ma; h.strip_seg[k] = (int)segs.size();
+    segs.insert(segs.end(), strips[k].segs.begin(), strips[k].segs.end());
+  }
+  h.strip_seg[h.nstrips] = (int)segs.size();
+  segs.push_back(YiSeg{}); // never empty
+  s->ntab = (int)steptab.size();
+  EMD_CUDA(cudaMalloc((void **)&s->d_segs, sizeof(YiSeg) * segs.size()));
+  EMD_CUDA(cudaMemcpy(s->d_segs, segs.data(), sizeof(YiSeg) * segs.size(), cudaMemcpyHostToDevice));
+  EMD_CUDA(cudaMalloc((void **)&s->d_steptab, sizeof(double) * steptab.size()));
+  EMD_CUDA(cudaMemcpy(s->d_steptab, steptab.data(), sizeof(double) * steptab.size(), cudaMemcpyHostToDevice));
 
   EMD_CUDA(cudaMalloc((void **)&s->d_tab, sizeof(SnapTab)));
   EMD_CUDA(cudaMemcpy(s->d_tab, &h, sizeof(SnapTab), cudaMemcpyHostToDevice));
@@ -712,9 +773,9 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
   int dev = 0;
   EMD_CUDA(cudaGetDevice(&dev));
   EMD_CUDA(cudaDeviceGetAttribute(&s->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (yi_smem(h) > (size_t)s->max_smem_optin) { set_error("emd_snap_create: U_tot batch does not fit in shared memory"); delete s; return 1; }
+  if (yi_smem(h, s->ntab) > (size_t)s->max_smem_optin) { set_error("emd_snap_create: U_tot batch does not fit in shared memory"); delete s; return 1; }
   EMD_CUDA(cudaFuncSetAttribute(snap_ui_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ui_smem(h)));
-  EMD_CUDA(cudaFuncSetAttribute(snap_yi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yi_smem(h)));
+  EMD_CUDA(cudaFuncSetAttribute(snap_yi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yi_smem(h, s->ntab)));
   EMD_CUDA(cudaFuncSetAttribute(snap_deidrj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)de_smem(h)));
   *out = s;
   return 0;
@@ -724,6 +785,8 @@ void emd_snap_destroy(emd_snap *s) {
   if (!s) return;
   if (s->d_tab) cudaFree(s->d_tab);
   if (s->d_betaj) cudaFree(s->d_betaj);
+  if (s->d_segs) cudaFree(s->d_segs);
+  if (s->d_steptab) cudaFree(s->d_steptab);
   s->ulist.release(); s->ylist.release(); s->cnt.release(); s->pair_i.release(); s->pair_j.release(); s->queue.release();
   delete s;
 }
@@ -777,7 +840,8 @@ int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const i
   double2 *ulist = s->ulist.as<double2>(), *ylist = s->ylist.as<double2>();
   const int nbatch = grid_for(n_local, 32);
   EMD_LAUNCH(ctx, snap_ui_kernel, nbatch, 32 * h.ncol, ui_smem(h), s->d_tab, d_x, d_type, n_local, cnt, pair_j, ulist, s->ucap);
-  EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h), s->d_tab, s->d_betaj, d_type, n_local, ulist, s->ucap, ylist);
+  EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h, s->ntab), s->d_tab, s->d_betaj, s->d_segs, s->d_steptab, s->ntab, d_type, n_local,
+             ulist, s->ucap, ylist);
   if (npairs > 0)
     EMD_LAUNCH(ctx, snap_deidrj_kernel, grid_for(npairs, kDeThreads), kDeThreads, de_smem(h), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
                ylist, d_f);
