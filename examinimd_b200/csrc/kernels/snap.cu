@@ -43,22 +43,23 @@ namespace {
 constexpr int kMaxJ = 8;              // twojmax <= 8
 constexpr int kMaxCol = kMaxJ / 2 + 1;
 constexpr int kMaxTriples = 125;
-constexpr int kMaxStrips = 45;
+constexpr int kMaxItems = 64;      // snap_yi work items: (group of one or two output rows) x (half of the blocks of its level)
 constexpr int kRootDim = kMaxJ + 2;   // rootpq[p][q], p,q in 0..twojmax+1
 constexpr double kPi = 3.14159265358979323846;
 
 struct Triple { short j1, j2, j, pad; int cgoff; };
 
 struct SnapTab {
-  int twojmax, ncol, nuh, nuf, ntriples, nstrips, ncg, ntypes, nelements, switchflag;
+  int twojmax, ncol, nuh, nuf, ntriples, nitems, ncg, ntypes, nelements, switchflag;
   double rcutfac, rfac0, rmin0, wself, cutsq;
   int uh_block[kMaxJ + 1];   // half layout: (j,mb,ma), mb <= j/2, at uh_block[j] + mb*(j+1) + ma
   int uf_block[kMaxJ + 1];   // full layout: (j,ma,mb) at uf_block[j] + ma*(j+1) + mb  (the reference's u(j,ma,mb))
   double rootpq[kRootDim * kRootDim];
   Triple triple[kMaxTriples];         // sorted by j
   int tri_begin[kMaxJ + 2];           // blocks of output level j: [tri_begin[j], tri_begin[j+1]) (twojmax = 8 list)
-  short strip_j[kMaxStrips], strip_ma[kMaxStrips]; // output strips, most expensive first
-  int strip_seg[kMaxStrips + 1];                   // segments (YiSeg) of strip s: [strip_seg[s], strip_seg[s+1])
+  // snap_yi work items, most expensive first: output rows (j, ma) [and (j, ma+1) if rows == 2], nmb outputs each, written to
+  // Y array `half`; segments (YiSeg) [seg[0],seg[1]) advance both rows at once, [seg[1],seg[2]) only the first, [seg[2],seg[3]) only the second
+  struct YiItem { short j, ma, rows, nmb, half, pad; int seg[4]; } item[kMaxItems];
   int elem_of_type[kMaxTypesConst];
   double radelem[kMaxTypesConst], wjelem[kMaxTypesConst];
 };
@@ -330,48 +331,60 @@ struct __align__(16) YiSeg {
 };
 static_assert(sizeof(YiSeg) == 32, "YiSeg is read as two 16-byte words");
 
-template <int NMB>
+// One segment: ROWS = 2 advances the output rows ma and ma+1 together (same ma1, hence the same window of the long row and
+// the same step factors; the stepped elements are those of ma2 and ma2+1); the product c*a is shared, so a term costs
+// (2 + 4 ROWS) / ROWS FP64 instructions.  Every operand of the next step is requested right after the last use of the
+// registers it lands in (the window slot of output NMB-1 first), so the loads of a step fly during the step before it
+// without a second set of registers.
+template <int NMB, int ROWS>
 __device__ __forceinline__ void z_segment(const double2 *__restrict__ U, const double *__restrict__ s_tab, const YiSeg &g, double bj,
-                                          double (&yr)[kMaxCol], double (&yi)[kMaxCol]) {
+                                          double (&y0r)[kMaxCol], double (&y0i)[kMaxCol], double (&y1r)[kMaxCol], double (&y1i)[kMaxCol]) {
   constexpr int NC2 = (NMB + 1) / 2;
-  const double2 *arow = U + (size_t)g.a_off * 32;
-  const double2 *wrow = U + (size_t)g.w_off * 32;
+  const double2 *arow = U + g.a_off * 32;
+  const double2 *wrow = U + g.w_off * 32;
+  const int row1 = -g.w_stride * 32; // the second output row reads the short row ma2 + 1
   int cga_idx = g.cga_idx;
   for (int row = 0; row < g.nrows; row++) {
-    double sc = bj * c_cg[cga_idx];
-    asm volatile("" : "+d"(sc)); // keep it in its register (the compiler would re-load and re-multiply it in every step)
-    double2 w[NMB];
+    double sc0 = bj * c_cg[cga_idx], sc1 = ROWS == 2 ? bj * c_cg[cga_idx + 1] : 0.0;
+    asm volatile("" : "+d"(sc0), "+d"(sc1)); // keep them in registers (the compiler would re-load and re-multiply them in every step)
+    double2 w[NMB], c2[NC2];
 #pragma unroll
     for (int k = 0; k < NMB; k++) w[k] = arow[k * 32];
     const double2 *an = arow - 32;   // element entering the window after the current step
     const double2 *wp = wrow;
     const double2 *tp = reinterpret_cast<const double2 *>(s_tab + g.tab_off);
-    // operands of a step are fetched one step ahead (the fetch past the last step lands in a pad or a neighbouring row)
-    double2 e_next = *wp, a_next = *an, c_next[NC2];
+    double2 r0 = wp[0], r1 = ROWS == 2 ? wp[row1] : make_double2(0.0, 0.0);
 #pragma unroll
-    for (int q = 0; q < NC2; q++) c_next[q] = tp[q];
+    for (int q = 0; q < NC2; q++) c2[q] = tp[q];
     for (int s0 = 0; s0 < g.nsteps; s0 += NMB) {
 #pragma unroll
       for (int r = 0; r < NMB; r++) {
         if (s0 + r < g.nsteps) {
-          double2 c2[NC2];
-#pragma unroll
-          for (int q = 0; q < NC2; q++) c2[q] = c_next[q];
-          const double2 a_new = a_next;
-          const double2 e = make_double2(sc * e_next.x, sc * e_next.y);
-          wp += 32; an -= 32;
+          const double2 e0 = make_double2(sc0 * r0.x, sc0 * r0.y);
+          double2 e1 = make_double2(0.0, 0.0);
+          if (ROWS == 2) e1 = make_double2(sc1 * r1.x, sc1 * r1.y);
+          wp += 32;
+          r0 = wp[0];
+          if (ROWS == 2) r1 = wp[row1];
           tp = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(tp) + g.tab_stride);
-          e_next = *wp; a_next = *an;
+          int done = 0;
 #pragma unroll
-          for (int q = 0; q < NC2; q++) c_next[q] = tp[q];
-#pragma unroll
-          for (int k = 0; k < NMB; k++) {
+          for (int kk = 0; kk < NMB; kk++) {
+            const int k = (kk + NMB - 1) % NMB; // NMB-1 first: its window slot is the one that is refilled
             const double2 a = w[(k - r + NMB) % NMB];
             const double c = (k & 1) ? c2[k >> 1].y : c2[k >> 1].x;
-            yr[k] += c * (e.x * a.x - e.y * a.y);
-            yi[k] += c * (e.x * a.y + e.y * a.x);
+            const double cax = c * a.x, cay = c * a.y;
+            y0r[k] = fma(e0.x, cax, y0r[k]); y0r[k] = fma(-e0.y, cay, y0r[k]);
+            y0i[k] = fma(e0.x, cay, y0i[k]); y0i[k] = fma(e0.y, cax, y0i[k]);
+            if (ROWS == 2) {
+              y1r[k] = fma(e1.x, cax, y1r[k]); y1r[k] = fma(-e1.y, cay, y1r[k]);
+              y1i[k] = fma(e1.x, cay, y1i[k]); y1i[k] = fma(e1.y, cax, y1i[k]);
+            }
+            if (kk == 0) { w[(NMB - 1 - r + NMB) % NMB] = *an; an -= 32; } // receives what output 0 needs at the next step
+            done |= 1 << k;
+            const int q = k >> 1, mate = k ^ 1;
+            if (mate >= NMB || (done >> mate & 1)) c2[q] = tp[q]; // both factors of the pair are used: fetch the next step's
           }
-          w[(NMB - 1 - r + NMB) % NMB] = a_new; // the slot of output NMB-1 is free: it receives what output 0 needs next
         }
       }
     }
@@ -381,10 +394,47 @@ __device__ __forceinline__ void z_segment(const double2 *__restrict__ U, const d
   }
 }
 
+__device__ __forceinline__ YiSeg load_seg(const int4 *__restrict__ segs, int q) {
+  YiSeg g;
+  reinterpret_cast<int4 *>(&g)[0] = __ldg(segs + 2 * q);
+  reinterpret_cast<int4 *>(&g)[1] = __ldg(segs + 2 * q + 1);
+  return g;
+}
+
+template <int NMB>
+__device__ __forceinline__ void yi_item(const double2 *__restrict__ U, const double *__restrict__ s_tab, const int4 *__restrict__ segs,
+                                        const double *__restrict__ beta_i, const int (&seg)[4], double (&y0r)[kMaxCol],
+                                        double (&y0i)[kMaxCol], double (&y1r)[kMaxCol], double (&y1i)[kMaxCol]) {
+  // the descriptor of the next segment travels while the current one runs (the list ends with a spare descriptor)
+  YiSeg g = load_seg(segs, seg[0]);
+  for (int q = seg[0]; q < seg[1]; q++) {
+    const YiSeg gn = load_seg(segs, q + 1);
+    z_segment<NMB, 2>(U, s_tab, g, beta_i[g.tr], y0r, y0i, y1r, y1i);
+    g = gn;
+  }
+  for (int pass = 0; pass < 2; pass++) { // segments that reach only one of the two rows: one copy of the code, summed into a scratch row
+    if (seg[1 + pass] == seg[2 + pass]) continue;
+    double tr[kMaxCol], ti[kMaxCol];
+#pragma unroll
+    for (int k = 0; k < kMaxCol; k++) { tr[k] = 0.0; ti[k] = 0.0; }
+    g = load_seg(segs, seg[1 + pass]);
+    for (int q = seg[1 + pass]; q < seg[2 + pass]; q++) {
+      const YiSeg gn = load_seg(segs, q + 1);
+      z_segment<NMB, 1>(U, s_tab, g, beta_i[g.tr], tr, ti, tr, ti);
+      g = gn;
+    }
+#pragma unroll
+    for (int k = 0; k < NMB; k++) {
+      if (pass == 0) { y0r[k] += tr[k]; y0i[k] += ti[k]; }
+      else { y1r[k] += tr[k]; y1i[k] += ti[k]; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ betaj,
                                                                 const int4 *__restrict__ segs, const double *__restrict__ steptab, int ntab,
                                                                 const int *__restrict__ type, int n_local, const double2 *__restrict__ ulist,
-                                                                int ustride, double2 *__restrict__ ylist) {
+                                                                int ustride, double2 *__restrict__ ylist, size_t yhalf) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_next;
   const SnapTab &t = *tab;
@@ -416,49 +466,36 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
   const double *beta_i = betaj + (size_t)elem_i * kMaxTriples;
   const double2 *U = sU + lane;
 
-  for (;;) { // strips (j, ma) from a queue sorted by cost, most expensive first
+  for (;;) { // work items from a queue sorted by cost, most expensive first
     int s = 0;
     if (lane == 0) s = atomicAdd(&s_next, 1);
     s = __shfl_sync(0xffffffffu, s, 0);
-    if (s >= t.nstrips) break;
-    const int J = t.strip_j[s], ma = t.strip_ma[s];
-    // even J, ma below the diagonal of the middle column: that output has weight 0 in the contraction, leave it out
-    const int nmb = J / 2 + 1 - ((J % 2 == 0 && ma > J / 2) ? 1 : 0);
-    double yr[kMaxCol], yi[kMaxCol];
+    if (s >= t.nitems) break;
+    const int J = t.item[s].j, ma = t.item[s].ma, rows = t.item[s].rows;
+    const int seg[4] = {t.item[s].seg[0], t.item[s].seg[1], t.item[s].seg[2], t.item[s].seg[3]};
+    double y0r[kMaxCol], y0i[kMaxCol], y1r[kMaxCol], y1i[kMaxCol];
 #pragma unroll
-    for (int mb = 0; mb < kMaxCol; mb++) { yr[mb] = 0.0; yi[mb] = 0.0; }
-    const int sbeg = t.strip_seg[s], send = t.strip_seg[s + 1];
-    YiSeg g;
-    if (sbeg < send) {
-      reinterpret_cast<int4 *>(&g)[0] = __ldg(segs + 2 * sbeg);
-      reinterpret_cast<int4 *>(&g)[1] = __ldg(segs + 2 * sbeg + 1);
-    }
-    for (int q = sbeg; q < send; q++) {
-      YiSeg gn = g;
-      if (q + 1 < send) { // the next descriptor travels while this segment runs
-        reinterpret_cast<int4 *>(&gn)[0] = __ldg(segs + 2 * (q + 1));
-        reinterpret_cast<int4 *>(&gn)[1] = __ldg(segs + 2 * (q + 1) + 1);
-      }
-      const double bj = beta_i[g.tr];
-      switch (nmb) {
-        case 0: break;
-        case 1: z_segment<1>(U, s_tab, g, bj, yr, yi); break;
-        case 2: z_segment<2>(U, s_tab, g, bj, yr, yi); break;
-        case 3: z_segment<3>(U, s_tab, g, bj, yr, yi); break;
-        case 4: z_segment<4>(U, s_tab, g, bj, yr, yi); break;
-        default: z_segment<5>(U, s_tab, g, bj, yr, yi); break;
-      }
-      g = gn;
+    for (int mb = 0; mb < kMaxCol; mb++) { y0r[mb] = 0.0; y0i[mb] = 0.0; y1r[mb] = 0.0; y1i[mb] = 0.0; }
+    switch (t.item[s].nmb) {
+      case 1: yi_item<1>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      case 2: yi_item<2>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      case 3: yi_item<3>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      case 4: yi_item<4>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      default: yi_item<5>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
     }
     if (valid) {
-      double2 *Y = ylist + (size_t)i * t.nuh + t.uh_block[J] + ma;
+      double2 *Y = ylist + t.item[s].half * yhalf + (size_t)i * t.nuh + t.uh_block[J] + ma;
 #pragma unroll
       for (int mb = 0; mb < kMaxCol; mb++)
         if (2 * mb <= J) {
           // half-column weights of compute_dbidrj (:393-424): 1, and on the middle column of even J: 1 above the
-          // diagonal, 1/2 on it, 0 below
-          const double w = (2 * mb < J) ? 1.0 : (ma < mb ? 1.0 : (ma == mb ? 0.5 : 0.0));
-          Y[mb * (J + 1)] = make_double2(w * yr[mb], w * yi[mb]);
+          // diagonal, 1/2 on it, 0 below (those outputs are not computed: nmb stops short of them)
+          const double w0 = (2 * mb < J) ? 1.0 : (ma < mb ? 1.0 : (ma == mb ? 0.5 : 0.0));
+          Y[mb * (J + 1)] = make_double2(w0 * y0r[mb], w0 * y0i[mb]);
+          if (rows == 2) {
+            const double w1 = (2 * mb < J) ? 1.0 : (ma + 1 < mb ? 1.0 : (ma + 1 == mb ? 0.5 : 0.0));
+            Y[mb * (J + 1) + 1] = make_double2(w1 * y1r[mb], w1 * y1i[mb]);
+          }
         }
     }
   }
@@ -501,7 +538,7 @@ __device__ __forceinline__ void du_level(double2 (&u)[kMaxJ + 1], double2 (&du)[
 __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ x,
                                                                  const int *__restrict__ type, const int *__restrict__ pair_i,
                                                                  const int *__restrict__ pair_j, int npairs,
-                                                                 const double2 *__restrict__ ylist, double *__restrict__ f) {
+                                                                 const double2 *__restrict__ ylist, size_t yhalf, double *__restrict__ f) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ double s_rootpq[kRootDim * kRootDim];
   const SnapTab &t = *tab;
@@ -509,20 +546,14 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
   // Pairs are sorted by their central atom, so the CTA's 128 pairs belong to a short run of consecutive atoms (7 at 18
   // in-cutoff neighbors): their Y rows (atom-major, 2.4 KB each) are staged in shared memory with one contiguous copy,
   // so the contraction reads Y at LDS latency.  (Reading Y from global at its point of use left the kernel
-  // latency-bound at 8 warps/SM: 2.5 long-scoreboard stalls per issue, 42 % FP64 pipe.)  Atoms beyond the staged
-  // run (very short rows) fall back to global loads.
+  // latency-bound at 8 warps/SM: 2.5 long-scoreboard stalls per issue, 42 % FP64 pipe.)  Y arrives as the two partial
+  // sums of snap_yi's item halves and is added up on the way in.  A run longer than the staging area (very short rows)
+  // is worked off in rounds.
   double2 *s_y = reinterpret_cast<double2 *>(dyn) + (size_t)kMaxJ * 4 * blockDim.x;
   const int p0 = blockIdx.x * blockDim.x;
   const int i_first = pair_i[p0], i_last = pair_i[min(p0 + (int)blockDim.x, npairs) - 1];
-  const int n_staged = min(i_last - i_first + 1, kDeStageAtoms);
-  {
-    const double2 *src = ylist + (size_t)i_first * t.nuh;
-    const int n = n_staged * t.nuh;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) s_y[k] = src[k];
-  }
-  __syncthreads();
-  const int p = p0 + threadIdx.x;
-  if (p >= npairs) return;
+  const bool active = p0 + (int)threadIdx.x < npairs;
+  const int p = active ? p0 + threadIdx.x : npairs - 1;
   double2 *boot = reinterpret_cast<double2 *>(dyn) + threadIdx.x;
   const int bs = blockDim.x;
   const int twojmax = t.twojmax, ncol = t.ncol;
@@ -560,56 +591,69 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
   db_r[1] += r0inv;
   const double sfac = sfac_of(t, r, rcut) * wj, dsfac = dsfac_of(t, r, rcut) * wj;
 
-  const double2 *Y = (i - i_first < n_staged) ? s_y + (size_t)(i - i_first) * t.nuh : ylist + (size_t)i * t.nuh;
-  double S0 = 0.0, S[3] = {0.0, 0.0, 0.0};
-  double2 u[kMaxJ + 1], du[3][kMaxJ + 1];
-  u[0] = make_double2(1.0, 0.0);
-#pragma unroll
-  for (int k = 0; k < 3; k++) du[k][0] = make_double2(0.0, 0.0);
-  S0 += Y[t.uh_block[0]].x; // level 0: u = 1, du = 0
-
-  for (int c = 0; c < ncol; c++) {
-    if (c > 0) {
-#pragma unroll
-      for (int ma = 0; ma <= kMaxJ; ma++)
-        if (ma <= 2 * c - 1) {
-          u[ma] = boot[(ma * 4 + 0) * bs];
-#pragma unroll
-          for (int k = 0; k < 3; k++) du[k][ma] = boot[(ma * 4 + 1 + k) * bs];
-        }
-    }
-    for (int jl = max(1, 2 * c); jl <= twojmax; jl++) {
-      du_level(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i, da_r, da_i, db_r, db_i);
-      const double2 *Yl = Y + t.uh_block[jl] + c * (jl + 1);
-#pragma unroll
-      for (int ma = 0; ma <= kMaxJ; ma++)
-        if (ma <= jl) {
-          const double2 y = Yl[ma];
-          S0 += u[ma].x * y.x + u[ma].y * y.y;
-#pragma unroll
-          for (int k = 0; k < 3; k++) S[k] += du[k][ma].x * y.x + du[k][ma].y * y.y;
-        }
-      if (jl == 2 * c + 1 && c + 1 < ncol) { // image that starts column c+1 (:840-864)
-#pragma unroll
-        for (int s = 0; s <= kMaxJ; s++)
-          if (s <= jl) {
-            const double sg = ((s + c) & 1) ? -1.0 : 1.0;
-            boot[((jl - s) * 4 + 0) * bs] = make_double2(sg * u[s].x, -sg * u[s].y);
-#pragma unroll
-            for (int k = 0; k < 3; k++) boot[((jl - s) * 4 + 1 + k) * bs] = make_double2(sg * du[k][s].x, -sg * du[k][s].y);
-          }
+  for (int base = 0; base <= i_last - i_first; base += kDeStageAtoms) {
+    if (base > 0) __syncthreads();
+    {
+      const int n = min(i_last - i_first + 1 - base, kDeStageAtoms) * t.nuh;
+      const double2 *src = ylist + (size_t)(i_first + base) * t.nuh;
+      for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double2 y0 = src[k], y1 = src[yhalf + k];
+        s_y[k] = make_double2(y0.x + y1.x, y0.y + y1.y);
       }
     }
-  }
-  // dU_full = dsfac u uhat + sfac dU (:873-892); F_ij = 2 sum w Re(conj(dU_full) Y) + rij * (-1.5e6 / r^14) (force_snap_neigh_impl.h:698-711)
-  const double rsq7 = (rsq * rsq * rsq) * (rsq * rsq * rsq) * rsq;
-  const double fdivr = -1.5e6 / rsq7;
-  const double rij[3] = {dx, dy, dz};
+    __syncthreads();
+    if (!active || i - i_first < base || i - i_first >= base + kDeStageAtoms) continue;
+    const double2 *Y = s_y + (size_t)(i - i_first - base) * t.nuh;
+    double S0 = 0.0, S[3] = {0.0, 0.0, 0.0};
+    double2 u[kMaxJ + 1], du[3][kMaxJ + 1];
+    u[0] = make_double2(1.0, 0.0);
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const double fk = 2.0 * (dsfac * uhat[k] * S0 + sfac * S[k]) + rij[k] * fdivr;
-    atomicAdd(&f[3 * (size_t)i + k], fk);
-    atomicAdd(&f[3 * (size_t)j + k], -fk);
+    for (int k = 0; k < 3; k++) du[k][0] = make_double2(0.0, 0.0);
+    S0 += Y[t.uh_block[0]].x; // level 0: u = 1, du = 0
+
+    for (int c = 0; c < ncol; c++) {
+      if (c > 0) {
+#pragma unroll
+        for (int ma = 0; ma <= kMaxJ; ma++)
+          if (ma <= 2 * c - 1) {
+            u[ma] = boot[(ma * 4 + 0) * bs];
+#pragma unroll
+            for (int k = 0; k < 3; k++) du[k][ma] = boot[(ma * 4 + 1 + k) * bs];
+          }
+      }
+      for (int jl = max(1, 2 * c); jl <= twojmax; jl++) {
+        du_level(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i, da_r, da_i, db_r, db_i);
+        const double2 *Yl = Y + t.uh_block[jl] + c * (jl + 1);
+#pragma unroll
+        for (int ma = 0; ma <= kMaxJ; ma++)
+          if (ma <= jl) {
+            const double2 y = Yl[ma];
+            S0 += u[ma].x * y.x + u[ma].y * y.y;
+#pragma unroll
+            for (int k = 0; k < 3; k++) S[k] += du[k][ma].x * y.x + du[k][ma].y * y.y;
+          }
+        if (jl == 2 * c + 1 && c + 1 < ncol) { // image that starts column c+1 (:840-864)
+#pragma unroll
+          for (int s = 0; s <= kMaxJ; s++)
+            if (s <= jl) {
+              const double sg = ((s + c) & 1) ? -1.0 : 1.0;
+              boot[((jl - s) * 4 + 0) * bs] = make_double2(sg * u[s].x, -sg * u[s].y);
+#pragma unroll
+              for (int k = 0; k < 3; k++) boot[((jl - s) * 4 + 1 + k) * bs] = make_double2(sg * du[k][s].x, -sg * du[k][s].y);
+            }
+        }
+      }
+    }
+    // dU_full = dsfac u uhat + sfac dU (:873-892); F_ij = 2 sum w Re(conj(dU_full) Y) + rij * (-1.5e6 / r^14) (force_snap_neigh_impl.h:698-711)
+    const double rsq7 = (rsq * rsq * rsq) * (rsq * rsq * rsq) * rsq;
+    const double fdivr = -1.5e6 / rsq7;
+    const double rij[3] = {dx, dy, dz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double fk = 2.0 * (dsfac * uhat[k] * S0 + sfac * S[k]) + rij[k] * fdivr;
+      atomicAdd(&f[3 * (size_t)i + k], fk);
+      atomicAdd(&f[3 * (size_t)j + k], -fk);
+    }
   }
 }
 
@@ -720,41 +764,85 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
       }
   }
   for (int k = 0; k < 8; k++) steptab.push_back(0.0); // a step row is fetched whole
-  // output strips (j, ma) with their segments (one per block of level j that this twojmax has and that reaches row ma),
-  // sorted by FP64 instruction count, most expensive first
-  struct Strip { int j, ma; long cost; std::vector<YiSeg> segs; };
-  std::vector<Strip> strips;
+  // snap_yi work items.  The rows ma = 0..j of level j are taken in pairs of equal output count (the rows below the diagonal
+  // of an even level's middle column have one output less); per block of the level, the ma1 range that reaches both rows of a
+  // pair becomes a two-row segment, what reaches only one of them a one-row segment.  Every group is split in two halves of
+  // equal cost by blocks, so that 16 warps find ~50 items of similar size; the halves write two Y arrays that snap_deidrj adds.
+  auto nmb_of = [](int j, int ma) { return j / 2 + 1 - ((j % 2 == 0 && ma > j / 2) ? 1 : 0); };
+  auto make_seg = [&](int tI, int j, int ma, int nmb, int lo, int hi) {
+    const int j1 = full[tI].j1, j2 = full[tI].j2, C = (j1 + j2 - j) / 2, ma2 = ma + C - lo;
+    YiSeg g;
+    g.a_off = h.uf_block[j1] + lo * (j1 + 1) + C;
+    g.w_off = h.uf_block[j2] + ma2 * (j2 + 1);
+    g.tab_off = tab_off[tI];
+    g.cga_idx = kCgPad + kTri[tI].cgoff + lo * (j2 + 1) + ma2;
+    g.a_stride = (short)(j1 + 1); g.w_stride = (short)-(j2 + 1); g.cga_stride = (short)j2; g.tab_stride = (short)tab_stride[tI];
+    g.nrows = (short)(hi - lo + 1); g.nsteps = (short)(imin(j2, C + nmb - 1) + 1); g.tr = (short)tI; g.pad = 0;
+    return g;
+  };
+  struct Item { int j, ma, rows, nmb, half; long cost; std::vector<YiSeg> seg[3]; };
+  std::vector<Item> items;
   for (int j = 0; j <= J2; j++)
-    for (int ma = 0; ma <= j; ma++) {
-      Strip st{j, ma, 0, {}};
-      const int nmb = j / 2 + 1 - ((j % 2 == 0 && ma > j / 2) ? 1 : 0);
-      for (int tI = h.tri_begin[j]; tI < h.tri_begin[j + 1] && nmb > 0; tI++) {
-        const int j1 = full[tI].j1, j2 = full[tI].j2, C = (j1 + j2 - j) / 2;
-        if (j1 > J2) continue;
-        const int ma1lo = imax(0, ma + C - j2), ma1hi = imin(j1, ma + C); // 0 <= ma2 = ma + C - ma1 <= j2
-        if (ma1hi < ma1lo) continue;
-        const int ma2 = ma + C - ma1lo;
-        YiSeg g;
-        g.a_off = h.uf_block[j1] + ma1lo * (j1 + 1) + C;
-        g.w_off = h.uf_block[j2] + ma2 * (j2 + 1);
-        g.tab_off = tab_off[tI];
-        g.cga_idx = kCgPad + kTri[tI].cgoff + ma1lo * (j2 + 1) + ma2;
-        g.a_stride = (short)(j1 + 1); g.w_stride = (short)-(j2 + 1); g.cga_stride = (short)j2; g.tab_stride = (short)tab_stride[tI];
-        g.nrows = (short)(ma1hi - ma1lo + 1); g.nsteps = (short)(imin(j2, C + nmb - 1) + 1); g.tr = (short)tI; g.pad = 0;
-        st.cost += (long)g.nrows * (g.nsteps * (6 * nmb + 2) + 12) + 20;
-        st.segs.push_back(g);
+    for (int ma = 0; ma <= j;) {
+      const int nmb = nmb_of(j, ma);
+      const int rows = (ma + 1 <= j && nmb_of(j, ma + 1) == nmb) ? 2 : 1;
+      if (nmb > 0) {
+        struct Blk { long cost; YiSeg seg[3]; bool has[3]; };
+        std::vector<Blk> blks;
+        for (int tI = h.tri_begin[j]; tI < h.tri_begin[j + 1]; tI++) {
+          const int j1 = full[tI].j1, j2 = full[tI].j2, C = (j1 + j2 - j) / 2;
+          if (j1 > J2) continue;
+          // 0 <= ma2 = ma + C - ma1 <= j2
+          const int lo0 = imax(0, ma + C - j2), hi0 = imin(j1, ma + C);
+          const int lo1 = rows == 2 ? imax(0, ma + 1 + C - j2) : 1, hi1 = rows == 2 ? imin(j1, ma + 1 + C) : 0;
+          const int plo = imax(lo0, lo1), phi = imin(hi0, hi1);
+          Blk bk{0, {}, {false, false, false}};
+          const int nsteps = imin(j2, C + nmb - 1) + 1;
+          if (plo <= phi) {
+            bk.seg[0] = make_seg(tI, j, ma, nmb, plo, phi); bk.has[0] = true;
+            bk.cost += (long)(phi - plo + 1) * (nsteps * (10 * nmb + 4) + 16) + 24;
+            // what is left of either range is one ma1 at its outer end
+            if (lo0 < plo) { bk.seg[1] = make_seg(tI, j, ma, nmb, lo0, plo - 1); bk.has[1] = true; }
+            if (hi0 > phi) { set_error("emd_snap_create: internal range error"); delete s; return 1; }
+            if (hi1 > phi) { bk.seg[2] = make_seg(tI, j, ma + 1, nmb, phi + 1, hi1); bk.has[2] = true; }
+            if (lo1 < plo) { set_error("emd_snap_create: internal range error"); delete s; return 1; }
+          } else {
+            if (lo0 <= hi0) { bk.seg[1] = make_seg(tI, j, ma, nmb, lo0, hi0); bk.has[1] = true; }
+            if (lo1 <= hi1) { bk.seg[2] = make_seg(tI, j, ma + 1, nmb, lo1, hi1); bk.has[2] = true; }
+          }
+          for (int k = 1; k < 3; k++)
+            if (bk.has[k]) bk.cost += (long)bk.seg[k].nrows * (nsteps * (6 * nmb + 2) + 16) + 24;
+          if (bk.has[0] || bk.has[1] || bk.has[2]) blks.push_back(bk);
+        }
+        std::stable_sort(blks.begin(), blks.end(), [](const Blk &x, const Blk &y) { return x.cost > y.cost; });
+        Item half[2];
+        for (int k = 0; k < 2; k++) half[k] = Item{j, ma, rows, nmb, k, 0, {}};
+        for (const Blk &bk : blks) {
+          Item &it = half[half[0].cost <= half[1].cost ? 0 : 1];
+          it.cost += bk.cost;
+          for (int k = 0; k < 3; k++)
+            if (bk.has[k]) it.seg[k].push_back(bk.seg[k]);
+        }
+        // both halves exist even when one is empty: every Y element of both arrays is written
+        items.push_back(half[0]); items.push_back(half[1]);
       }
-      strips.push_back(st);
+      ma += rows;
     }
-  std::stable_sort(strips.begin(), strips.end(), [](const Strip &a, const Strip &b) { return a.cost > b.cost; });
-  h.nstrips = (int)strips.size();
+  std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) { return x.cost > y.cost; });
+  if ((int)items.size() > kMaxItems) { set_error("emd_snap_create: too many snap_yi work items"); delete s; return 1; }
+  h.nitems = (int)items.size();
   std::vector<YiSeg> segs;
-  for (int k = 0; k < h.nstrips; k++) {
-    h.strip_j[k] = (short)strips[k].j; h.strip_ma[k] = (short)strips[k].ma; h.strip_seg[k] = (int)segs.size();
-    segs.insert(segs.end(), strips[k].segs.begin(), strips[k].segs.end());
+  for (int k = 0; k < h.nitems; k++) {
+    const Item &it = items[k];
+    h.item[k].j = (short)it.j; h.item[k].ma = (short)it.ma; h.item[k].rows = (short)it.rows; h.item[k].nmb = (short)it.nmb;
+    h.item[k].half = (short)it.half; h.item[k].pad = 0;
+    for (int q = 0; q < 3; q++) {
+      h.item[k].seg[q] = (int)segs.size();
+      segs.insert(segs.end(), it.seg[q].begin(), it.seg[q].end());
+    }
+    h.item[k].seg[3] = (int)segs.size();
   }
-  h.strip_seg[h.nstrips] = (int)segs.size();
-  segs.push_back(YiSeg{}); // never empty
+  segs.push_back(YiSeg{}); // the kernel fetches one descriptor ahead
   s->ntab = (int)steptab.size();
   EMD_CUDA(cudaMalloc((void **)&s->d_segs, sizeof(YiSeg) * segs.size()));
   EMD_CUDA(cudaMemcpy(s->d_segs, segs.data(), sizeof(YiSeg) * segs.size(), cudaMemcpyHostToDevice));
@@ -832,7 +920,7 @@ int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const i
   if (s->pair_i.ensure(sizeof(int) * ((size_t)npairs + 1)) || s->pair_j.ensure(sizeof(int) * ((size_t)npairs + 1))) return 1;
   if (n_local > s->ucap) {
     const int want = (n_local + n_local / 8 + 31) / 32 * 32;
-    if (s->ulist.ensure(sizeof(double2) * (size_t)h.nuh * want) || s->ylist.ensure(sizeof(double2) * (size_t)h.nuh * want)) { s->ucap = 0; return 1; }
+    if (s->ulist.ensure(sizeof(double2) * (size_t)h.nuh * want) || s->ylist.ensure(sizeof(double2) * (size_t)h.nuh * want * 2)) { s->ucap = 0; return 1; }
     s->ucap = want;
   }
   int *pair_i = s->pair_i.as<int>(), *pair_j = s->pair_j.as<int>();
@@ -841,10 +929,10 @@ int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const i
   const int nbatch = grid_for(n_local, 32);
   EMD_LAUNCH(ctx, snap_ui_kernel, nbatch, 32 * h.ncol, ui_smem(h), s->d_tab, d_x, d_type, n_local, cnt, pair_j, ulist, s->ucap);
   EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h, s->ntab), s->d_tab, s->d_betaj, s->d_segs, s->d_steptab, s->ntab, d_type, n_local,
-             ulist, s->ucap, ylist);
+             ulist, s->ucap, ylist, (size_t)h.nuh * s->ucap);
   if (npairs > 0)
     EMD_LAUNCH(ctx, snap_deidrj_kernel, grid_for(npairs, kDeThreads), kDeThreads, de_smem(h), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
-               ylist, d_f);
+               ylist, (size_t)h.nuh * s->ucap, d_f);
   return 0;
 }
 
