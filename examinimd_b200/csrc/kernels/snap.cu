@@ -198,16 +198,101 @@ __device__ __forceinline__ void u_level(double2 (&u)[kMaxJ + 1], int j, int mb, 
 // ------------------------------------------------------------------------------------ snap_ui
 // block = 32 atoms (lanes) x ncol warps (warp = column mb).  Dynamic shared memory:
 //   acc  [nuh][32] double2   U_tot accumulators of the batch (each warp touches only its column)
-//   boot [kMaxJ][blockDim] double2  hand-over of the inversion-symmetry image that starts the next column
+// A thread runs the recursion of TWO neighbors at a time (independent dependency chains: the kernel is bound by the
+// latency of the FP64 pipe at ~2.5 warps per scheduler, profiles/r02s1_snap_ncu.csv: `wait` 2.7 warps per issue) and
+// adds both to an accumulator with one read-modify-write.  The column loop is unrolled, so the inversion-symmetry image
+// that starts the next column is a reversal of the register array with static indices (no scratch memory).
+struct UiGeom { double a_r, a_i, b_r, b_i, sfac; };
+
+__device__ __forceinline__ UiGeom ui_geom(const SnapTab &t, const double *__restrict__ x, const int *__restrict__ type, int j, bool act,
+                                          double x_i, double y_i, double z_i, double rad_i) {
+  double dx = x[3 * (size_t)j] - x_i, dy = x[3 * (size_t)j + 1] - y_i, dz = x[3 * (size_t)j + 2] - z_i;
+  if (!act) { dx = 1.0; dy = 0.0; dz = 0.0; }
+  const int elem_j = t.elem_of_type[type[j]];
+  const double rcut = (rad_i + t.radelem[elem_j]) * t.rcutfac;
+  const double rsq = dx * dx + dy * dy + dz * dz;
+  const double r = sqrt(rsq);
+  const double theta0 = (r - t.rmin0) * t.rfac0 * kPi / (rcut - t.rmin0);
+  double sn, cs;
+  sincos(theta0, &sn, &cs);
+  const double z0 = r * cs / sn; // = r / tan(theta0), compute_ui :178
+  const double r0inv = 1.0 / sqrt(r * r + z0 * z0);
+  UiGeom g;
+  g.a_r = r0inv * z0; g.a_i = -r0inv * dz; g.b_r = r0inv * dy; g.b_i = -r0inv * dx;
+  g.sfac = act ? sfac_of(t, r, rcut) * t.wjelem[elem_j] : 0.0;
+  return g;
+}
+
+// inversion symmetry VMK 4.4(2) (:697-717): u(J, J-ma, J-mb) = (-1)^(ma+mb) conj(u(J, ma, mb)), J = 2c+1, mb = c: level J of
+// column c, reversed in place, is level J of column c+1
+template <int C>
+__device__ __forceinline__ void u_image(double2 (&u)[kMaxJ + 1]) {
+  constexpr int J = 2 * C + 1;
+#pragma unroll
+  for (int s = 0; s <= J / 2; s++) {
+    const double sg = ((s + C) & 1) ? -1.0 : 1.0, sh = ((J - s + C) & 1) ? -1.0 : 1.0;
+    const double2 lo = u[s], hi = u[J - s];
+    u[J - s] = make_double2(sg * lo.x, -sg * lo.y);
+    u[s] = make_double2(sh * hi.x, -sh * hi.y);
+  }
+}
+
+// one element of a level for both neighbors (two independent chains inside one guarded block), see u_level
+__device__ __forceinline__ double2 u_elem(const double2 (&u)[kMaxJ + 1], int ma, int j, double c1, double c2, const UiGeom &g) {
+  double nr = 0.0, ni = 0.0;
+  if (ma < j) {
+    nr = c1 * (g.a_r * u[ma].x + g.a_i * u[ma].y);
+    ni = c1 * (g.a_r * u[ma].y - g.a_i * u[ma].x);
+  }
+  if (ma > 0) {
+    nr -= c2 * (g.b_r * u[ma - 1].x + g.b_i * u[ma - 1].y);
+    ni -= c2 * (g.b_r * u[ma - 1].y - g.b_i * u[ma - 1].x);
+  }
+  return make_double2(nr, ni);
+}
+
+// column C: one copy of the level code for all columns (five unrolled copies left the kernel waiting for instructions:
+// 1.4 warps per issue in no_instruction); only the register reversal that starts the next column needs C at compile time
+__device__ __forceinline__ void ui_column(int C, const SnapTab &t, double2 *__restrict__ acc, const double *__restrict__ s_rootpq, int col, int lane,
+                                          double2 (&uA)[kMaxJ + 1], double2 (&uB)[kMaxJ + 1], const UiGeom &gA, const UiGeom &gB) {
+  const bool own = C == col;
+  const int jend = own ? t.twojmax : 2 * C + 1;
+  for (int jl = (C == 0 ? 1 : 2 * C); jl <= jend; jl++) {
+    double2 *q = acc + (size_t)(t.uh_block[jl] + col * (jl + 1)) * 32 + lane;
+    const double *rq = s_rootpq + (jl - C);
+#pragma unroll
+    for (int ma = kMaxJ; ma >= 0; --ma) // downwards: u_{j-1}(ma-1) is still the old value
+      if (ma <= jl) {
+        const double c1 = ma < jl ? rq[(jl - ma) * kRootDim] : 0.0, c2 = ma > 0 ? rq[ma * kRootDim] : 0.0;
+        const double2 nA = u_elem(uA, ma, jl, c1, c2, gA), nB = u_elem(uB, ma, jl, c1, c2, gB);
+        uA[ma] = nA;
+        uB[ma] = nB;
+        if (own) {
+          double2 v = q[ma * 32];
+          v.x += gA.sfac * nA.x + gB.sfac * nB.x;
+          v.y += gA.sfac * nA.y + gB.sfac * nB.y;
+          q[ma * 32] = v;
+        }
+      }
+  }
+  if (C < col) {
+    switch (C) {
+      case 0: u_image<0>(uA); u_image<0>(uB); break;
+      case 1: u_image<1>(uA); u_image<1>(uB); break;
+      case 2: u_image<2>(uA); u_image<2>(uB); break;
+      default: u_image<3>(uA); u_image<3>(uB); break;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(32 * kMaxCol) snap_ui_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ x,
                                                                const int *__restrict__ type, int n_local, const int *__restrict__ poff,
                                                                const int *__restrict__ pair_j, double2 *__restrict__ ulist, int ustride) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ double s_rootpq[kRootDim * kRootDim];
   const SnapTab &t = *tab;
-  const int twojmax = t.twojmax, nuh = t.nuh;
+  const int twojmax = t.twojmax;
   double2 *acc = reinterpret_cast<double2 *>(dyn);
-  double2 *boot = acc + (size_t)nuh * 32;
   const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
   for (int k = threadIdx.x; k < kRootDim * kRootDim; k += blockDim.x) s_rootpq[k] = t.rootpq[k];
   for (int j = 2 * col; j <= twojmax; j++)
@@ -218,65 +303,26 @@ __global__ void __launch_bounds__(32 * kMaxCol) snap_ui_kernel(const SnapTab *__
   const bool valid = i < n_local;
   const int ic = valid ? i : 0;
   const double x_i = x[3 * (size_t)ic], y_i = x[3 * (size_t)ic + 1], z_i = x[3 * (size_t)ic + 2];
-  const int elem_i = t.elem_of_type[type[ic]];
-  const double rad_i = t.radelem[elem_i];
+  const double rad_i = t.radelem[t.elem_of_type[type[ic]]];
   const int pbeg = valid ? poff[i] : 0, pcnt = valid ? poff[i + 1] - pbeg : 0;
   int nmax = pcnt;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
 
-  double2 u[kMaxJ + 1];
-  double2 *myboot = boot + threadIdx.x;
-  const int bstride = blockDim.x;
-  for (int k = 0; k < nmax; k++) {
-    const bool act = k < pcnt;
-    const int j = act ? pair_j[pbeg + k] : ic;
-    double dx = x[3 * (size_t)j] - x_i, dy = x[3 * (size_t)j + 1] - y_i, dz = x[3 * (size_t)j + 2] - z_i;
-    if (!act) { dx = 1.0; dy = 0.0; dz = 0.0; }
-    const int elem_j = t.elem_of_type[type[j]];
-    const double rcut = (rad_i + t.radelem[elem_j]) * t.rcutfac;
-    const double rsq = dx * dx + dy * dy + dz * dz;
-    const double r = sqrt(rsq);
-    const double theta0 = (r - t.rmin0) * t.rfac0 * kPi / (rcut - t.rmin0);
-    double sn, cs;
-    sincos(theta0, &sn, &cs);
-    const double z0 = r * cs / sn; // = r / tan(theta0), compute_ui :178
-    const double r0inv = 1.0 / sqrt(r * r + z0 * z0);
-    const double a_r = r0inv * z0, a_i = -r0inv * dz, b_r = r0inv * dy, b_i = -r0inv * dx;
-    const double sfac = act ? sfac_of(t, r, rcut) * t.wjelem[elem_j] : 0.0;
-
-    u[0] = make_double2(1.0, 0.0);
+  for (int k = 0; k < nmax; k += 2) {
+    const bool actA = k < pcnt, actB = k + 1 < pcnt;
+    const UiGeom gA = ui_geom(t, x, type, actA ? pair_j[pbeg + k] : ic, actA, x_i, y_i, z_i, rad_i);
+    const UiGeom gB = ui_geom(t, x, type, actB ? pair_j[pbeg + k + 1] : ic, actB, x_i, y_i, z_i, rad_i);
+    double2 uA[kMaxJ + 1], uB[kMaxJ + 1];
+    uA[0] = make_double2(1.0, 0.0);
+    uB[0] = make_double2(1.0, 0.0);
     if (col == 0) { // level 0 belongs to column 0 (add_uarraytot :612-635)
       double2 &q = acc[(size_t)t.uh_block[0] * 32 + lane];
-      q.x += sfac;
+      q.x += gA.sfac + gB.sfac;
     }
-    for (int c = 0; c <= col; c++) {
-      if (c > 0) { // level 2c-1 of column c = image of column c-1, written below
-#pragma unroll
-        for (int ma = 0; ma <= kMaxJ; ma++)
-          if (ma <= 2 * c - 1) u[ma] = myboot[ma * bstride];
-      }
-      const int jend = (c == col) ? twojmax : 2 * c + 1;
-      for (int jl = max(1, 2 * c); jl <= jend; jl++) {
-        u_level(u, jl, c, s_rootpq, a_r, a_i, b_r, b_i);
-        if (c == col) {
-          double2 *q = acc + (size_t)(t.uh_block[jl] + col * (jl + 1)) * 32 + lane;
-#pragma unroll
-          for (int ma = 0; ma <= kMaxJ; ma++)
-            if (ma <= jl) { double2 v = q[ma * 32]; v.x += sfac * u[ma].x; v.y += sfac * u[ma].y; q[ma * 32] = v; }
-        }
-      }
-      if (c < col) {
-        // inversion symmetry VMK 4.4(2) (:697-717): u(J, J-ma, J-mb) = (-1)^(ma+mb) conj(u(J, ma, mb)), J = 2c+1, mb = c
-        const int J = 2 * c + 1;
-#pragma unroll
-        for (int s = 0; s <= kMaxJ; s++)
-          if (s <= J) {
-            const double sg = ((s + c) & 1) ? -1.0 : 1.0;
-            myboot[(J - s) * bstride] = make_double2(sg * u[s].x, -sg * u[s].y);
-          }
-      }
-    }
+    // column c: levels 2c, 2c+1 re-derived by every warp of a later column (first level = image of column c-1), all
+    // remaining levels by its own warp
+    for (int c = 0; c <= col; c++) ui_column(c, t, acc, s_rootpq, col, lane, uA, uB, gA, gB);
   }
   // self term (addself_uarraytot :594-605) and write-out of this warp's column
   if (valid) {
@@ -657,7 +703,7 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
   }
 }
 
-size_t ui_smem(const SnapTab &h) { return ((size_t)h.nuh * 32 + (size_t)kMaxJ * 32 * h.ncol) * sizeof(double2); }
+size_t ui_smem(const SnapTab &h) { return (size_t)h.nuh * 32 * sizeof(double2); }
 size_t yi_smem(const SnapTab &h, int ntab) { return ((size_t)h.nuf + kYiFrontPad + kYiBackPad) * 32 * sizeof(double2) + sizeof(double) * (size_t)ntab; }
 size_t de_smem(const SnapTab &h) { return ((size_t)kMaxJ * 4 * kDeThreads + (size_t)kDeStageAtoms * h.nuh) * sizeof(double2); }
 
