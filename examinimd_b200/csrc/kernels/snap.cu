@@ -43,6 +43,7 @@ namespace {
 constexpr int kMaxJ = 8;              // twojmax <= 8
 constexpr int kMaxCol = kMaxJ / 2 + 1;
 constexpr int kMaxTriples = 125;
+constexpr int kMaxHalf = 155;       // U elements (j, mb <= j/2, ma) at twojmax = 8
 constexpr int kMaxItems = 64;      // snap_yi work items: (group of one or two output rows) x (half of the blocks of its level)
 constexpr int kRootDim = kMaxJ + 2;   // rootpq[p][q], p,q in 0..twojmax+1
 constexpr double kPi = 3.14159265358979323846;
@@ -60,6 +61,9 @@ struct SnapTab {
   // snap_yi work items, most expensive first: output rows (j, ma) [and (j, ma+1) if rows == 2], nmb outputs each, written to
   // Y array `half`; segments (YiSeg) [seg[0],seg[1]) advance both rows at once, [seg[1],seg[2]) only the first, [seg[2],seg[3]) only the second
   struct YiItem { short j, ma, rows, nmb, half, pad; int seg[4]; } item[kMaxItems];
+  // snap_yi's expansion of the half range to the full one: half element e goes to full element exp_dst[e] and, unless it lies
+  // on the middle column, its inversion image (conjugated, sign exp_img[e] < 0 ? -1 : +1) to |exp_img[e]| - 1
+  short exp_dst[kMaxHalf], exp_img[kMaxHalf];
   int elem_of_type[kMaxTypesConst];
   double radelem[kMaxTypesConst], wjelem[kMaxTypesConst];
 };
@@ -489,21 +493,30 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const bool valid = i < n_local;
-  const int twojmax = t.twojmax;
   if (threadIdx.x == 0) s_next = 0;
   for (int k = threadIdx.x; k < kYiFrontPad * 32; k += blockDim.x) sU[k - kYiFrontPad * 32] = make_double2(0.0, 0.0);
   for (int k = threadIdx.x; k < kYiBackPad * 32; k += blockDim.x) sU[(size_t)t.nuf * 32 + k] = make_double2(0.0, 0.0);
   for (int k = threadIdx.x; k < ntab; k += blockDim.x) s_tab[k] = steptab[k];
-  // expand the half range to the full (ma,mb) range with the inversion symmetry
-  for (int j = 0; j <= twojmax; j++) {
-    const int nhalf = (j / 2 + 1) * (j + 1);
-    for (int k = warp; k < nhalf; k += nwarps) {
-      const int mb = k / (j + 1), ma = k - mb * (j + 1);
-      const double2 v = valid ? ulist[(size_t)(t.uh_block[j] + k) * ustride + i] : make_double2(0.0, 0.0);
-      sU[(size_t)(t.uf_block[j] + ma * (j + 1) + mb) * 32 + lane] = v;
-      if (2 * mb != j) {
-        const double sg = ((ma + mb) & 1) ? -1.0 : 1.0;
-        sU[(size_t)(t.uf_block[j] + (j - ma) * (j + 1) + (j - mb)) * 32 + lane] = make_double2(sg * v.x, -sg * v.y);
+  // expand the half range to the full (ma,mb) range with the inversion symmetry: a warp requests all of its elements
+  // (at most kMaxHalf / kYiWarps + 1) before it stores the first one
+  {
+    constexpr int kPer = (kMaxHalf + kYiWarps - 1) / kYiWarps;
+    double2 v[kPer];
+#pragma unroll
+    for (int n = 0; n < kPer; n++) {
+      const int e = warp + n * nwarps;
+      v[n] = (valid && e < t.nuh) ? ulist[(size_t)e * ustride + i] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int n = 0; n < kPer; n++) {
+      const int e = warp + n * nwarps;
+      if (e < t.nuh) {
+        sU[(size_t)t.exp_dst[e] * 32 + lane] = v[n];
+        const int img = t.exp_img[e];
+        if (img != 0) {
+          const double sg = img < 0 ? -1.0 : 1.0;
+          sU[(size_t)(abs(img) - 1) * 32 + lane] = make_double2(sg * v[n].x, -sg * v[n].y);
+        }
       }
     }
   }
@@ -523,9 +536,9 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
 #pragma unroll
     for (int mb = 0; mb < kMaxCol; mb++) { y0r[mb] = 0.0; y0i[mb] = 0.0; y1r[mb] = 0.0; y1i[mb] = 0.0; }
     switch (t.item[s].nmb) {
-      case 1: yi_item<1>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
-      case 2: yi_item<2>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
-      case 3: yi_item<3>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      // levels j <= 3 (one or two outputs per row, 3 % of the terms) run the three-output code: what it adds to the outputs
+      // beyond the row's own is finite and never written; four instantiations less to keep in the instruction cache
+      case 1: case 2: case 3: yi_item<3>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
       case 4: yi_item<4>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
       default: yi_item<5>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
     }
@@ -642,9 +655,18 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
     {
       const int n = min(i_last - i_first + 1 - base, kDeStageAtoms) * t.nuh;
       const double2 *src = ylist + (size_t)(i_first + base) * t.nuh;
-      for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const double2 y0 = src[k], y1 = src[yhalf + k];
-        s_y[k] = make_double2(y0.x + y1.x, y0.y + y1.y);
+      for (int k0 = threadIdx.x; k0 < n; k0 += 4 * blockDim.x) { // eight loads in flight per thread (the copy was 8 % of the kernel's stall samples)
+        double2 y0[4], y1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int k = min(k0 + q * (int)blockDim.x, n - 1);
+          y0[q] = src[k]; y1[q] = src[yhalf + k];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int k = k0 + q * blockDim.x;
+          if (k < n) s_y[k] = make_double2(y0[q].x + y1[q].x, y0[q].y + y1[q].y);
+        }
       }
     }
     __syncthreads();
@@ -726,6 +748,14 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
   int nuh = 0, nuf = 0;
   for (int j = 0; j <= J2; j++) { h.uh_block[j] = nuh; nuh += (j / 2 + 1) * (j + 1); h.uf_block[j] = nuf; nuf += (j + 1) * (j + 1); }
   h.nuh = nuh; h.nuf = nuf;
+  for (int j = 0; j <= J2; j++)
+    for (int mb = 0; 2 * mb <= j; mb++)
+      for (int ma = 0; ma <= j; ma++) {
+        const int e = h.uh_block[j] + mb * (j + 1) + ma;
+        h.exp_dst[e] = (short)(h.uf_block[j] + ma * (j + 1) + mb);
+        const int img = h.uf_block[j] + (j - ma) * (j + 1) + (j - mb) + 1;
+        h.exp_img[e] = (short)(2 * mb == j ? 0 : (((ma + mb) & 1) ? -img : img));
+      }
   for (int pp = 1; pp <= J2; pp++) // init_rootpqarray, sna_impl.hpp:1053-1061
     for (int q = 1; q <= J2; q++) h.rootpq[pp * kRootDim + q] = sqrt(static_cast<double>(pp) / q);
   double rcutmax = 0.0; // force_snap_neigh_impl.h:321-329
