@@ -107,7 +107,7 @@ struct emd_snap {
   double *d_betaj = nullptr;  // [nelements][ntriples]
   int4 *d_segs = nullptr;     // YiSeg descriptors of snap_yi, strip after strip
   double *d_steptab = nullptr; // Clebsch-Gordan factors of snap_yi's steps: [block][mb2][k], rows padded to an even length
-  int ntab = 0;
+  int ntab = 0, nsegs = 0;
   int ncoeff = 0;
   // work arrays (grow-only)
   Scratch ulist, ylist, cnt, pair_i, pair_j, queue;
@@ -379,7 +379,6 @@ struct __align__(16) YiSeg {
   short tab_stride; // doubles per step row (NMB of the block's j rounded up to even)
   short nrows, nsteps, tr, pad;
 };
-static_assert(sizeof(YiSeg) == 32, "YiSeg is read as two 16-byte words");
 
 // One segment: ROWS = 2 advances the output rows ma and ma+1 together (same ma1, hence the same window of the long row and
 // the same step factors; the stepped elements are those of ma2 and ma2+1); the product c*a is shared, so a term costs
@@ -406,36 +405,34 @@ __device__ __forceinline__ void z_segment(const double2 *__restrict__ U, const d
     double2 r0 = wp[0], r1 = ROWS == 2 ? wp[row1] : make_double2(0.0, 0.0);
 #pragma unroll
     for (int q = 0; q < NC2; q++) c2[q] = tp[q];
-    for (int s0 = 0; s0 < g.nsteps; s0 += NMB) {
+#pragma unroll 1
+    for (int st = 0; st < g.nsteps; st++) { // not unrolled: the instruction cache decides this kernel (see the header)
+      const double2 e0 = make_double2(sc0 * r0.x, sc0 * r0.y);
+      double2 e1 = make_double2(0.0, 0.0);
+      if (ROWS == 2) e1 = make_double2(sc1 * r1.x, sc1 * r1.y);
+      wp += 32;
+      r0 = wp[0];
+      if (ROWS == 2) r1 = wp[row1];
+      const double2 a_new = *an; // what output 0 needs at the next step
+      an -= 32;
+      tp = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(tp) + g.tab_stride);
+      int done = 0;
 #pragma unroll
-      for (int r = 0; r < NMB; r++) {
-        if (s0 + r < g.nsteps) {
-          const double2 e0 = make_double2(sc0 * r0.x, sc0 * r0.y);
-          double2 e1 = make_double2(0.0, 0.0);
-          if (ROWS == 2) e1 = make_double2(sc1 * r1.x, sc1 * r1.y);
-          wp += 32;
-          r0 = wp[0];
-          if (ROWS == 2) r1 = wp[row1];
-          tp = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(tp) + g.tab_stride);
-          int done = 0;
-#pragma unroll
-          for (int kk = 0; kk < NMB; kk++) {
-            const int k = (kk + NMB - 1) % NMB; // NMB-1 first: its window slot is the one that is refilled
-            const double2 a = w[(k - r + NMB) % NMB];
-            const double c = (k & 1) ? c2[k >> 1].y : c2[k >> 1].x;
-            const double cax = c * a.x, cay = c * a.y;
-            y0r[k] = fma(e0.x, cax, y0r[k]); y0r[k] = fma(-e0.y, cay, y0r[k]);
-            y0i[k] = fma(e0.x, cay, y0i[k]); y0i[k] = fma(e0.y, cax, y0i[k]);
-            if (ROWS == 2) {
-              y1r[k] = fma(e1.x, cax, y1r[k]); y1r[k] = fma(-e1.y, cay, y1r[k]);
-              y1i[k] = fma(e1.x, cay, y1i[k]); y1i[k] = fma(e1.y, cax, y1i[k]);
-            }
-            if (kk == 0) { w[(NMB - 1 - r + NMB) % NMB] = *an; an -= 32; } // receives what output 0 needs at the next step
-            done |= 1 << k;
-            const int q = k >> 1, mate = k ^ 1;
-            if (mate >= NMB || (done >> mate & 1)) c2[q] = tp[q]; // both factors of the pair are used: fetch the next step's
-          }
+      for (int kk = 0; kk < NMB; kk++) {
+        const int k = NMB - 1 - kk; // downwards: the window moves up behind the terms
+        const double2 a = w[k];
+        const double c = (k & 1) ? c2[k >> 1].y : c2[k >> 1].x;
+        const double cax = c * a.x, cay = c * a.y;
+        y0r[k] = fma(e0.x, cax, y0r[k]); y0r[k] = fma(-e0.y, cay, y0r[k]);
+        y0i[k] = fma(e0.x, cay, y0i[k]); y0i[k] = fma(e0.y, cax, y0i[k]);
+        if (ROWS == 2) {
+          y1r[k] = fma(e1.x, cax, y1r[k]); y1r[k] = fma(-e1.y, cay, y1r[k]);
+          y1i[k] = fma(e1.x, cay, y1i[k]); y1i[k] = fma(e1.y, cax, y1i[k]);
         }
+        w[k] = k > 0 ? w[k - 1] : a_new; // output k's element of the next step is output k-1's of this one
+        done |= 1 << k;
+        const int q = k >> 1, mate = k ^ 1;
+        if (mate >= NMB || (done >> mate & 1)) c2[q] = tp[q]; // both factors of the pair are used: fetch the next step's
       }
     }
     arow += g.a_stride * 32;
@@ -444,10 +441,23 @@ __device__ __forceinline__ void z_segment(const double2 *__restrict__ U, const d
   }
 }
 
+// storage form of a descriptor (16 bytes, kept in shared memory next to the step table)
+__host__ __device__ inline int4 pack_seg(const YiSeg &g) {
+  int4 p;
+  p.x = g.a_off | (g.w_off << 16);
+  p.y = g.tab_off | (g.cga_idx << 16);
+  p.z = g.a_stride | (-g.w_stride << 4) | (g.cga_stride << 8) | (g.tab_stride << 12) | (g.nrows << 16) | (g.nsteps << 20) | (g.tr << 24);
+  p.w = 0;
+  return p;
+}
 __device__ __forceinline__ YiSeg load_seg(const int4 *__restrict__ segs, int q) {
+  const int4 p = segs[q];
   YiSeg g;
-  reinterpret_cast<int4 *>(&g)[0] = __ldg(segs + 2 * q);
-  reinterpret_cast<int4 *>(&g)[1] = __ldg(segs + 2 * q + 1);
+  g.a_off = p.x & 0xffff; g.w_off = (unsigned)p.x >> 16;
+  g.tab_off = p.y & 0xffff; g.cga_idx = (unsigned)p.y >> 16;
+  g.a_stride = (short)(p.z & 15); g.w_stride = (short)-((p.z >> 4) & 15); g.cga_stride = (short)((p.z >> 8) & 15);
+  g.tab_stride = (short)((p.z >> 12) & 15); g.nrows = (short)((p.z >> 16) & 15); g.nsteps = (short)((p.z >> 20) & 15);
+  g.tr = (short)((unsigned)p.z >> 24); g.pad = 0;
   return g;
 }
 
@@ -482,14 +492,16 @@ __device__ __forceinline__ void yi_item(const double2 *__restrict__ U, const dou
 }
 
 __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ betaj,
-                                                                const int4 *__restrict__ segs, const double *__restrict__ steptab, int ntab,
-                                                                const int *__restrict__ type, int n_local, const double2 *__restrict__ ulist,
+                                                                const int4 *__restrict__ segs, int nsegs, const double *__restrict__ steptab,
+                                                                int ntab, const int *__restrict__ type, int n_local, const double2 *__restrict__ ulist,
                                                                 int ustride, double2 *__restrict__ ylist, size_t yhalf) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_next;
   const SnapTab &t = *tab;
   double2 *sU = reinterpret_cast<double2 *>(dyn) + kYiFrontPad * 32;
   double *s_tab = reinterpret_cast<double *>(sU + ((size_t)t.nuf + kYiBackPad) * 32);
+  int4 *s_segs = reinterpret_cast<int4 *>(s_tab + ntab);       // ntab is even
+  double *s_beta = reinterpret_cast<double *>(s_segs + nsegs); // [nelements][kMaxTriples]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const bool valid = i < n_local;
@@ -497,6 +509,8 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
   for (int k = threadIdx.x; k < kYiFrontPad * 32; k += blockDim.x) sU[k - kYiFrontPad * 32] = make_double2(0.0, 0.0);
   for (int k = threadIdx.x; k < kYiBackPad * 32; k += blockDim.x) sU[(size_t)t.nuf * 32 + k] = make_double2(0.0, 0.0);
   for (int k = threadIdx.x; k < ntab; k += blockDim.x) s_tab[k] = steptab[k];
+  for (int k = threadIdx.x; k < nsegs; k += blockDim.x) s_segs[k] = segs[k];
+  for (int k = threadIdx.x; k < t.nelements * kMaxTriples; k += blockDim.x) s_beta[k] = betaj[k];
   // expand the half range to the full (ma,mb) range with the inversion symmetry: a warp requests all of its elements
   // (at most kMaxHalf / kYiWarps + 1) before it stores the first one
   {
@@ -522,7 +536,7 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
   }
   __syncthreads();
   const int elem_i = valid ? t.elem_of_type[type[i]] : 0;
-  const double *beta_i = betaj + (size_t)elem_i * kMaxTriples;
+  const double *beta_i = s_beta + elem_i * kMaxTriples;
   const double2 *U = sU + lane;
 
   for (;;) { // work items from a queue sorted by cost, most expensive first
@@ -536,11 +550,11 @@ __global__ void __launch_bounds__(32 * kYiWarps) snap_yi_kernel(const SnapTab *_
 #pragma unroll
     for (int mb = 0; mb < kMaxCol; mb++) { y0r[mb] = 0.0; y0i[mb] = 0.0; y1r[mb] = 0.0; y1i[mb] = 0.0; }
     switch (t.item[s].nmb) {
-      // levels j <= 3 (one or two outputs per row, 3 % of the terms) run the three-output code: what it adds to the outputs
-      // beyond the row's own is finite and never written; four instantiations less to keep in the instruction cache
-      case 1: case 2: case 3: yi_item<3>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
-      case 4: yi_item<4>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
-      default: yi_item<5>(U, s_tab, segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      case 1: yi_item<1>(U, s_tab, s_segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      case 2: yi_item<2>(U, s_tab, s_segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      case 3: yi_item<3>(U, s_tab, s_segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      case 4: yi_item<4>(U, s_tab, s_segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
+      default: yi_item<5>(U, s_tab, s_segs, beta_i, seg, y0r, y0i, y1r, y1i); break;
     }
     if (valid) {
       double2 *Y = ylist + t.item[s].half * yhalf + (size_t)i * t.nuh + t.uh_block[J] + ma;
@@ -726,7 +740,10 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
 }
 
 size_t ui_smem(const SnapTab &h) { return (size_t)h.nuh * 32 * sizeof(double2); }
-size_t yi_smem(const SnapTab &h, int ntab) { return ((size_t)h.nuf + kYiFrontPad + kYiBackPad) * 32 * sizeof(double2) + sizeof(double) * (size_t)ntab; }
+size_t yi_smem(const SnapTab &h, int ntab, int nsegs) {
+  return ((size_t)h.nuf + kYiFrontPad + kYiBackPad) * 32 * sizeof(double2) + sizeof(double) * (size_t)ntab + sizeof(int4) * (size_t)nsegs +
+         sizeof(double) * (size_t)h.nelements * kMaxTriples;
+}
 size_t de_smem(const SnapTab &h) { return ((size_t)kMaxJ * 4 * kDeThreads + (size_t)kDeStageAtoms * h.nuh) * sizeof(double2); }
 
 } // namespace
@@ -919,9 +936,14 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
     h.item[k].seg[3] = (int)segs.size();
   }
   segs.push_back(YiSeg{}); // the kernel fetches one descriptor ahead
+  if (steptab.size() % 2) steptab.push_back(0.0);
   s->ntab = (int)steptab.size();
-  EMD_CUDA(cudaMalloc((void **)&s->d_segs, sizeof(YiSeg) * segs.size()));
-  EMD_CUDA(cudaMemcpy(s->d_segs, segs.data(), sizeof(YiSeg) * segs.size(), cudaMemcpyHostToDevice));
+  if (steptab.size() > 0xffff) { set_error("emd_snap_create: step table too long for the packed descriptors"); delete s; return 1; }
+  std::vector<int4> packed;
+  for (const YiSeg &g : segs) packed.push_back(pack_seg(g));
+  s->nsegs = (int)packed.size();
+  EMD_CUDA(cudaMalloc((void **)&s->d_segs, sizeof(int4) * packed.size()));
+  EMD_CUDA(cudaMemcpy(s->d_segs, packed.data(), sizeof(int4) * packed.size(), cudaMemcpyHostToDevice));
   EMD_CUDA(cudaMalloc((void **)&s->d_steptab, sizeof(double) * steptab.size()));
   EMD_CUDA(cudaMemcpy(s->d_steptab, steptab.data(), sizeof(double) * steptab.size(), cudaMemcpyHostToDevice));
 
@@ -937,9 +959,9 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
   int dev = 0;
   EMD_CUDA(cudaGetDevice(&dev));
   EMD_CUDA(cudaDeviceGetAttribute(&s->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (yi_smem(h, s->ntab) > (size_t)s->max_smem_optin) { set_error("emd_snap_create: U_tot batch does not fit in shared memory"); delete s; return 1; }
+  if (yi_smem(h, s->ntab, s->nsegs) > (size_t)s->max_smem_optin) { set_error("emd_snap_create: U_tot batch does not fit in shared memory"); delete s; return 1; }
   EMD_CUDA(cudaFuncSetAttribute(snap_ui_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ui_smem(h)));
-  EMD_CUDA(cudaFuncSetAttribute(snap_yi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yi_smem(h, s->ntab)));
+  EMD_CUDA(cudaFuncSetAttribute(snap_yi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yi_smem(h, s->ntab, s->nsegs)));
   EMD_CUDA(cudaFuncSetAttribute(snap_deidrj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)de_smem(h)));
   *out = s;
   return 0;
@@ -1004,7 +1026,7 @@ int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const i
   double2 *ulist = s->ulist.as<double2>(), *ylist = s->ylist.as<double2>();
   const int nbatch = grid_for(n_local, 32);
   EMD_LAUNCH(ctx, snap_ui_kernel, nbatch, 32 * h.ncol, ui_smem(h), s->d_tab, d_x, d_type, n_local, cnt, pair_j, ulist, s->ucap);
-  EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h, s->ntab), s->d_tab, s->d_betaj, s->d_segs, s->d_steptab, s->ntab, d_type, n_local,
+  EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h, s->ntab, s->nsegs), s->d_tab, s->d_betaj, s->d_segs, s->nsegs, s->d_steptab, s->ntab, d_type, n_local,
              ulist, s->ucap, ylist, (size_t)h.nuh * s->ucap);
   if (npairs > 0)
     EMD_LAUNCH(ctx, snap_deidrj_kernel, grid_for(npairs, kDeThreads), kDeThreads, de_smem(h), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
