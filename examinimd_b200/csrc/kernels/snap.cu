@@ -53,6 +53,7 @@ struct Triple { short j1, j2, j, pad; int cgoff; };
 struct SnapTab {
   int twojmax, ncol, nuh, nuf, ntriples, nitems, ncg, ntypes, nelements, switchflag;
   double rcutfac, rfac0, rmin0, wself, cutsq;
+  double unit_min_ar;        // snap_deidrj: smallest |a_r| for the unit-tangent recursion (EMD_SNAP_DEIDRJ_DIRECT=1: never)
   int uh_block[kMaxJ + 1];   // half layout: (j,mb,ma), mb <= j/2, at uh_block[j] + mb*(j+1) + ma
   int uf_block[kMaxJ + 1];   // full layout: (j,ma,mb) at uf_block[j] + ma*(j+1) + mb  (the reference's u(j,ma,mb))
   double rootpq[kRootDim * kRootDim];
@@ -111,6 +112,7 @@ struct emd_snap {
   int ncoeff = 0;
   // work arrays (grow-only)
   Scratch ulist, ylist, cnt, pair_i, pair_j, queue;
+  int *d_direct = nullptr;    // snap_deidrj: a pair needs the direct recursion (set by the first launch, read by the second)
   int ucap = 0;           // atoms the U/Y arrays are sized for (= row stride of ulist)
   int npairs = 0;
   int max_smem_optin = 0;
@@ -607,13 +609,146 @@ __device__ __forceinline__ void du_level(double2 (&u)[kMaxJ + 1], double2 (&du)[
   }
 }
 
+// The same level for the three UNIT tangents d/da_i, d/db_r, d/db_i (derivatives with respect to the Cayley-Klein
+// parameters themselves): the inhomogeneous term of each is a single element of u, so a tangent costs 12 FP64
+// instructions per element instead of the 20 of a direction x, y, z.  The fourth parameter derivative follows from
+// homogeneity (every u_j is a homogeneous polynomial of degree j in (a_r, a_i, b_r, b_i): the recursion multiplies by
+// conj(a) or conj(b) once per level, the inversion image conjugates), i.e. Euler:
+//     a_r d/da_r u_j = j u_j - a_i d/da_i u_j - b_r d/db_r u_j - b_i d/db_i u_j,
+// and the directional derivative is the chain rule over the four parameters (snap_deidrj_kernel).
+__device__ __forceinline__ void du_level_unit(double2 (&u)[kMaxJ + 1], double2 (&d)[3][kMaxJ + 1], int j, int mb, const double *__restrict__ s_rootpq,
+                                              double a_r, double a_i, double b_r, double b_i) {
+#pragma unroll
+  for (int ma = kMaxJ; ma >= 0; --ma) {
+    if (ma <= j) {
+      double c1 = 0.0, c2 = 0.0;
+      double2 uo = make_double2(0.0, 0.0), um = make_double2(0.0, 0.0);
+      if (ma < j) { c1 = s_rootpq[(j - ma) * kRootDim + (j - mb)]; uo = u[ma]; }
+      if (ma > 0) { c2 = s_rootpq[ma * kRootDim + (j - mb)]; um = u[ma - 1]; }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        double2 dq = make_double2(0.0, 0.0), dm = make_double2(0.0, 0.0);
+        if (ma < j) dq = d[k][ma];
+        if (ma > 0) dm = d[k][ma - 1];
+        // conj(da) uo with da = i (k = 0); conj(db) um with db = 1 (k = 1), db = i (k = 2)
+        const double i1r = k == 0 ? uo.y : 0.0, i1i = k == 0 ? -uo.x : 0.0;
+        const double i2r = k == 1 ? um.x : (k == 2 ? um.y : 0.0), i2i = k == 1 ? um.y : (k == 2 ? -um.x : 0.0);
+        const double t1r = a_r * dq.x + (a_i * dq.y + i1r), t1i = a_r * dq.y - (a_i * dq.x - i1i);
+        const double t2r = b_r * dm.x + (b_i * dm.y + i2r), t2i = b_r * dm.y - (b_i * dm.x - i2i);
+        d[k][ma] = make_double2(c1 * t1r - c2 * t2r, c1 * t1i - c2 * t2i);
+      }
+      const double t1r = a_r * uo.x + a_i * uo.y, t1i = a_r * uo.y - a_i * uo.x;
+      const double t2r = b_r * um.x + b_i * um.y, t2i = b_r * um.y - b_i * um.x;
+      u[ma] = make_double2(c1 * t1r - c2 * t2r, c1 * t1i - c2 * t2i);
+    }
+  }
+}
+
+// S0 = sum w Re(conj(u) Y), Sj = the same weighted with the level j, T[k] = sum w Re(conj(d_k u) Y) over the half columns of one
+// pair; d_k = the unit tangents d/da_i, d/db_r, d/db_i (UNIT) or the directions x, y, z themselves.
+template <bool UNIT>
+__device__ __forceinline__ void de_sums(const SnapTab &t, const double2 *__restrict__ Y, double2 *__restrict__ boot, int bs,
+                                        const double *__restrict__ s_rootpq, double a_r, double a_i, double b_r, double b_i,
+                                        const double (&da_r)[3], const double (&da_i)[3], const double (&db_r)[3], const double (&db_i)[3],
+                                        double &S0, double &Sj, double (&T)[3]) {
+  const int twojmax = t.twojmax, ncol = t.ncol;
+  Sj = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) T[k] = 0.0;
+  double2 u[kMaxJ + 1], du[3][kMaxJ + 1];
+  u[0] = make_double2(1.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < 3; k++) du[k][0] = make_double2(0.0, 0.0);
+  S0 = Y[t.uh_block[0]].x; // level 0: u = 1, du = 0
+
+  for (int c = 0; c < ncol; c++) {
+    if (c > 0) {
+#pragma unroll
+      for (int ma = 0; ma <= kMaxJ; ma++)
+        if (ma <= 2 * c - 1) {
+          u[ma] = boot[(ma * 4 + 0) * bs];
+#pragma unroll
+          for (int k = 0; k < 3; k++) du[k][ma] = boot[(ma * 4 + 1 + k) * bs];
+        }
+    }
+    for (int jl = max(1, 2 * c); jl <= twojmax; jl++) {
+      if (UNIT) du_level_unit(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i);
+      else du_level(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i, da_r, da_i, db_r, db_i);
+      const double2 *Yl = Y + t.uh_block[jl] + c * (jl + 1);
+      double L = 0.0;
+#pragma unroll
+      for (int ma = 0; ma <= kMaxJ; ma++)
+        if (ma <= jl) {
+          const double2 y = Yl[ma];
+          L += u[ma].x * y.x + u[ma].y * y.y;
+#pragma unroll
+          for (int k = 0; k < 3; k++) T[k] += du[k][ma].x * y.x + du[k][ma].y * y.y;
+        }
+      S0 += L;
+      if (UNIT) Sj += jl * L;
+      if (jl == 2 * c + 1 && c + 1 < ncol) { // image that starts column c+1 (:840-864)
+#pragma unroll
+        for (int s = 0; s <= kMaxJ; s++)
+          if (s <= jl) {
+            const double sg = ((s + c) & 1) ? -1.0 : 1.0;
+            boot[((jl - s) * 4 + 0) * bs] = make_double2(sg * u[s].x, -sg * u[s].y);
+#pragma unroll
+            for (int k = 0; k < 3; k++) boot[((jl - s) * 4 + 1 + k) * bs] = make_double2(sg * du[k][s].x, -sg * du[k][s].y);
+          }
+      }
+    }
+  }
+}
+
+// compute_duidrj :290-321, compute_duarray :740-771: Cayley-Klein parameters of a pair and their derivatives
+struct DeGeom {
+  double a_r, a_i, b_r, b_i, da_r[3], da_i[3], db_r[3], db_i[3], uhat[3], sfac, dsfac, rsq;
+};
+__device__ __forceinline__ DeGeom de_geom(const SnapTab &t, double dx, double dy, double dz, double rcut, double wj) {
+  DeGeom g;
+  const double rsq = dx * dx + dy * dy + dz * dz;
+  const double r = sqrt(rsq);
+  const double rscale0 = t.rfac0 * kPi / (rcut - t.rmin0);
+  const double theta0 = (r - t.rmin0) * rscale0;
+  double sn, cs;
+  sincos(theta0, &sn, &cs);
+  const double z0 = r * cs / sn;
+  const double dz0dr = z0 / r - (r * rscale0) * (rsq + z0 * z0) / rsq;
+  const double rinv = 1.0 / r;
+  g.uhat[0] = dx * rinv; g.uhat[1] = dy * rinv; g.uhat[2] = dz * rinv;
+  const double r0inv = 1.0 / sqrt(r * r + z0 * z0);
+  g.a_r = z0 * r0inv; g.a_i = -dz * r0inv; g.b_r = dy * r0inv; g.b_i = -dx * r0inv;
+  const double dr0invdr = -(r0inv * r0inv * r0inv) * (r + z0 * dz0dr);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double dr0inv = dr0invdr * g.uhat[k], dz0 = dz0dr * g.uhat[k];
+    g.da_r[k] = dz0 * r0inv + z0 * dr0inv;
+    g.da_i[k] = -dz * dr0inv;
+    g.db_r[k] = dy * dr0inv;
+    g.db_i[k] = -dx * dr0inv;
+  }
+  g.da_i[2] += -r0inv;
+  g.db_i[0] += -r0inv;
+  g.db_r[1] += r0inv;
+  g.sfac = sfac_of(t, r, rcut) * wj; g.dsfac = dsfac_of(t, r, rcut) * wj;
+  g.rsq = rsq;
+  return g;
+}
+
 // lanes = in-cutoff pairs.  Dynamic shared memory: boot [kMaxJ][4][blockDim] double2.
+// UNIT = true: the launch that does the work (pairs with |a_r| >= unit_min_ar); it raises *direct_flag if it met a pair
+// below that bound.  UNIT = false: the second launch, which returns at once unless the flag is up and then handles
+// exactly those pairs with the three directions in the recursion (two kernels, because one kernel holding both
+// recursions spills its hot loop: 5.3 -> 7.1 ms).
+template <bool UNIT>
 __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ x,
                                                                  const int *__restrict__ type, const int *__restrict__ pair_i,
                                                                  const int *__restrict__ pair_j, int npairs,
-                                                                 const double2 *__restrict__ ylist, size_t yhalf, double *__restrict__ f) {
+                                                                 const double2 *__restrict__ ylist, size_t yhalf, double *__restrict__ f,
+                                                                 int *__restrict__ direct_flag) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ double s_rootpq[kRootDim * kRootDim];
+  if (!UNIT && *direct_flag == 0) return;
   const SnapTab &t = *tab;
   for (int k = threadIdx.x; k < kRootDim * kRootDim; k += blockDim.x) s_rootpq[k] = t.rootpq[k];
   // Pairs are sorted by their central atom, so the CTA's 128 pairs belong to a short run of consecutive atoms (7 at 18
@@ -629,41 +764,12 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
   const int p = active ? p0 + threadIdx.x : npairs - 1;
   double2 *boot = reinterpret_cast<double2 *>(dyn) + threadIdx.x;
   const int bs = blockDim.x;
-  const int twojmax = t.twojmax, ncol = t.ncol;
   const int i = pair_i[p], j = pair_j[p];
   const double dx = x[3 * (size_t)j] - x[3 * (size_t)i], dy = x[3 * (size_t)j + 1] - x[3 * (size_t)i + 1],
                dz = x[3 * (size_t)j + 2] - x[3 * (size_t)i + 2];
   const int elem_i = t.elem_of_type[type[i]], elem_j = t.elem_of_type[type[j]];
   const double rcut = (t.radelem[elem_i] + t.radelem[elem_j]) * t.rcutfac;
   const double wj = t.wjelem[elem_j];
-  // compute_duidrj :290-321, compute_duarray :740-771
-  const double rsq = dx * dx + dy * dy + dz * dz;
-  const double r = sqrt(rsq);
-  const double rscale0 = t.rfac0 * kPi / (rcut - t.rmin0);
-  const double theta0 = (r - t.rmin0) * rscale0;
-  double sn, cs;
-  sincos(theta0, &sn, &cs);
-  const double z0 = r * cs / sn;
-  const double dz0dr = z0 / r - (r * rscale0) * (rsq + z0 * z0) / rsq;
-  const double rinv = 1.0 / r;
-  const double uhat[3] = {dx * rinv, dy * rinv, dz * rinv};
-  const double r0inv = 1.0 / sqrt(r * r + z0 * z0);
-  const double a_r = z0 * r0inv, a_i = -dz * r0inv, b_r = dy * r0inv, b_i = -dx * r0inv;
-  const double dr0invdr = -(r0inv * r0inv * r0inv) * (r + z0 * dz0dr);
-  double da_r[3], da_i[3], db_r[3], db_i[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const double dr0inv = dr0invdr * uhat[k], dz0 = dz0dr * uhat[k];
-    da_r[k] = dz0 * r0inv + z0 * dr0inv;
-    da_i[k] = -dz * dr0inv;
-    db_r[k] = dy * dr0inv;
-    db_i[k] = -dx * dr0inv;
-  }
-  da_i[2] += -r0inv;
-  db_i[0] += -r0inv;
-  db_r[1] += r0inv;
-  const double sfac = sfac_of(t, r, rcut) * wj, dsfac = dsfac_of(t, r, rcut) * wj;
-
   for (int base = 0; base <= i_last - i_first; base += kDeStageAtoms) {
     if (base > 0) __syncthreads();
     {
@@ -686,53 +792,35 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
     __syncthreads();
     if (!active || i - i_first < base || i - i_first >= base + kDeStageAtoms) continue;
     const double2 *Y = s_y + (size_t)(i - i_first - base) * t.nuh;
-    double S0 = 0.0, S[3] = {0.0, 0.0, 0.0};
-    double2 u[kMaxJ + 1], du[3][kMaxJ + 1];
-    u[0] = make_double2(1.0, 0.0);
+    double S0, Sj, T[3], S[3];
+    double dxg = dx, dyg = dy, dzg = dz;
+    DeGeom g = de_geom(t, dxg, dyg, dzg, rcut, wj);
+    // |a_r| = |z0| / r0 passes through 0 where theta0 = pi/2 (r ~ half the cutoff: closer than any neighbor of the decks'
+    // lattices, but legal); such pairs are left to the UNIT = false launch
+    const bool unit_ok = fabs(g.a_r) >= t.unit_min_ar;
+    if (UNIT && !unit_ok) atomicOr(direct_flag, 1);
+    if (unit_ok != UNIT) continue;
+    if (UNIT) {
+      // The unit-tangent recursion needs only a and b: the rest of the geometry is evaluated again after it (a few hundred
+      // instructions against 9 000) instead of being kept in 40 registers.
+      de_sums<true>(t, Y, boot, bs, s_rootpq, g.a_r, g.a_i, g.b_r, g.b_i, g.da_r, g.da_i, g.db_r, g.db_i, S0, Sj, T);
+      asm volatile("" : "+d"(dxg), "+d"(dyg), "+d"(dzg));
+      g = de_geom(t, dxg, dyg, dzg, rcut, wj);
+      const double T_ar = (Sj - g.a_i * T[0] - g.b_r * T[1] - g.b_i * T[2]) / g.a_r; // Euler (du_level_unit)
 #pragma unroll
-    for (int k = 0; k < 3; k++) du[k][0] = make_double2(0.0, 0.0);
-    S0 += Y[t.uh_block[0]].x; // level 0: u = 1, du = 0
-
-    for (int c = 0; c < ncol; c++) {
-      if (c > 0) {
+      for (int k = 0; k < 3; k++) S[k] = g.da_r[k] * T_ar + g.da_i[k] * T[0] + g.db_r[k] * T[1] + g.db_i[k] * T[2];
+    } else {
+      de_sums<false>(t, Y, boot, bs, s_rootpq, g.a_r, g.a_i, g.b_r, g.b_i, g.da_r, g.da_i, g.db_r, g.db_i, S0, Sj, T);
 #pragma unroll
-        for (int ma = 0; ma <= kMaxJ; ma++)
-          if (ma <= 2 * c - 1) {
-            u[ma] = boot[(ma * 4 + 0) * bs];
-#pragma unroll
-            for (int k = 0; k < 3; k++) du[k][ma] = boot[(ma * 4 + 1 + k) * bs];
-          }
-      }
-      for (int jl = max(1, 2 * c); jl <= twojmax; jl++) {
-        du_level(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i, da_r, da_i, db_r, db_i);
-        const double2 *Yl = Y + t.uh_block[jl] + c * (jl + 1);
-#pragma unroll
-        for (int ma = 0; ma <= kMaxJ; ma++)
-          if (ma <= jl) {
-            const double2 y = Yl[ma];
-            S0 += u[ma].x * y.x + u[ma].y * y.y;
-#pragma unroll
-            for (int k = 0; k < 3; k++) S[k] += du[k][ma].x * y.x + du[k][ma].y * y.y;
-          }
-        if (jl == 2 * c + 1 && c + 1 < ncol) { // image that starts column c+1 (:840-864)
-#pragma unroll
-          for (int s = 0; s <= kMaxJ; s++)
-            if (s <= jl) {
-              const double sg = ((s + c) & 1) ? -1.0 : 1.0;
-              boot[((jl - s) * 4 + 0) * bs] = make_double2(sg * u[s].x, -sg * u[s].y);
-#pragma unroll
-              for (int k = 0; k < 3; k++) boot[((jl - s) * 4 + 1 + k) * bs] = make_double2(sg * du[k][s].x, -sg * du[k][s].y);
-            }
-        }
-      }
+      for (int k = 0; k < 3; k++) S[k] = T[k];
     }
     // dU_full = dsfac u uhat + sfac dU (:873-892); F_ij = 2 sum w Re(conj(dU_full) Y) + rij * (-1.5e6 / r^14) (force_snap_neigh_impl.h:698-711)
-    const double rsq7 = (rsq * rsq * rsq) * (rsq * rsq * rsq) * rsq;
+    const double rsq7 = (g.rsq * g.rsq * g.rsq) * (g.rsq * g.rsq * g.rsq) * g.rsq;
     const double fdivr = -1.5e6 / rsq7;
     const double rij[3] = {dx, dy, dz};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const double fk = 2.0 * (dsfac * uhat[k] * S0 + sfac * S[k]) + rij[k] * fdivr;
+      const double fk = 2.0 * (g.dsfac * g.uhat[k] * S0 + g.sfac * S[k]) + rij[k] * fdivr;
       atomicAdd(&f[3 * (size_t)i + k], fk);
       atomicAdd(&f[3 * (size_t)j + k], -fk);
     }
@@ -762,6 +850,7 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
   const int J2 = p->twojmax;
   h.twojmax = J2; h.ncol = J2 / 2 + 1; h.ntypes = p->ntypes; h.nelements = p->nelements; h.switchflag = p->switchflag;
   h.rcutfac = p->rcutfac; h.rfac0 = p->rfac0; h.rmin0 = p->rmin0; h.wself = p->wself;
+  { const char *e = getenv("EMD_SNAP_DEIDRJ_DIRECT"); h.unit_min_ar = (e && atoi(e)) ? 2.0 : 0.25; }
   int nuh = 0, nuf = 0;
   for (int j = 0; j <= J2; j++) { h.uh_block[j] = nuh; nuh += (j / 2 + 1) * (j + 1); h.uf_block[j] = nuf; nuf += (j + 1) * (j + 1); }
   h.nuh = nuh; h.nuf = nuf;
@@ -962,7 +1051,9 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
   if (yi_smem(h, s->ntab, s->nsegs) > (size_t)s->max_smem_optin) { set_error("emd_snap_create: U_tot batch does not fit in shared memory"); delete s; return 1; }
   EMD_CUDA(cudaFuncSetAttribute(snap_ui_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ui_smem(h)));
   EMD_CUDA(cudaFuncSetAttribute(snap_yi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yi_smem(h, s->ntab, s->nsegs)));
-  EMD_CUDA(cudaFuncSetAttribute(snap_deidrj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)de_smem(h)));
+  EMD_CUDA(cudaFuncSetAttribute(snap_deidrj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)de_smem(h)));
+  EMD_CUDA(cudaFuncSetAttribute(snap_deidrj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)de_smem(h)));
+  EMD_CUDA(cudaMalloc((void **)&s->d_direct, sizeof(int)));
   *out = s;
   return 0;
 }
@@ -973,6 +1064,7 @@ void emd_snap_destroy(emd_snap *s) {
   if (s->d_betaj) cudaFree(s->d_betaj);
   if (s->d_segs) cudaFree(s->d_segs);
   if (s->d_steptab) cudaFree(s->d_steptab);
+  if (s->d_direct) cudaFree(s->d_direct);
   s->ulist.release(); s->ylist.release(); s->cnt.release(); s->pair_i.release(); s->pair_j.release(); s->queue.release();
   delete s;
 }
@@ -1028,9 +1120,13 @@ int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const i
   EMD_LAUNCH(ctx, snap_ui_kernel, nbatch, 32 * h.ncol, ui_smem(h), s->d_tab, d_x, d_type, n_local, cnt, pair_j, ulist, s->ucap);
   EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h, s->ntab, s->nsegs), s->d_tab, s->d_betaj, s->d_segs, s->nsegs, s->d_steptab, s->ntab, d_type, n_local,
              ulist, s->ucap, ylist, (size_t)h.nuh * s->ucap);
-  if (npairs > 0)
-    EMD_LAUNCH(ctx, snap_deidrj_kernel, grid_for(npairs, kDeThreads), kDeThreads, de_smem(h), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
-               ylist, (size_t)h.nuh * s->ucap, d_f);
+  if (npairs > 0) {
+    EMD_CUDA(cudaMemsetAsync(s->d_direct, 0, sizeof(int), ctx->stream));
+    EMD_LAUNCH(ctx, snap_deidrj_kernel<true>, grid_for(npairs, kDeThreads), kDeThreads, de_smem(h), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
+               ylist, (size_t)h.nuh * s->ucap, d_f, s->d_direct);
+    EMD_LAUNCH(ctx, snap_deidrj_kernel<false>, grid_for(npairs, kDeThreads), kDeThreads, de_smem(h), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
+               ylist, (size_t)h.nuh * s->ucap, d_f, s->d_direct);
+  }
   return 0;
 }
 
