@@ -103,3 +103,32 @@ def test_snap_utot_and_pair_list_match_oracle(emd, oracle_lib, tmp_path):
     assert worst < 1e-12, worst
     app.close()
     md.close()
+
+
+@pytest.mark.parametrize("direct_only", [False, True])
+def test_snap_deidrj_direct_recursion(emd, oracle_lib, tmp_path, monkeypatch, direct_only):
+    """snap_deidrj evaluates dU through unit tangents and Euler's relation, dividing by a_r; pairs with |a_r| < 0.25 (theta0
+    near pi/2, r near half the cutoff) go to the second launch with the direct recursion.  A lattice compressed to a
+    nearest-neighbor distance of 2.39 (a_r ~ 0) puts the 6 nearest neighbors of every atom on that path and the other 20
+    on the first one; EMD_SNAP_DEIDRJ_DIRECT=1 sends every pair there."""
+    if direct_only:
+        monkeypatch.setenv("EMD_SNAP_DEIDRJ_DIRECT", "1")
+    d = snap_deck(tmp_path, "in.snap.W", (4, 5, 6), 3)
+    if not direct_only:
+        d.write_text(re.sub(r"lattice\s+sc\s+\S+", "lattice         sc 2.39", d.read_text()))
+    app = emd.App(["-il", str(d), "--neigh-type", "CSR", "--comm-type", "SERIAL"])
+    md = OracleMD.from_deck(d, "CSR", "NEIGH_FULL", coeff_dir=tmp_path)
+    n = md.geti("N_local")
+    done = 0
+    for s_ in (0, 1, 3):
+        app.advance(s_ - done)
+        md.step(s_ - done)
+        done = s_
+        cur = app.download()
+        o, r = np.argsort(cur["id"]), np.argsort(md.arr("id")[:n])
+        fo = md.arr("f")[:n][r]
+        fscale = max(np.sqrt((fo ** 2).mean()), 1e-3)
+        assert np.abs(cur["f"][o] - fo).max() / fscale < TOL, f"step {s_}: forces"
+        assert np.abs(cur["x"][o] - md.arr("x")[:n][r]).max() < 1e-9, f"step {s_}: x"
+    app.close()
+    md.close()
