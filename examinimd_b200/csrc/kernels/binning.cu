@@ -56,19 +56,59 @@ __global__ void __launch_bounds__(256) bin_place_kernel(const int *__restrict__ 
   permute[binoffsets[b] + slot] = i;
 }
 
-// one thread per bin: insertion sort of its slice of the permute vector (ascending atom index)
-__global__ void __launch_bounds__(128) bin_order_kernel(int nbins, const int *__restrict__ bincount,
+// warp per bin: the bin's slice of the permute vector in ascending atom index (= the stable order of the reference's
+// one-thread arrival).  The keys are distinct, so the rank of a key is the number of smaller keys: every lane holds up to
+// kOrderKeys keys in registers, all keys pass by through shuffles, and each key is stored at its rank (no divergence,
+// O(n^2 / 32) per bin instead of a one-thread insertion sort).  Bins beyond 32 * kOrderKeys atoms (never in the decks:
+// ~20 atoms per bin) are sorted by lane 0.
+constexpr int kOrderKeys = 8;
+__global__ void __launch_bounds__(256) bin_order_kernel(int nbins, const int *__restrict__ bincount,
                                                         const int *__restrict__ binoffsets, int *permute) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= nbins) return;
   const int cnt = bincount[b];
+  if (cnt < 2) return;
   int *p = permute + binoffsets[b];
-  for (int a = 1; a < cnt; a++) {
-    const int key = p[a];
-    int k = a - 1;
-    while (k >= 0 && p[k] > key) { p[k + 1] = p[k]; k--; }
-    p[k + 1] = key;
+  if (cnt > 32 * kOrderKeys) {
+    if (lane == 0)
+      for (int a = 1; a < cnt; a++) {
+        const int key = p[a];
+        int k = a - 1;
+        while (k >= 0 && p[k] > key) { p[k + 1] = p[k]; k--; }
+        p[k + 1] = key;
+      }
+    return;
   }
+  if (cnt <= 32) { // the usual bin: one key per lane
+    const int key = lane < cnt ? p[lane] : 0x7fffffff;
+    int rank = 0;
+#pragma unroll
+    for (int src = 0; src < 32; src++) rank += __shfl_sync(0xffffffffu, key, src) < key;
+    __syncwarp();
+    if (lane < cnt) p[rank] = key;
+    return;
+  }
+  const int nk = (cnt + 31) >> 5;
+  int key[kOrderKeys], rank[kOrderKeys];
+#pragma unroll
+  for (int q = 0; q < kOrderKeys; q++) {
+    key[q] = (q < nk && lane + 32 * q < cnt) ? p[lane + 32 * q] : 0x7fffffff;
+    rank[q] = 0;
+  }
+#pragma unroll
+  for (int q2 = 0; q2 < kOrderKeys; q2++) {
+    if (q2 < nk) { // warp-uniform
+      for (int src = 0; src < 32; src++) {
+        const int other = __shfl_sync(0xffffffffu, key[q2], src);
+#pragma unroll
+        for (int q = 0; q < kOrderKeys; q++) rank[q] += other < key[q];
+      }
+    }
+  }
+  __syncwarp(); // every key has been read
+#pragma unroll
+  for (int q = 0; q < kOrderKeys; q++)
+    if (q < nk && lane + 32 * q < cnt) p[rank[q]] = key[q];
 }
 
 __global__ void __launch_bounds__(256) permute_kernel(const int *__restrict__ permute, int n,
@@ -144,7 +184,7 @@ int emd_binning_build(emd_ctx *ctx, const double *d_x, int n, const emd_bin_geom
   if (exclusive_scan_int(ctx, d_bincount, d_binoffsets, nbins, nullptr)) return 1;
   if (n > 0) {
     EMD_LAUNCH(ctx, bin_place_kernel, grid_for(n, 256), 256, 0, binid, n, d_binoffsets, cursor, d_permute);
-    EMD_LAUNCH(ctx, bin_order_kernel, grid_for(nbins, 128), 128, 0, nbins, d_bincount, d_binoffsets, d_permute);
+    EMD_LAUNCH(ctx, bin_order_kernel, grid_for((size_t)nbins * 32, 256), 256, 0, nbins, d_bincount, d_binoffsets, d_permute);
   }
   EMD_CUDA(cudaMemcpyAsync(ctx->h_pinned, err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   EMD_CUDA(cudaStreamSynchronize(ctx->stream));
