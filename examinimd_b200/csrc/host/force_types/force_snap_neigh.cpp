@@ -148,4 +148,16 @@ void ForceSNAP::compute(System *system, Binning *, Neighbor *neighbor) {
   }
 }
 
+T_F_FLOAT ForceSNAP::compute_energy(System *system, Binning *, Neighbor *neighbor) {
+  const char *e = getenv("EMD_SNAP_ENERGY");
+  if (!e || !atoi(e) || !snap) return 0.0; // src/force.h:54
+  const emd_neigh_list l = neighbor->list_view();
+  double pe = 0.0;
+  if (emd_force_snap_energy(system->ctx, snap, system->x, system->type, system->N_local, &l, bzeroflag, &pe)) {
+    fprintf(stderr, "ForceSNAP: compute_energy: %s\n", emd_last_error());
+    emd_host_exit(1);
+  }
+  return pe;
+}
+
 const char *ForceSNAP::name() { return "ForceSNAP"; }

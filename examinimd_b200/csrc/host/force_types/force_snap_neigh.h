@@ -36,7 +36,10 @@ public:
   ~ForceSNAP();
   void init_coeff(int nargs, char **args);
   void compute(System *system, Binning *binning, Neighbor *neighbor);
-  // Force::compute_energy is NOT overridden, as in the reference (thermo PE prints 0, src/force.h:54)
+  // The reference does not override Force::compute_energy (thermo PE prints 0, src/force.h:54), and by default neither does
+  // this class's behaviour differ: 0 is returned.  With EMD_SNAP_ENERGY=1 in the environment (an extension)
+  // the SNAP energy of the owned atoms is evaluated (emd_force_snap_energy), which gives the deck a total-energy drift check.
+  T_F_FLOAT compute_energy(System *system, Binning *binning, Neighbor *neighbor);
   bool zeroes_forces() const { return false; }
   const char *name();
   T_F_FLOAT cutoff() const { return rcutmax; }

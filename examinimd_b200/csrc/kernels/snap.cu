@@ -38,6 +38,8 @@
 
 using namespace emd;
 
+namespace emd { int device_sum_partials(emd_ctx *ctx, const double *d_partial, int n, double *h_out); }
+
 namespace {
 
 constexpr int kMaxJ = 8;              // twojmax <= 8
@@ -106,6 +108,8 @@ struct emd_snap {
   SnapTab h;              // host copy of the tables
   SnapTab *d_tab = nullptr;
   double *d_betaj = nullptr;  // [nelements][ntriples]
+  double *d_betaj_e = nullptr; // the same for the energy: beta_k of the bispectrum blocks alone
+  double *d_e0 = nullptr;      // [nelements][2]: beta_0, beta_0 - sum_k beta_k bzero_k
   int4 *d_segs = nullptr;     // YiSeg descriptors of snap_yi, strip after strip
   double *d_steptab = nullptr; // Clebsch-Gordan factors of snap_yi's steps: [block][mb2][k], rows padded to an even length
   int ntab = 0, nsegs = 0;
@@ -827,6 +831,49 @@ __global__ void __launch_bounds__(kDeThreads) snap_deidrj_kernel(const SnapTab *
   }
 }
 
+// ------------------------------------------------------------------------------- snap_energy
+// E_i = e0(elem) + 2 sum_{half range} Re(conj(U_tot) Y_E) + sum_{j inside the cutoff} 1.25e5 / r_ij^12, with Y_E = the adjoint Y
+// for the coefficients beta_k of the blocks (j1,j2,j) of the bispectrum list alone (no fold factors): the first sum is
+// sum_k beta_k B_k of LAMMPS' SNA::compute_bi (B_k = 2 sum w Re(conj(U) Z_k), the same half-column weights), e0 = beta_0
+// - sum_k beta_k bzero_k; the last term is the potential whose gradient the force kernel adds as rij * (-1.5e6 / r^14) from
+// both ends of a pair (force_snap_neigh_impl.h:698-711).  Not in the reference (ForceSNAP inherits Force::compute_energy = 0).
+__global__ void __launch_bounds__(256) snap_energy_kernel(const SnapTab *__restrict__ tab, const double *__restrict__ x, const int *__restrict__ type,
+                                                          int n_local, const int *__restrict__ poff, const int *__restrict__ pair_j,
+                                                          const double2 *__restrict__ ulist, int ustride, const double2 *__restrict__ ylist,
+                                                          size_t yhalf, const double *__restrict__ e0, int which, double *__restrict__ partial) {
+  __shared__ double sm[8];
+  const SnapTab &t = *tab;
+  double e = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += gridDim.x * blockDim.x) {
+    double b = 0.0;
+    const double2 *Y = ylist + (size_t)i * t.nuh;
+    for (int k = 0; k < t.nuh; k++) {
+      const double2 u = ulist[(size_t)k * ustride + i], y0 = Y[k], y1 = Y[yhalf + k];
+      b += u.x * (y0.x + y1.x) + u.y * (y0.y + y1.y);
+    }
+    double rep = 0.0;
+    const double x_i = x[3 * (size_t)i], y_i = x[3 * (size_t)i + 1], z_i = x[3 * (size_t)i + 2];
+    for (int p = poff[i]; p < poff[i + 1]; p++) {
+      const int j = pair_j[p];
+      const double dx = x[3 * (size_t)j] - x_i, dy = x[3 * (size_t)j + 1] - y_i, dz = x[3 * (size_t)j + 2] - z_i;
+      const double rsq = dx * dx + dy * dy + dz * dz, r6 = rsq * rsq * rsq;
+      rep += 1.25e5 / (r6 * r6);
+    }
+    e += e0[2 * t.elem_of_type[type[i]] + which] + 2.0 * b + rep;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sm[warp] = e;
+  __syncthreads();
+  if (warp == 0) {
+    double v = lane < 8 ? sm[lane] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) partial[blockIdx.x] = v;
+  }
+}
+
 size_t ui_smem(const SnapTab &h) { return (size_t)h.nuh * 32 * sizeof(double2); }
 size_t yi_smem(const SnapTab &h, int ntab, int nsegs) {
   return ((size_t)h.nuf + kYiFrontPad + kYiBackPad) * 32 * sizeof(double2) + sizeof(double) * (size_t)ntab + sizeof(int4) * (size_t)nsegs +
@@ -916,7 +963,7 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
     return -1;
   };
   // betaj: the coefficient of every Z block in Y (fold of compute_dbidrj's three sums, :393-527, with beta)
-  std::vector<double> betaj((size_t)p->nelements * h.ntriples, 0.0);
+  std::vector<double> betaj((size_t)p->nelements * h.ntriples, 0.0), betaj_e((size_t)p->nelements * h.ntriples, 0.0), e0(2 * (size_t)p->nelements, 0.0);
   for (int e = 0; e < p->nelements; e++) {
     const double *coeff = p->coeffelem + (size_t)e * p->ncoeffall;
     double *bj = betaj.data() + (size_t)e * h.ntriples;
@@ -930,7 +977,11 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
       bj[t1] += b;
       bj[t2] += b * ((j + 1) / (j1 + 1.0));
       bj[t3] += b * ((j + 1) / (j2 + 1.0));
+      betaj_e[(size_t)e * h.ntriples + t1] += b;
+      e0[2 * e + 1] -= b * (p->wself * p->wself * p->wself) * (j + 1); // bzero[j] of SNA::init (LAMMPS sna.cpp)
     }
+    e0[2 * e] = coeff[0];
+    e0[2 * e + 1] += coeff[0];
   }
   // snap_yi's step table: for block tI, step mb2 and output k the factor cg(mb1 = C + k - mb2, mb2), 0 outside the block
   std::vector<double> steptab;
@@ -1045,6 +1096,10 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
   }
   EMD_CUDA(cudaMalloc((void **)&s->d_betaj, sizeof(double) * betaj.size()));
   EMD_CUDA(cudaMemcpy(s->d_betaj, betaj.data(), sizeof(double) * betaj.size(), cudaMemcpyHostToDevice));
+  EMD_CUDA(cudaMalloc((void **)&s->d_betaj_e, sizeof(double) * betaj_e.size()));
+  EMD_CUDA(cudaMemcpy(s->d_betaj_e, betaj_e.data(), sizeof(double) * betaj_e.size(), cudaMemcpyHostToDevice));
+  EMD_CUDA(cudaMalloc((void **)&s->d_e0, sizeof(double) * e0.size()));
+  EMD_CUDA(cudaMemcpy(s->d_e0, e0.data(), sizeof(double) * e0.size(), cudaMemcpyHostToDevice));
   int dev = 0;
   EMD_CUDA(cudaGetDevice(&dev));
   EMD_CUDA(cudaDeviceGetAttribute(&s->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -1062,6 +1117,8 @@ void emd_snap_destroy(emd_snap *s) {
   if (!s) return;
   if (s->d_tab) cudaFree(s->d_tab);
   if (s->d_betaj) cudaFree(s->d_betaj);
+  if (s->d_betaj_e) cudaFree(s->d_betaj_e);
+  if (s->d_e0) cudaFree(s->d_e0);
   if (s->d_segs) cudaFree(s->d_segs);
   if (s->d_steptab) cudaFree(s->d_steptab);
   if (s->d_direct) cudaFree(s->d_direct);
@@ -1090,11 +1147,8 @@ void *emd_snap_device_ptr(emd_snap *s, const char *what) {
   return nullptr;
 }
 
-int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const int *d_type, double *d_f, int n_local, int n_all,
-                           const emd_neigh_list *list) {
-  if (!ctx || !s || !list) { set_error("emd_force_snap_compute: NULL argument"); return 1; }
-  (void)n_all;
-  if (n_local <= 0) return 0;
+// in-cutoff pair list + U_tot of every owned atom (the part ForceSNAP::compute and the energy share)
+static int snap_pairs_and_ui(emd_ctx *ctx, emd_snap *s, const double *d_x, const int *d_type, int n_local, const emd_neigh_list *list) {
   const SnapTab &h = s->h;
   // in-cutoff pairs: count -> exclusive scan -> fill
   if (s->cnt.ensure(sizeof(int) * ((size_t)n_local + 1))) return 1;
@@ -1113,13 +1167,30 @@ int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const i
     if (s->ulist.ensure(sizeof(double2) * (size_t)h.nuh * want) || s->ylist.ensure(sizeof(double2) * (size_t)h.nuh * want * 2)) { s->ucap = 0; return 1; }
     s->ucap = want;
   }
+  EMD_LAUNCH(ctx, (snap_pairs_kernel<true>), grid_for(n_local, 128), 128, 0, d_x, n_local, *list, h.cutsq, cnt, s->pair_i.as<int>(), s->pair_j.as<int>());
+  EMD_LAUNCH(ctx, snap_ui_kernel, grid_for(n_local, 32), 32 * h.ncol, ui_smem(h), s->d_tab, d_x, d_type, n_local, cnt, s->pair_j.as<int>(),
+             s->ulist.as<double2>(), s->ucap);
+  return 0;
+}
+
+static int snap_yi(emd_ctx *ctx, emd_snap *s, const double *d_betaj, const int *d_type, int n_local) {
+  const SnapTab &h = s->h;
+  EMD_LAUNCH(ctx, snap_yi_kernel, grid_for(n_local, 32), 32 * kYiWarps, yi_smem(h, s->ntab, s->nsegs), s->d_tab, d_betaj, s->d_segs, s->nsegs, s->d_steptab,
+             s->ntab, d_type, n_local, s->ulist.as<double2>(), s->ucap, s->ylist.as<double2>(), (size_t)h.nuh * s->ucap);
+  return 0;
+}
+
+int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const int *d_type, double *d_f, int n_local, int n_all,
+                           const emd_neigh_list *list) {
+  if (!ctx || !s || !list) { set_error("emd_force_snap_compute: NULL argument"); return 1; }
+  (void)n_all;
+  if (n_local <= 0) return 0;
+  const SnapTab &h = s->h;
+  if (int rc = snap_pairs_and_ui(ctx, s, d_x, d_type, n_local, list)) return rc;
+  if (int rc = snap_yi(ctx, s, s->d_betaj, d_type, n_local)) return rc;
+  const int npairs = s->npairs;
   int *pair_i = s->pair_i.as<int>(), *pair_j = s->pair_j.as<int>();
-  EMD_LAUNCH(ctx, (snap_pairs_kernel<true>), grid_for(n_local, 128), 128, 0, d_x, n_local, *list, h.cutsq, cnt, pair_i, pair_j);
-  double2 *ulist = s->ulist.as<double2>(), *ylist = s->ylist.as<double2>();
-  const int nbatch = grid_for(n_local, 32);
-  EMD_LAUNCH(ctx, snap_ui_kernel, nbatch, 32 * h.ncol, ui_smem(h), s->d_tab, d_x, d_type, n_local, cnt, pair_j, ulist, s->ucap);
-  EMD_LAUNCH(ctx, snap_yi_kernel, nbatch, 32 * kYiWarps, yi_smem(h, s->ntab, s->nsegs), s->d_tab, s->d_betaj, s->d_segs, s->nsegs, s->d_steptab, s->ntab, d_type, n_local,
-             ulist, s->ucap, ylist, (size_t)h.nuh * s->ucap);
+  double2 *ylist = s->ylist.as<double2>();
   if (npairs > 0) {
     EMD_CUDA(cudaMemsetAsync(s->d_direct, 0, sizeof(int), ctx->stream));
     EMD_LAUNCH(ctx, snap_deidrj_kernel<true>, grid_for(npairs, kDeThreads), kDeThreads, de_smem(h), s->d_tab, d_x, d_type, pair_i, pair_j, npairs,
@@ -1128,6 +1199,22 @@ int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const i
                ylist, (size_t)h.nuh * s->ucap, d_f, s->d_direct);
   }
   return 0;
+}
+
+int emd_force_snap_energy(emd_ctx *ctx, emd_snap *s, const double *d_x, const int *d_type, int n_local, const emd_neigh_list *list,
+                          int bzeroflag, double *h_energy) {
+  if (!ctx || !s || !list || !h_energy) { set_error("emd_force_snap_energy: NULL argument"); return 1; }
+  *h_energy = 0.0;
+  if (n_local <= 0) return 0;
+  const SnapTab &h = s->h;
+  if (int rc = snap_pairs_and_ui(ctx, s, d_x, d_type, n_local, list)) return rc;
+  if (int rc = snap_yi(ctx, s, s->d_betaj_e, d_type, n_local)) return rc; // overwrites the Y of the last force call
+  const int grid = max(1, min(grid_for(n_local, 256), ctx->num_sms * 8));
+  if (ctx->s_c.ensure(sizeof(double) * ((size_t)grid + 8))) return 1;
+  double *partial = ctx->s_c.as<double>() + 8;
+  EMD_LAUNCH(ctx, snap_energy_kernel, grid, 256, 0, s->d_tab, d_x, d_type, n_local, s->cnt.as<int>(), s->pair_j.as<int>(), s->ulist.as<double2>(),
+             s->ucap, s->ylist.as<double2>(), (size_t)h.nuh * s->ucap, s->d_e0, bzeroflag ? 1 : 0, partial);
+  return device_sum_partials(ctx, partial, grid, h_energy);
 }
 
 } // extern "C"

@@ -274,6 +274,17 @@ void *emd_snap_device_ptr(emd_snap *s, const char *what);
  * reference's max_neighs reduction (:181). */
 int emd_force_snap_compute(emd_ctx *ctx, emd_snap *s, const double *d_x, const int *d_type, double *d_f,
                            int n_local, int n_all, const emd_neigh_list *list);
+/* SNAP potential energy of the owned atoms -- NOT in the reference: ForceSNAP inherits Force::compute_energy, which
+ * returns 0 (src/force.h:54).  E = sum_i [ beta_0 + sum_k beta_k (B_k(i) - bzero_k) ] +
+ * sum_i sum_{j: rsq < rcutmax^2} 1.25e5 / r_ij^12, where B_k = 2 sum_{mb <= j/2, ma} w Re(conj(U_tot) Z_k) is the
+ * bispectrum component of the published SNA::compute_bi (LAMMPS src/SNAP/sna.cpp, the code sna_impl.hpp was
+ * taken from; w = 1, 1/2 on the diagonal of an even level's middle column, 0 below it), bzero_k = wself^3 (j+1)
+ * if bzeroflag, and the last term is the potential of the rij * (-1.5e6 / r^14) the force kernel adds from both
+ * ends of a pair (force_snap_neigh_impl.h:698-711).  -dE/dx equals the force of emd_force_snap_compute
+ * (tests/test_gpu_snap.py: finite differences).  Recomputes the pair list and U_tot from d_x; overwrites the Y
+ * array of the last force call.  *h_energy is valid on return. */
+int emd_force_snap_energy(emd_ctx *ctx, emd_snap *s, const double *d_x, const int *d_type, int n_local,
+                          const emd_neigh_list *list, int bzeroflag, double *h_energy);
 
 /* ---- integrator: IntegratorNVE, src/integrator_nve.cpp:41-121 --------------------------- */
 /* dtf = 0.5*dt/mvv2e, dtv = dt (:41-44).  Bit-exact with the reference's CPU arithmetic

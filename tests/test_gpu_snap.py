@@ -132,3 +132,102 @@ def test_snap_deidrj_direct_recursion(emd, oracle_lib, tmp_path, monkeypatch, di
         assert np.abs(cur["x"][o] - md.arr("x")[:n][r]).max() < 1e-9, f"step {s_}: x"
     app.close()
     md.close()
+
+
+# ----------------------------------------------------------------------------- SNAP energy
+def _cg(j1, j2, j, m1, m2):
+    """Clebsch-Gordan coefficient in the doubled-index convention of SNA::init_clebsch_gordan (sna_impl.hpp:991-1046)"""
+    from math import factorial as f, sqrt
+    aa2, bb2 = 2 * m1 - j1, 2 * m2 - j2
+    m = (aa2 + bb2 + j) // 2
+    if m < 0 or m > j:
+        return 0.0
+    s = 0.0
+    for z in range(max(0, max(-(j - j2 + aa2) // 2, -(j - j1 - bb2) // 2)), min((j1 + j2 - j) // 2, min((j1 - aa2) // 2, (j2 + bb2) // 2)) + 1):
+        s += (-1 if z % 2 else 1) / (f(z) * f((j1 + j2 - j) // 2 - z) * f((j1 - aa2) // 2 - z) * f((j2 + bb2) // 2 - z) *
+                                     f((j - j2 + aa2) // 2 + z) * f((j - j1 - bb2) // 2 + z))
+    cc2 = 2 * m - j
+    dcg = sqrt(f((j1 + j2 - j) // 2) * f((j1 - j2 + j) // 2) * f((-j1 + j2 + j) // 2) / f((j1 + j2 + j) // 2 + 1))
+    sf = sqrt(f((j1 + aa2) // 2) * f((j1 - aa2) // 2) * f((j2 + bb2) // 2) * f((j2 - bb2) // 2) * f((j + cc2) // 2) * f((j - cc2) // 2) * (j + 1))
+    return s * dcg * sf
+
+
+def _snap_energy_numpy(U, beta, twojmax=8, bzero=False, wself=1.0):
+    """sum_i [beta_0 + sum_k beta_k (B_k(i) - bzero_k)] from U_tot[atom, j, ma, mb]: a plain restatement of the published
+    SNA::compute_zi / compute_bi (LAMMPS src/SNAP/sna.cpp; compute_zi = sna_impl.hpp:196-283), vectorised over atoms only"""
+    n = U.shape[0]
+    e = np.full(n, beta[0])
+    k = 0
+    for j1 in range(twojmax + 1):
+        for j2 in range(j1 + 1):
+            for j in range(j1 - j2, min(twojmax, j1 + j2) + 1, 2):
+                if j < j1:
+                    continue
+                k += 1
+                b = np.zeros(n)
+                for mb in range(j // 2 + 1):
+                    for ma in range(j + 1):
+                        w = 1.0
+                        if 2 * mb == j:
+                            w = 1.0 if ma < mb else (0.5 if ma == mb else 0.0)
+                        if w == 0.0:
+                            continue
+                        z = np.zeros(n, complex)
+                        for ma1 in range(max(0, (2 * ma - j - j2 + j1) // 2), min(j1, (2 * ma - j + j2 + j1) // 2) + 1):
+                            ma2 = (2 * ma - j - (2 * ma1 - j1) + j2) // 2
+                            ca = _cg(j1, j2, j, ma1, ma2)
+                            for mb1 in range(max(0, (2 * mb - j - j2 + j1) // 2), min(j1, (2 * mb - j + j2 + j1) // 2) + 1):
+                                mb2 = (2 * mb - j - (2 * mb1 - j1) + j2) // 2
+                                z += ca * _cg(j1, j2, j, mb1, mb2) * U[:, j1, ma1, mb1] * U[:, j2, ma2, mb2]
+                        b += w * (U[:, j, ma, mb].conjugate() * z).real
+                b *= 2.0
+                if bzero:
+                    b -= wself ** 3 * (j + 1)
+                e += beta[k] * b
+    assert k == len(beta) - 1
+    return e.sum()
+
+
+def test_snap_energy(emd, oracle_lib, tmp_path, monkeypatch):
+    """EMD_SNAP_ENERGY=1 (an extension: the reference's ForceSNAP has no energy).  (i) the value against a plain numpy
+    restatement of the published compute_zi / compute_bi on the oracle's U_tot plus the pair term of the force kernel's
+    1.5e6 / r^14; (ii) it is the potential of the forces: d(PE)/dt = -sum F.v along the trajectory (central difference over
+    two steps: 2e-5 of the scale measured); (iii) total energy is conserved to 2e-5 of the kinetic energy (3e-6 measured)
+    over the 40 steps before the first pair crosses the cutoff, where the reference's unshifted 1/r^12 term jumps by
+    2 x 1.25e5 / rcut^12 = 1.97e-3 eV (tools/dbg_snap_energy.py shows the steps)."""
+    monkeypatch.setenv("EMD_SNAP_ENERGY", "1")
+    d = snap_deck(tmp_path, "in.snap.W", (4, 4, 4), 80)
+    app = emd.App(["-il", str(d), "--neigh-type", "CSR", "--comm-type", "SERIAL"])
+    md = OracleMD.from_deck(d, "CSR", "NEIGH_FULL", coeff_dir=tmp_path)
+    n = md.geti("N_local")
+    app.advance(6)
+    md.step(6)
+    # (i)
+    coeff = [float(t) for t in " ".join(l for l in (SNAP_DIR / "W.snapcoeff").read_text().splitlines() if l.strip() and not l.startswith("#")).split()[5:]]
+    assert len(coeff) == 56
+    U = np.stack([md.snap_probe(i, with_forces=False)[0] for i in range(n)])
+    x = md.arr("x")
+    rep = 0.0
+    for i in range(n):
+        inside = md.snap_probe(i, with_forces=False)[1]
+        r2 = ((x[inside] - x[i]) ** 2).sum(1)
+        rep += (1.25e5 / r2 ** 6).sum()
+    e_np = _snap_energy_numpy(U, coeff) + rep
+    T, pe, ke = app.thermo()
+    assert abs(pe * n - e_np) < 1e-10 * abs(e_np), (pe * n, e_np)
+    # (ii), (iii)
+    dt = 0.001  # units metal (input.cpp)
+    pes, kes, fv = [], [], []
+    for s_ in range(32):
+        T, pe, ke = app.thermo()
+        cur = app.download()
+        pes.append(pe * n); kes.append(ke * n); fv.append((cur["f"] * cur["v"]).sum())
+        app.advance(1)
+    pes, kes, fv = np.array(pes), np.array(kes), np.array(fv)
+    dpe = (pes[2:] - pes[:-2]) / (2 * dt)
+    scale = np.abs(fv).max()
+    assert np.abs(dpe + fv[1:-1]).max() < 1e-4 * scale, (np.abs(dpe + fv[1:-1]).max(), scale)
+    etot = pes + kes
+    assert np.abs(etot - etot[0]).max() < 2e-5 * kes.mean(), (np.abs(etot - etot[0]).max(), kes.mean())
+    app.close()
+    md.close()
