@@ -181,30 +181,6 @@ __device__ __forceinline__ double dsfac_of(const SnapTab &t, double r, double rc
   return -0.5 * sin((r - t.rmin0) * rcutfac) * rcutfac;
 }
 
-// One level of the Wigner-U recursion for column mb, in place (sna_impl.hpp:667-692):
-//   u_j(ma) = rootpq(j-ma, j-mb) conj(a) u_{j-1}(ma) - rootpq(ma, j-mb) conj(b) u_{j-1}(ma-1)
-// walked from ma = j down so that u_{j-1}(ma-1) is still the old value.
-__device__ __forceinline__ void u_level(double2 (&u)[kMaxJ + 1], int j, int mb, const double *__restrict__ s_rootpq, double a_r, double a_i,
-                                        double b_r, double b_i) {
-#pragma unroll
-  for (int ma = kMaxJ; ma >= 0; --ma) {
-    if (ma <= j) {
-      double nr = 0.0, ni = 0.0;
-      if (ma < j) {
-        const double c1 = s_rootpq[(j - ma) * kRootDim + (j - mb)];
-        nr = c1 * (a_r * u[ma].x + a_i * u[ma].y);
-        ni = c1 * (a_r * u[ma].y - a_i * u[ma].x);
-      }
-      if (ma > 0) {
-        const double c2 = s_rootpq[ma * kRootDim + (j - mb)];
-        nr -= c2 * (b_r * u[ma - 1].x + b_i * u[ma - 1].y);
-        ni -= c2 * (b_r * u[ma - 1].y - b_i * u[ma - 1].x);
-      }
-      u[ma] = make_double2(nr, ni);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------ snap_ui
 // block = 32 atoms (lanes) x ncol warps (warp = column mb).  Dynamic shared memory:
 //   acc  [nuh][32] double2   U_tot accumulators of the batch (each warp touches only its column)
@@ -247,13 +223,14 @@ __device__ __forceinline__ void u_image(double2 (&u)[kMaxJ + 1]) {
   }
 }
 
-// one element of a level for both neighbors (two independent chains inside one guarded block), see u_level
+// One element of a level of the Wigner-U recursion for column mb (sna_impl.hpp:667-692), evaluated for both neighbors inside one
+// guarded block (two independent chains):
+//   u_j(ma) = rootpq(j-ma, j-mb) conj(a) u_{j-1}(ma) - rootpq(ma, j-mb) conj(b) u_{j-1}(ma-1)
+// in place, walked from ma = j down so that u_{j-1}(ma-1) is still the old value.
 __device__ __forceinline__ double2 u_elem(const double2 (&u)[kMaxJ + 1], int ma, int j, double c1, double c2, const UiGeom &g) {
-  double nr = 0.0, ni = 0.0;
-  if (ma < j) {
-    nr = c1 * (g.a_r * u[ma].x + g.a_i * u[ma].y);
-    ni = c1 * (g.a_r * u[ma].y - g.a_i * u[ma].x);
-  }
+  // c1 = rootpq(0, .) = 0 at the top element (ma == j), where u[ma] still holds a finite value of an earlier level or column
+  double nr = c1 * (g.a_r * u[ma].x + g.a_i * u[ma].y);
+  double ni = c1 * (g.a_r * u[ma].y - g.a_i * u[ma].x);
   if (ma > 0) {
     nr -= c2 * (g.b_r * u[ma - 1].x + g.b_i * u[ma - 1].y);
     ni -= c2 * (g.b_r * u[ma - 1].y - g.b_i * u[ma - 1].x);
@@ -273,7 +250,7 @@ __device__ __forceinline__ void ui_column(int C, const SnapTab &t, double2 *__re
 #pragma unroll
     for (int ma = kMaxJ; ma >= 0; --ma) // downwards: u_{j-1}(ma-1) is still the old value
       if (ma <= jl) {
-        const double c1 = ma < jl ? rq[(jl - ma) * kRootDim] : 0.0, c2 = ma > 0 ? rq[ma * kRootDim] : 0.0;
+        const double c1 = rq[(jl - ma) * kRootDim], c2 = ma > 0 ? rq[ma * kRootDim] : 0.0;
         const double2 nA = u_elem(uA, ma, jl, c1, c2, gA), nB = u_elem(uB, ma, jl, c1, c2, gB);
         uA[ma] = nA;
         uB[ma] = nB;
@@ -324,8 +301,8 @@ __global__ void __launch_bounds__(32 * kMaxCol) snap_ui_kernel(const SnapTab *__
     const UiGeom gA = ui_geom(t, x, type, actA ? pair_j[pbeg + k] : ic, actA, x_i, y_i, z_i, rad_i);
     const UiGeom gB = ui_geom(t, x, type, actB ? pair_j[pbeg + k + 1] : ic, actB, x_i, y_i, z_i, rad_i);
     double2 uA[kMaxJ + 1], uB[kMaxJ + 1];
-    uA[0] = make_double2(1.0, 0.0);
-    uB[0] = make_double2(1.0, 0.0);
+#pragma unroll
+    for (int ma = 0; ma <= kMaxJ; ma++) uA[ma] = uB[ma] = make_double2(ma == 0 ? 1.0 : 0.0, 0.0); // all finite (u_elem)
     if (col == 0) { // level 0 belongs to column 0 (add_uarraytot :612-635)
       double2 &q = acc[(size_t)t.uh_block[0] * 32 + lane];
       q.x += gA.sfac + gB.sfac;
@@ -591,14 +568,15 @@ __device__ __forceinline__ void du_level(double2 (&u)[kMaxJ + 1], double2 (&du)[
 #pragma unroll
   for (int ma = kMaxJ; ma >= 0; --ma) {
     if (ma <= j) {
-      double c1 = 0.0, c2 = 0.0;
-      double2 uo = make_double2(0.0, 0.0), um = make_double2(0.0, 0.0);
-      if (ma < j) { c1 = s_rootpq[(j - ma) * kRootDim + (j - mb)]; uo = u[ma]; }
+      const double c1 = s_rootpq[(j - ma) * kRootDim + (j - mb)]; // rootpq(0, .) = 0 at the top element (see du_level_unit)
+      double c2 = 0.0;
+      const double2 uo = u[ma];
+      double2 um = make_double2(0.0, 0.0);
       if (ma > 0) { c2 = s_rootpq[ma * kRootDim + (j - mb)]; um = u[ma - 1]; }
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        double2 dq = make_double2(0.0, 0.0), dm = make_double2(0.0, 0.0);
-        if (ma < j) dq = du[k][ma];
+        const double2 dq = du[k][ma];
+        double2 dm = make_double2(0.0, 0.0);
         if (ma > 0) dm = du[k][ma - 1];
         const double t1r = da_r[k] * uo.x + da_i[k] * uo.y + a_r * dq.x + a_i * dq.y;
         const double t1i = da_r[k] * uo.y - da_i[k] * uo.x + a_r * dq.y - a_i * dq.x;
@@ -625,14 +603,17 @@ __device__ __forceinline__ void du_level_unit(double2 (&u)[kMaxJ + 1], double2 (
 #pragma unroll
   for (int ma = kMaxJ; ma >= 0; --ma) {
     if (ma <= j) {
-      double c1 = 0.0, c2 = 0.0;
-      double2 uo = make_double2(0.0, 0.0), um = make_double2(0.0, 0.0);
-      if (ma < j) { c1 = s_rootpq[(j - ma) * kRootDim + (j - mb)]; uo = u[ma]; }
+      // the top element (ma == j) has no first term: its factor rootpq(0, .) is 0 and u[j], d[.][j] still hold finite values
+      // (zero, or what an earlier column left there), so nothing is selected at run time
+      const double c1 = s_rootpq[(j - ma) * kRootDim + (j - mb)];
+      double c2 = 0.0;
+      const double2 uo = u[ma];
+      double2 um = make_double2(0.0, 0.0);
       if (ma > 0) { c2 = s_rootpq[ma * kRootDim + (j - mb)]; um = u[ma - 1]; }
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        double2 dq = make_double2(0.0, 0.0), dm = make_double2(0.0, 0.0);
-        if (ma < j) dq = d[k][ma];
+        const double2 dq = d[k][ma];
+        double2 dm = make_double2(0.0, 0.0);
         if (ma > 0) dm = d[k][ma - 1];
         // conj(da) uo with da = i (k = 0); conj(db) um with db = 1 (k = 1), db = i (k = 2)
         const double i1r = k == 0 ? uo.y : 0.0, i1i = k == 0 ? -uo.x : 0.0;
@@ -660,9 +641,12 @@ __device__ __forceinline__ void de_sums(const SnapTab &t, const double2 *__restr
 #pragma unroll
   for (int k = 0; k < 3; k++) T[k] = 0.0;
   double2 u[kMaxJ + 1], du[3][kMaxJ + 1];
-  u[0] = make_double2(1.0, 0.0);
 #pragma unroll
-  for (int k = 0; k < 3; k++) du[k][0] = make_double2(0.0, 0.0);
+  for (int ma = 0; ma <= kMaxJ; ma++) { // every element finite from the start (du_level_unit)
+    u[ma] = make_double2(ma == 0 ? 1.0 : 0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < 3; k++) du[k][ma] = make_double2(0.0, 0.0);
+  }
   S0 = Y[t.uh_block[0]].x; // level 0: u = 1, du = 0
 
   for (int c = 0; c < ncol; c++) {
