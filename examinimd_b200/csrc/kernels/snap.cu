@@ -599,7 +599,8 @@ __device__ __forceinline__ void du_level(double2 (&u)[kMaxJ + 1], double2 (&du)[
 //     a_r d/da_r u_j = j u_j - a_i d/da_i u_j - b_r d/db_r u_j - b_i d/db_i u_j,
 // and the directional derivative is the chain rule over the four parameters (snap_deidrj_kernel).
 __device__ __forceinline__ void du_level_unit(double2 (&u)[kMaxJ + 1], double2 (&d)[3][kMaxJ + 1], int j, int mb, const double *__restrict__ s_rootpq,
-                                              double a_r, double a_i, double b_r, double b_i) {
+                                              double a_r, double a_i, double b_r, double b_i, const double2 *__restrict__ Yl, double &L,
+                                              double (&T)[3]) {
 #pragma unroll
   for (int ma = kMaxJ; ma >= 0; --ma) {
     if (ma <= j) {
@@ -625,6 +626,11 @@ __device__ __forceinline__ void du_level_unit(double2 (&u)[kMaxJ + 1], double2 (
       const double t1r = a_r * uo.x + a_i * uo.y, t1i = a_r * uo.y - a_i * uo.x;
       const double t2r = b_r * um.x + b_i * um.y, t2i = b_r * um.y - b_i * um.x;
       u[ma] = make_double2(c1 * t1r - c2 * t2r, c1 * t1i - c2 * t2i);
+      // contraction with Y inside the same guarded block (the Y element travels during the update)
+      const double2 y = Yl[ma];
+      L += u[ma].x * y.x + u[ma].y * y.y;
+#pragma unroll
+      for (int k = 0; k < 3; k++) T[k] += d[k][ma].x * y.x + d[k][ma].y * y.y;
     }
   }
 }
@@ -660,18 +666,20 @@ __device__ __forceinline__ void de_sums(const SnapTab &t, const double2 *__restr
         }
     }
     for (int jl = max(1, 2 * c); jl <= twojmax; jl++) {
-      if (UNIT) du_level_unit(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i);
-      else du_level(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i, da_r, da_i, db_r, db_i);
       const double2 *Yl = Y + t.uh_block[jl] + c * (jl + 1);
       double L = 0.0;
+      if (UNIT) du_level_unit(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i, Yl, L, T);
+      else {
+        du_level(u, du, jl, c, s_rootpq, a_r, a_i, b_r, b_i, da_r, da_i, db_r, db_i);
 #pragma unroll
-      for (int ma = 0; ma <= kMaxJ; ma++)
-        if (ma <= jl) {
-          const double2 y = Yl[ma];
-          L += u[ma].x * y.x + u[ma].y * y.y;
+        for (int ma = 0; ma <= kMaxJ; ma++)
+          if (ma <= jl) {
+            const double2 y = Yl[ma];
+            L += u[ma].x * y.x + u[ma].y * y.y;
 #pragma unroll
-          for (int k = 0; k < 3; k++) T[k] += du[k][ma].x * y.x + du[k][ma].y * y.y;
-        }
+            for (int k = 0; k < 3; k++) T[k] += du[k][ma].x * y.x + du[k][ma].y * y.y;
+          }
+      }
       S0 += L;
       if (UNIT) Sj += jl * L;
       if (jl == 2 * c + 1 && c + 1 < ncol) { // image that starts column c+1 (:840-864)
