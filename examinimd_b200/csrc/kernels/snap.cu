@@ -247,20 +247,36 @@ __device__ __forceinline__ void ui_column(int C, const SnapTab &t, double2 *__re
   for (int jl = (C == 0 ? 1 : 2 * C); jl <= jend; jl++) {
     double2 *q = acc + (size_t)(t.uh_block[jl] + col * (jl + 1)) * 32 + lane;
     const double *rq = s_rootpq + (jl - C);
-#pragma unroll
-    for (int ma = kMaxJ; ma >= 0; --ma) // downwards: u_{j-1}(ma-1) is still the old value
-      if (ma <= jl) {
-        const double c1 = rq[(jl - ma) * kRootDim], c2 = ma > 0 ? rq[ma * kRootDim] : 0.0;
-        const double2 nA = u_elem(uA, ma, jl, c1, c2, gA), nB = u_elem(uB, ma, jl, c1, c2, gB);
-        uA[ma] = nA;
-        uB[ma] = nB;
-        if (own) {
-          double2 v = q[ma * 32];
-          v.x += gA.sfac * nA.x + gB.sfac * nB.x;
-          v.y += gA.sfac * nA.y + gB.sfac * nB.y;
-          q[ma * 32] = v;
-        }
+    // one element: both neighbors, then (own column) the accumulator; elements are taken downwards so that u_{j-1}(ma-1) is
+    // still the old value, two per guarded block (eight independent FP64 chains instead of four)
+    auto elem = [&](int ma, double2 &nA, double2 &nB) {
+      const double c1 = rq[(jl - ma) * kRootDim], c2 = ma > 0 ? rq[ma * kRootDim] : 0.0;
+      nA = u_elem(uA, ma, jl, c1, c2, gA);
+      nB = u_elem(uB, ma, jl, c1, c2, gB);
+    };
+    auto commit = [&](int ma, const double2 &nA, const double2 &nB) {
+      uA[ma] = nA;
+      uB[ma] = nB;
+      if (own) {
+        double2 v = q[ma * 32];
+        v.x += gA.sfac * nA.x + gB.sfac * nB.x;
+        v.y += gA.sfac * nA.y + gB.sfac * nB.y;
+        q[ma * 32] = v;
       }
+    };
+#pragma unroll
+    for (int mh = kMaxJ; mh >= 0; mh -= 2) {
+      double2 hA, hB, lA, lB;
+      if (mh <= jl) {
+        elem(mh, hA, hB);
+        if (mh > 0) elem(mh - 1, lA, lB);
+        commit(mh, hA, hB);
+        if (mh > 0) commit(mh - 1, lA, lB);
+      } else if (mh > 0 && mh - 1 <= jl) {
+        elem(mh - 1, lA, lB);
+        commit(mh - 1, lA, lB);
+      }
+    }
   }
   if (C < col) {
     switch (C) {
