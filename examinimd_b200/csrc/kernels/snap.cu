@@ -189,6 +189,7 @@ __device__ __forceinline__ double dsfac_of(const SnapTab &t, double r, double rc
 // adds both to an accumulator with one read-modify-write.  The column loop is unrolled, so the inversion-symmetry image
 // that starts the next column is a reversal of the register array with static indices (no scratch memory).
 struct UiGeom { double a_r, a_i, b_r, b_i, sfac; };
+constexpr int kUiGeomIt = 10; // neighbor-pair iterations whose geometry is staged in shared memory at a time
 
 __device__ __forceinline__ UiGeom ui_geom(const SnapTab &t, const double *__restrict__ x, const int *__restrict__ type, int j, bool act,
                                           double x_i, double y_i, double z_i, double rad_i) {
@@ -312,20 +313,43 @@ __global__ void __launch_bounds__(32 * kMaxCol) snap_ui_kernel(const SnapTab *__
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
 
-  for (int k = 0; k < nmax; k += 2) {
-    const bool actA = k < pcnt, actB = k + 1 < pcnt;
-    const UiGeom gA = ui_geom(t, x, type, actA ? pair_j[pbeg + k] : ic, actA, x_i, y_i, z_i, rad_i);
-    const UiGeom gB = ui_geom(t, x, type, actB ? pair_j[pbeg + k + 1] : ic, actB, x_i, y_i, z_i, rad_i);
-    double2 uA[kMaxJ + 1], uB[kMaxJ + 1];
+  // The geometry of a neighbor (square root, sincos, two divisions: ~350 instructions against the 1 600 of the recursion of
+  // a neighbor pair) is the same for every column: the warps evaluate it in turns for kUiGeomIt iterations at a time and
+  // hand it over through shared memory, instead of every warp evaluating all of it.
+  double *geom = reinterpret_cast<double *>(acc + (size_t)t.nuh * 32) + lane; // [kUiGeomIt][2 neighbors][5][32]
+  const int nit = (nmax + 1) >> 1, ncolw = blockDim.x >> 5;
+  for (int it0 = 0; it0 < nit; it0 += kUiGeomIt) {
+    const int it1 = min(nit, it0 + kUiGeomIt);
+    if (it0 > 0) __syncthreads(); // the chunk before has been consumed
+    for (int it = it0 + col; it < it1; it += ncolw) {
 #pragma unroll
-    for (int ma = 0; ma <= kMaxJ; ma++) uA[ma] = uB[ma] = make_double2(ma == 0 ? 1.0 : 0.0, 0.0); // all finite (u_elem)
-    if (col == 0) { // level 0 belongs to column 0 (add_uarraytot :612-635)
-      double2 &q = acc[(size_t)t.uh_block[0] * 32 + lane];
-      q.x += gA.sfac + gB.sfac;
+      for (int h = 0; h < 2; h++) {
+        const int k = 2 * it + h;
+        const bool act = k < pcnt;
+        const UiGeom g = ui_geom(t, x, type, act ? pair_j[pbeg + k] : ic, act, x_i, y_i, z_i, rad_i);
+        double *gp = geom + ((it - it0) * 2 + h) * 5 * 32;
+        gp[0] = g.a_r; gp[32] = g.a_i; gp[64] = g.b_r; gp[96] = g.b_i; gp[128] = g.sfac;
+      }
     }
-    // column c: levels 2c, 2c+1 re-derived by every warp of a later column (first level = image of column c-1), all
-    // remaining levels by its own warp
-    for (int c = 0; c <= col; c++) ui_column(c, t, acc, s_rootpq, col, lane, uA, uB, gA, gB);
+    __syncthreads();
+    for (int it = it0; it < it1; it++) {
+      UiGeom gA, gB;
+      {
+        const double *gp = geom + (it - it0) * 2 * 5 * 32;
+        gA.a_r = gp[0]; gA.a_i = gp[32]; gA.b_r = gp[64]; gA.b_i = gp[96]; gA.sfac = gp[128];
+        gB.a_r = gp[160]; gB.a_i = gp[192]; gB.b_r = gp[224]; gB.b_i = gp[256]; gB.sfac = gp[288];
+      }
+      double2 uA[kMaxJ + 1], uB[kMaxJ + 1];
+#pragma unroll
+      for (int ma = 0; ma <= kMaxJ; ma++) uA[ma] = uB[ma] = make_double2(ma == 0 ? 1.0 : 0.0, 0.0); // all finite (u_elem)
+      if (col == 0) { // level 0 belongs to column 0 (add_uarraytot :612-635)
+        double2 &q = acc[(size_t)t.uh_block[0] * 32 + lane];
+        q.x += gA.sfac + gB.sfac;
+      }
+      // column c: levels 2c, 2c+1 re-derived by every warp of a later column (first level = image of column c-1), all
+      // remaining levels by its own warp
+      for (int c = 0; c <= col; c++) ui_column(c, t, acc, s_rootpq, col, lane, uA, uB, gA, gB);
+    }
   }
   // self term (addself_uarraytot :594-605) and write-out of this warp's column
   if (valid) {
@@ -882,7 +906,7 @@ __global__ void __launch_bounds__(256) snap_energy_kernel(const SnapTab *__restr
   }
 }
 
-size_t ui_smem(const SnapTab &h) { return (size_t)h.nuh * 32 * sizeof(double2); }
+size_t ui_smem(const SnapTab &h) { return (size_t)h.nuh * 32 * sizeof(double2) + (size_t)kUiGeomIt * 2 * 5 * 32 * sizeof(double); }
 size_t yi_smem(const SnapTab &h, int ntab, int nsegs) {
   return ((size_t)h.nuf + kYiFrontPad + kYiBackPad) * 32 * sizeof(double2) + sizeof(double) * (size_t)ntab + sizeof(int4) * (size_t)nsegs +
          sizeof(double) * (size_t)h.nelements * kMaxTriples;
