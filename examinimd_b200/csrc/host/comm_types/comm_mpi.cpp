@@ -82,6 +82,13 @@ void CommMPI::exchange() {
     if (!decomposed(pa)) continue;
     DeviceArray<char> *pk[2] = {&pack_buffer, &pack_buffer2}, *up[2] = {&unpack_buffer, &unpack_buffer2};
     int send[2] = {0, 0}, recv[2] = {0, 0};
+    // a floor under the migration buffers: nothing leaves at step 0 of a lattice start, and the first real migration should
+    // not pay for allocations and a second packing pass inside somebody's measurement window
+    for (int k = 0; k < 2; k++) {
+      const size_t floor_bytes = (size_t)std::max<T_INT>(4096, N_local / 128) * kParticleBytes;
+      ensure_bytes(*pk[k], floor_bytes);
+      ensure_bytes(*up[k], floor_bytes);
+    }
     for (int k = 0; k < 2; k++) {
       for (int attempt = 0; attempt < 2; attempt++) {
         const int cap = (int)(pk[k]->extent() / kParticleBytes);
