@@ -50,7 +50,7 @@ void CommMPI::fail(const char *what) {
 
 void CommMPI::ensure_bytes(DeviceArray<char> &b, size_t bytes) {
   if (bytes <= b.extent()) return;
-  if (!b.alloc(bytes + bytes / 8 + 1024)) fail("buffer allocation");
+  if (!b.alloc(bytes + bytes / 2 + 1024)) fail("buffer allocation"); // half again: a lattice start under-estimates the faces of a melt by up to 15 %
 }
 
 // src/comm_types/comm_mpi.cpp:52-147
@@ -154,8 +154,8 @@ void CommMPI::exchange_halo() {
                                  pack_indicies[ph].ptr, pk[k]->ptr, cap, &send[k]))
             fail("halo_pack");
           if (send[k] <= cap) break;
-          ensure_bytes(*pk[k], (size_t)(send[k] * 1.1 + 16) * kParticleBytes); // :319-327
-          if ((size_t)send[k] > pack_indicies[ph].extent() && !pack_indicies[ph].alloc((size_t)(send[k] * 1.1) + 16)) fail("alloc pack_indicies");
+          ensure_bytes(*pk[k], (size_t)(send[k] * 1.5 + 1024) * kParticleBytes); // :319-327
+          if ((size_t)send[k] > pack_indicies[ph].extent() && !pack_indicies[ph].alloc((size_t)(send[k] * 1.5) + 1024)) fail("alloc pack_indicies");
         }
         proc_num_send[ph] = send[k];
       }
@@ -184,7 +184,7 @@ void CommMPI::exchange_halo() {
         bool redo = false;
         if (N_local + N_ghost + count > system->N_max) { system->grow(N_local + N_ghost + count + count / 4); redo = true; }
         if ((size_t)count > pack_indicies[phase].extent()) {
-          if (!pack_indicies[phase].alloc((size_t)(count * 1.1) + 1)) fail("alloc pack_indicies");
+          if (!pack_indicies[phase].alloc((size_t)(count * 1.5) + 1024)) fail("alloc pack_indicies");
           redo = true;
         }
         if (!redo) break;
@@ -208,7 +208,7 @@ void CommMPI::exchange_halo() {
   for (int phase = 0; phase < 2 * local_dims; phase++) local_ghosts += proc_num_recv[phase];
   if (local_dims > 0 && local_ghosts > 0) {
     if (local_root.extent() < (size_t)local_ghosts) {
-      if (!local_root.alloc((size_t)local_ghosts + local_ghosts / 8) || !local_shift.alloc(3 * ((size_t)local_ghosts + local_ghosts / 8))) fail("alloc local roots");
+      if (!local_root.alloc((size_t)local_ghosts + local_ghosts / 2 + 16) || !local_shift.alloc(3 * ((size_t)local_ghosts + local_ghosts / 2 + 16))) fail("alloc local roots");
     }
     const int *lists[6];
     int counts[6];

@@ -40,7 +40,7 @@ void CommSerial::exchange_halo() {
         redo = true;
       }
       if ((size_t)count > pack_indicies[phase].extent()) { // :80-84
-        if (!pack_indicies[phase].alloc((size_t)(count * 1.1) + 1)) fail("alloc pack_indicies");
+        if (!pack_indicies[phase].alloc((size_t)(count * 1.5) + 1024)) fail("alloc pack_indicies");
         redo = true;
       }
       if (!redo) break;
@@ -51,7 +51,7 @@ void CommSerial::exchange_halo() {
   system->N_ghost = N_ghost;
   // resolve every ghost to its owned root atom + total shift for the single-kernel refresh
   if (ghost_root.extent() < (size_t)N_ghost) {
-    if (!ghost_root.alloc((size_t)N_ghost + N_ghost / 8 + 1) || !ghost_shift.alloc(3 * ((size_t)N_ghost + N_ghost / 8 + 1))) fail("alloc ghost_root");
+    if (!ghost_root.alloc((size_t)N_ghost + N_ghost / 2 + 1) || !ghost_shift.alloc(3 * ((size_t)N_ghost + N_ghost / 2 + 1))) fail("alloc ghost_root");
   }
   const int *lists[6];
   int counts[6];
