@@ -124,7 +124,7 @@ void CommMPI::exchange() {
     fail("compact");
   system->N_local = N_local;
   system->N_ghost = 0;
-  if (dbg) { emd_ctx_sync(ctx); if (g_n_calls++ >= 5) g_t_exchange += now_s() - t0; }
+  if (dbg) { emd_ctx_sync(ctx); if (g_n_calls++ >= 5) g_t_exchange += now_s() - t0; if (getenv("EMD_COMM_TRACE") && proc_rank == 0) fprintf(stderr, "TRACE exchange %.3f ms\n", 1e3 * (now_s() - t0)); }
 }
 
 // src/comm_types/comm_mpi.cpp:291-380
@@ -223,7 +223,7 @@ void CommMPI::exchange_halo() {
     if (!system->x_alt) { emd_peer_destroy(peer); peer = nullptr; }
     else if (emd_peer_publish(peer, &dec, system->x, system->x_alt, ghost_begin)) fail("peer publish");
   }
-  if (dbg) { emd_ctx_sync(ctx); if (g_n_calls > 5) g_t_publish += now_s() - t1; }
+  if (dbg) { emd_ctx_sync(ctx); if (g_n_calls > 5) g_t_publish += now_s() - t1; if (getenv("EMD_COMM_TRACE") && proc_rank == 0) fprintf(stderr, "TRACE exchange_halo %.3f ms publish %.3f ms\n", 1e3 * (t1 - t0), 1e3 * (now_s() - t1)); }
 }
 
 // src/comm_types/comm_mpi.cpp:382-423: no host synchronisation anywhere in here.  The two phases of a dimension do not

@@ -317,7 +317,8 @@ static int pack_common(emd_ctx *ctx, bool halo, int phase, const emd_decomp *dec
   if (phase_geometry(phase, dec, domain, depth, halo, &dim, &upper, &thr, &shift)) return 1;
   int count = 0;
   if (n_scan > 0) {
-    if (ctx->s_a.ensure(sizeof(int) * (2 * (size_t)n_scan + 2))) return 1;
+    // (sized for emd_comm_exchange_compact as well, which first runs when the first atom migrates: no allocation then)
+    if (ctx->s_a.ensure(sizeof(int) * (4 * (size_t)n_scan + 4096))) return 1;
     int *flags = ctx->s_a.as<int>(), *offsets = flags + n_scan, *d_total = offsets + n_scan;
     if (halo) EMD_LAUNCH(ctx, (flag_kernel<1>), grid_for(n_scan, 256), 256, 0, d_x, d_type, n_scan, dim, upper, thr, flags);
     else EMD_LAUNCH(ctx, (flag_kernel<0>), grid_for(n_scan, 256), 256, 0, d_x, d_type, n_scan, dim, upper, thr, flags);
