@@ -130,6 +130,7 @@ _SIGS = {
                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "emd_snap_device_ptr": (_P, [_P, C.c_char_p]),
     "emd_force_snap_compute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(NeighList)]),
+    "emd_snap_yi_plan_stats": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "emd_force_snap_energy": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(NeighList), C.c_int, C.POINTER(C.c_double)]),
     "emd_nve_initial_integrate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double]),
     "emd_nve_final_initial_integrate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double]),

@@ -906,30 +906,17 @@ __global__ void __launch_bounds__(256) snap_energy_kernel(const SnapTab *__restr
   }
 }
 
-size_t ui_smem(const SnapTab &h) { return (size_t)h.nuh * 32 * sizeof(double2) + (size_t)kUiGeomIt * 2 * 5 * 32 * sizeof(double); }
-size_t yi_smem(const SnapTab &h, int ntab, int nsegs) {
-  return ((size_t)h.nuf + kYiFrontPad + kYiBackPad) * 32 * sizeof(double2) + sizeof(double) * (size_t)ntab + sizeof(int4) * (size_t)nsegs +
-         sizeof(double) * (size_t)h.nelements * kMaxTriples;
-}
-size_t de_smem(const SnapTab &h) { return ((size_t)kMaxJ * 4 * kDeThreads + (size_t)kDeStageAtoms * h.nuh) * sizeof(double2); }
+// ------------------------------------------------------------------ host: index tables and the snap_yi plan (no CUDA calls)
+struct T3 { int j1, j2, j; };
+const struct { int idx, j1, j2, j, cgoff; } kTri[] = {
+#define X(IDX, TJ1, TJ2, TJ, CGOFF) {IDX, TJ1, TJ2, TJ, CGOFF},
+#include "snap_triples.inc"
+#undef X
+};
+static_assert(sizeof kTri / sizeof kTri[0] == kMaxTriples, "snap_triples.inc must list the 125 blocks of twojmax = 8");
 
-} // namespace
-
-extern "C" {
-
-int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
-  if (!out || !p) { set_error("emd_snap_create: NULL argument"); return 1; }
-  if (p->twojmax < 0 || p->twojmax > kMaxJ) { set_error("emd_snap_create: twojmax %d not in [0,%d]", p->twojmax, kMaxJ); return 1; }
-  if (p->ntypes < 1 || p->ntypes > kMaxTypesConst || p->nelements < 1 || p->nelements > kMaxTypesConst) {
-    set_error("emd_snap_create: ntypes/nelements out of range"); return 1;
-  }
-  emd_snap *s = new emd_snap();
-  SnapTab &h = s->h;
-  memset(&h, 0, sizeof h);
-  const int J2 = p->twojmax;
-  h.twojmax = J2; h.ncol = J2 / 2 + 1; h.ntypes = p->ntypes; h.nelements = p->nelements; h.switchflag = p->switchflag;
-  h.rcutfac = p->rcutfac; h.rfac0 = p->rfac0; h.rmin0 = p->rmin0; h.wself = p->wself;
-  { const char *e = getenv("EMD_SNAP_DEIDRJ_DIRECT"); h.unit_min_ar = (e && atoi(e)) ? 2.0 : 0.25; }
+// layouts of U (half / full range), the expansion table, the blocks (j1,j2,j) of twojmax = 8 and their Clebsch-Gordan factors
+int build_index_tables(SnapTab &h, int J2, std::vector<T3> &full, std::vector<double> &cg) {
   int nuh = 0, nuf = 0;
   for (int j = 0; j <= J2; j++) { h.uh_block[j] = nuh; nuh += (j / 2 + 1) * (j + 1); h.uf_block[j] = nuf; nuf += (j + 1) * (j + 1); }
   h.nuh = nuh; h.nuf = nuf;
@@ -941,45 +928,15 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
         const int img = h.uf_block[j] + (j - ma) * (j + 1) + (j - mb) + 1;
         h.exp_img[e] = (short)(2 * mb == j ? 0 : (((ma + mb) & 1) ? -img : img));
       }
-  for (int pp = 1; pp <= J2; pp++) // init_rootpqarray, sna_impl.hpp:1053-1061
-    for (int q = 1; q <= J2; q++) h.rootpq[pp * kRootDim + q] = sqrt(static_cast<double>(pp) / q);
-  double rcutmax = 0.0; // force_snap_neigh_impl.h:321-329
-  for (int e = 0; e < p->nelements; e++) {
-    h.radelem[e] = p->radelem[e]; h.wjelem[e] = p->wjelem[e];
-    rcutmax = std::max(2.0 * p->radelem[e] * p->rcutfac, rcutmax);
-  }
-  h.cutsq = rcutmax * rcutmax;
-  for (int ty = 0; ty < p->ntypes; ty++) h.elem_of_type[ty] = p->elem_of_type[ty];
-
-  // index lists (build_indexlist, sna_impl.hpp:86-132, diagonalstyle 3): idxj = the ncoeff bispectrum components of THIS
-  // twojmax; the Z blocks (idxj_full) are always the twojmax = 8 list of snap_triples.inc (sorted by j), of which a
-  // smaller twojmax uses the blocks with j1 <= twojmax
-  struct T3 { int j1, j2, j; };
-  std::vector<T3> idxj;
-  for (int j1 = 0; j1 <= J2; j1++)
-    for (int j2 = 0; j2 <= j1; j2++)
-      for (int j = abs(j1 - j2); j <= imin(J2, j1 + j2); j += 2)
-        if (j >= j1) idxj.push_back({j1, j2, j});
-  s->ncoeff = (int)idxj.size();
-  if (s->ncoeff != p->ncoeffall - 1) { // :315-318
-    set_error("emd_snap_create: coefficient count %d does not match twojmax %d (expected %d + 1)", p->ncoeffall, J2, s->ncoeff);
-    delete s; return 1;
-  }
-  static const struct { int idx, j1, j2, j, cgoff; } kTri[] = {
-#define X(IDX, TJ1, TJ2, TJ, CGOFF) {IDX, TJ1, TJ2, TJ, CGOFF},
-#include "snap_triples.inc"
-#undef X
-  };
-  static_assert(sizeof kTri / sizeof kTri[0] == kMaxTriples, "snap_triples.inc must list the 125 blocks of twojmax = 8");
-  std::vector<T3> full;
   h.ntriples = kMaxTriples;
-  std::vector<double> cg(kNumCg, 0.0);
+  cg.assign(kNumCg, 0.0);
+  full.clear();
   for (int tI = 0; tI < kMaxTriples; tI++) {
     const int j1 = kTri[tI].j1, j2 = kTri[tI].j2, j = kTri[tI].j;
     full.push_back({j1, j2, j});
     h.triple[tI].j1 = (short)j1; h.triple[tI].j2 = (short)j2; h.triple[tI].j = (short)j; h.triple[tI].cgoff = kTri[tI].cgoff;
     if (kTri[tI].idx != tI || kTri[tI].cgoff + (j1 + 1) * (j2 + 1) > kNumCg || (tI > 0 && full[tI - 1].j > j)) {
-      set_error("emd_snap_create: snap_triples.inc is inconsistent"); delete s; return 1;
+      set_error("emd_snap_create: snap_triples.inc is inconsistent"); return 1;
     }
     for (int m1 = 0; m1 <= j1; m1++)
       for (int m2 = 0; m2 <= j2; m2++) cg[kTri[tI].cgoff + m1 * (j2 + 1) + m2] = clebsch_gordan(j1, j2, j, m1, m2);
@@ -989,34 +946,14 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
     while (tI < h.ntriples && full[tI].j < j) tI++;
     h.tri_begin[j] = tI;
   }
-  auto tri_index = [&](int a, int b, int c) {
-    for (int tI = 0; tI < h.ntriples; tI++)
-      if (full[tI].j1 == a && full[tI].j2 == b && full[tI].j == c) return tI;
-    return -1;
-  };
-  // betaj: the coefficient of every Z block in Y (fold of compute_dbidrj's three sums, :393-527, with beta)
-  std::vector<double> betaj((size_t)p->nelements * h.ntriples, 0.0), betaj_e((size_t)p->nelements * h.ntriples, 0.0), e0(2 * (size_t)p->nelements, 0.0);
-  for (int e = 0; e < p->nelements; e++) {
-    const double *coeff = p->coeffelem + (size_t)e * p->ncoeffall;
-    double *bj = betaj.data() + (size_t)e * h.ntriples;
-    for (int JJ = 0; JJ < s->ncoeff; JJ++) {
-      const int j1 = idxj[JJ].j1, j2 = idxj[JJ].j2, j = idxj[JJ].j;
-      const double b = coeff[JJ + 1];
-      const int t1 = tri_index(imax(j1, j2), imin(j1, j2), j);
-      const int t2 = tri_index(imax(j, j2), imin(j, j2), j1);
-      const int t3 = tri_index(imax(j1, j), imin(j1, j), j2);
-      if (t1 < 0 || t2 < 0 || t3 < 0) { set_error("emd_snap_create: internal index error"); delete s; return 1; }
-      bj[t1] += b;
-      bj[t2] += b * ((j + 1) / (j1 + 1.0));
-      bj[t3] += b * ((j + 1) / (j2 + 1.0));
-      betaj_e[(size_t)e * h.ntriples + t1] += b;
-      e0[2 * e + 1] -= b * (p->wself * p->wself * p->wself) * (j + 1); // bzero[j] of SNA::init (LAMMPS sna.cpp)
-    }
-    e0[2 * e] = coeff[0];
-    e0[2 * e + 1] += coeff[0];
-  }
+  return 0;
+}
+
+// the work items, segments and step table of snap_yi (see the kernel's header)
+int build_yi_plan(SnapTab &h, int J2, const std::vector<T3> &full, const std::vector<double> &cg, std::vector<double> &steptab,
+                  std::vector<YiSeg> &segs) {
   // snap_yi's step table: for block tI, step mb2 and output k the factor cg(mb1 = C + k - mb2, mb2), 0 outside the block
-  std::vector<double> steptab;
+  steptab.clear();
   std::vector<int> tab_off(kMaxTriples, 0), tab_stride(kMaxTriples, 0);
   for (int tI = 0; tI < kMaxTriples; tI++) {
     const int j1 = full[tI].j1, j2 = full[tI].j2, j = full[tI].j, C = (j1 + j2 - j) / 2;
@@ -1068,9 +1005,9 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
             bk.cost += (long)(phi - plo + 1) * (nsteps * (10 * nmb + 4) + 16) + 24;
             // what is left of either range is one ma1 at its outer end
             if (lo0 < plo) { bk.seg[1] = make_seg(tI, j, ma, nmb, lo0, plo - 1); bk.has[1] = true; }
-            if (hi0 > phi) { set_error("emd_snap_create: internal range error"); delete s; return 1; }
+            if (hi0 > phi) { set_error("emd_snap_create: internal range error"); return 1; }
             if (hi1 > phi) { bk.seg[2] = make_seg(tI, j, ma + 1, nmb, phi + 1, hi1); bk.has[2] = true; }
-            if (lo1 < plo) { set_error("emd_snap_create: internal range error"); delete s; return 1; }
+            if (lo1 < plo) { set_error("emd_snap_create: internal range error"); return 1; }
           } else {
             if (lo0 <= hi0) { bk.seg[1] = make_seg(tI, j, ma, nmb, lo0, hi0); bk.has[1] = true; }
             if (lo1 <= hi1) { bk.seg[2] = make_seg(tI, j, ma + 1, nmb, lo1, hi1); bk.has[2] = true; }
@@ -1094,9 +1031,9 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
       ma += rows;
     }
   std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) { return x.cost > y.cost; });
-  if ((int)items.size() > kMaxItems) { set_error("emd_snap_create: too many snap_yi work items"); delete s; return 1; }
+  if ((int)items.size() > kMaxItems) { set_error("emd_snap_create: too many snap_yi work items"); return 1; }
   h.nitems = (int)items.size();
-  std::vector<YiSeg> segs;
+  segs.clear();
   for (int k = 0; k < h.nitems; k++) {
     const Item &it = items[k];
     h.item[k].j = (short)it.j; h.item[k].ma = (short)it.ma; h.item[k].rows = (short)it.rows; h.item[k].nmb = (short)it.nmb;
@@ -1108,6 +1045,145 @@ int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
     h.item[k].seg[3] = (int)segs.size();
   }
   segs.push_back(YiSeg{}); // the kernel fetches one descriptor ahead
+  return 0;
+}
+
+size_t ui_smem(const SnapTab &h) { return (size_t)h.nuh * 32 * sizeof(double2) + (size_t)kUiGeomIt * 2 * 5 * 32 * sizeof(double); }
+size_t yi_smem(const SnapTab &h, int ntab, int nsegs) {
+  return ((size_t)h.nuf + kYiFrontPad + kYiBackPad) * 32 * sizeof(double2) + sizeof(double) * (size_t)ntab + sizeof(int4) * (size_t)nsegs +
+         sizeof(double) * (size_t)h.nelements * kMaxTriples;
+}
+size_t de_smem(const SnapTab &h) { return ((size_t)kMaxJ * 4 * kDeThreads + (size_t)kDeStageAtoms * h.nuh) * sizeof(double2); }
+
+} // namespace
+
+extern "C" {
+
+// Host-only self-check of the snap_yi plan for a given twojmax (no device needed; tests/test_snap_plan.py): every (block, output row,
+// ma1) of compute_zi (sna_impl.hpp:196-283) that has a non-empty mb range must be covered by exactly one segment row.  Returns the
+// plan's sizes, the Clebsch-Gordan terms it executes and the non-zero ones among them.
+int emd_snap_yi_plan_stats(int twojmax, int *nitems, int *nsegs, int *ntab, long long *terms_executed, long long *terms_nonzero) {
+  if (twojmax < 0 || twojmax > kMaxJ) { set_error("emd_snap_yi_plan_stats: twojmax %d not in [0,%d]", twojmax, kMaxJ); return 1; }
+  SnapTab *hp = new SnapTab();
+  SnapTab &h = *hp;
+  memset(&h, 0, sizeof h);
+  h.twojmax = twojmax; h.ncol = twojmax / 2 + 1;
+  std::vector<T3> full;
+  std::vector<double> cg, steptab;
+  std::vector<YiSeg> segs;
+  if (build_index_tables(h, twojmax, full, cg) || build_yi_plan(h, twojmax, full, cg, steptab, segs)) { delete hp; return 1; }
+  std::vector<int> cover((size_t)kMaxTriples * (kMaxJ + 1) * (kMaxJ + 1), 0);
+  long long exec = 0, nonzero = 0;
+  for (int it = 0; it < h.nitems; it++) {
+    const int j = h.item[it].j, nmb = h.item[it].nmb;
+    for (int q = 0; q < 3; q++)
+      for (int sg = h.item[it].seg[q]; sg < h.item[it].seg[q + 1]; sg++) {
+        const YiSeg &g = segs[sg];
+        const int j1 = full[g.tr].j1, j2 = full[g.tr].j2, C = (j1 + j2 - j) / 2;
+        if (full[g.tr].j != j) { set_error("emd_snap_yi_plan_stats: segment of another level"); delete hp; return 1; }
+        const int lo = (g.a_off - h.uf_block[j1] - C) / (j1 + 1), ma2 = (g.w_off - h.uf_block[j2]) / (j2 + 1);
+        const int rows = q == 0 ? 2 : 1;
+        for (int r = 0; r < g.nrows; r++)
+          for (int o = 0; o < rows; o++) {
+            const int ma1 = lo + r, ma = ma2 - r + o - C + ma1; // ma2 of this row = ma2 - r (+ o for the second output row)
+            const int want = h.item[it].ma + (q == 2 ? 1 : o);
+            if (ma != want || ma1 < 0 || ma1 > j1) { set_error("emd_snap_yi_plan_stats: segment row does not belong to its item"); delete hp; return 1; }
+            cover[((size_t)g.tr * (kMaxJ + 1) + ma) * (kMaxJ + 1) + ma1]++;
+            exec += (long long)g.nsteps * nmb;
+            for (int st = 0; st < g.nsteps; st++)
+              for (int k = 0; k < nmb; k++) nonzero += steptab[g.tab_off + st * g.tab_stride + k] != 0.0;
+          }
+      }
+  }
+  for (int tI = 0; tI < kMaxTriples; tI++) {
+    const int j1 = full[tI].j1, j2 = full[tI].j2, j = full[tI].j, C = (j1 + j2 - j) / 2;
+    for (int ma = 0; ma <= j; ma++)
+      for (int ma1 = 0; ma1 <= kMaxJ; ma1++) {
+        const int nmb = j / 2 + 1 - ((j % 2 == 0 && ma > j / 2) ? 1 : 0);
+        const bool needed = j1 <= twojmax && j <= twojmax && nmb > 0 && ma1 <= j1 && ma + C - ma1 >= 0 && ma + C - ma1 <= j2;
+        if (cover[((size_t)tI * (kMaxJ + 1) + ma) * (kMaxJ + 1) + ma1] != (needed ? 1 : 0)) {
+          set_error("emd_snap_yi_plan_stats: block %d row %d ma1 %d covered %d times", tI, ma, ma1, cover[((size_t)tI * (kMaxJ + 1) + ma) * (kMaxJ + 1) + ma1]);
+          delete hp; return 1;
+        }
+      }
+  }
+  if (nitems) *nitems = h.nitems;
+  if (nsegs) *nsegs = (int)segs.size();
+  if (ntab) *ntab = (int)steptab.size();
+  if (terms_executed) *terms_executed = exec;
+  if (terms_nonzero) *terms_nonzero = nonzero;
+  delete hp;
+  return 0;
+}
+
+int emd_snap_create(emd_snap **out, const emd_snap_params *p) {
+  if (!out || !p) { set_error("emd_snap_create: NULL argument"); return 1; }
+  if (p->twojmax < 0 || p->twojmax > kMaxJ) { set_error("emd_snap_create: twojmax %d not in [0,%d]", p->twojmax, kMaxJ); return 1; }
+  if (p->ntypes < 1 || p->ntypes > kMaxTypesConst || p->nelements < 1 || p->nelements > kMaxTypesConst) {
+    set_error("emd_snap_create: ntypes/nelements out of range"); return 1;
+  }
+  emd_snap *s = new emd_snap();
+  SnapTab &h = s->h;
+  memset(&h, 0, sizeof h);
+  const int J2 = p->twojmax;
+  h.twojmax = J2; h.ncol = J2 / 2 + 1; h.ntypes = p->ntypes; h.nelements = p->nelements; h.switchflag = p->switchflag;
+  h.rcutfac = p->rcutfac; h.rfac0 = p->rfac0; h.rmin0 = p->rmin0; h.wself = p->wself;
+  { const char *e = getenv("EMD_SNAP_DEIDRJ_DIRECT"); h.unit_min_ar = (e && atoi(e)) ? 2.0 : 0.25; }
+  std::vector<T3> full;
+  std::vector<double> cg;
+  if (build_index_tables(h, J2, full, cg)) { delete s; return 1; }
+  for (int pp = 1; pp <= J2; pp++) // init_rootpqarray, sna_impl.hpp:1053-1061
+    for (int q = 1; q <= J2; q++) h.rootpq[pp * kRootDim + q] = sqrt(static_cast<double>(pp) / q);
+  double rcutmax = 0.0; // force_snap_neigh_impl.h:321-329
+  for (int e = 0; e < p->nelements; e++) {
+    h.radelem[e] = p->radelem[e]; h.wjelem[e] = p->wjelem[e];
+    rcutmax = std::max(2.0 * p->radelem[e] * p->rcutfac, rcutmax);
+  }
+  h.cutsq = rcutmax * rcutmax;
+  for (int ty = 0; ty < p->ntypes; ty++) h.elem_of_type[ty] = p->elem_of_type[ty];
+
+  // index lists (build_indexlist, sna_impl.hpp:86-132, diagonalstyle 3): idxj = the ncoeff bispectrum components of THIS
+  // twojmax; the Z blocks (idxj_full) are always the twojmax = 8 list of snap_triples.inc (sorted by j), of which a
+  // smaller twojmax uses the blocks with j1 <= twojmax
+  std::vector<T3> idxj;
+  for (int j1 = 0; j1 <= J2; j1++)
+    for (int j2 = 0; j2 <= j1; j2++)
+      for (int j = abs(j1 - j2); j <= imin(J2, j1 + j2); j += 2)
+        if (j >= j1) idxj.push_back({j1, j2, j});
+  s->ncoeff = (int)idxj.size();
+  if (s->ncoeff != p->ncoeffall - 1) { // :315-318
+    set_error("emd_snap_create: coefficient count %d does not match twojmax %d (expected %d + 1)", p->ncoeffall, J2, s->ncoeff);
+    delete s; return 1;
+  }
+  auto tri_index = [&](int a, int b, int c) {
+    for (int tI = 0; tI < h.ntriples; tI++)
+      if (full[tI].j1 == a && full[tI].j2 == b && full[tI].j == c) return tI;
+    return -1;
+  };
+  // betaj: the coefficient of every Z block in Y (fold of compute_dbidrj's three sums, :393-527, with beta)
+  std::vector<double> betaj((size_t)p->nelements * h.ntriples, 0.0), betaj_e((size_t)p->nelements * h.ntriples, 0.0), e0(2 * (size_t)p->nelements, 0.0);
+  for (int e = 0; e < p->nelements; e++) {
+    const double *coeff = p->coeffelem + (size_t)e * p->ncoeffall;
+    double *bj = betaj.data() + (size_t)e * h.ntriples;
+    for (int JJ = 0; JJ < s->ncoeff; JJ++) {
+      const int j1 = idxj[JJ].j1, j2 = idxj[JJ].j2, j = idxj[JJ].j;
+      const double b = coeff[JJ + 1];
+      const int t1 = tri_index(imax(j1, j2), imin(j1, j2), j);
+      const int t2 = tri_index(imax(j, j2), imin(j, j2), j1);
+      const int t3 = tri_index(imax(j1, j), imin(j1, j), j2);
+      if (t1 < 0 || t2 < 0 || t3 < 0) { set_error("emd_snap_create: internal index error"); delete s; return 1; }
+      bj[t1] += b;
+      bj[t2] += b * ((j + 1) / (j1 + 1.0));
+      bj[t3] += b * ((j + 1) / (j2 + 1.0));
+      betaj_e[(size_t)e * h.ntriples + t1] += b;
+      e0[2 * e + 1] -= b * (p->wself * p->wself * p->wself) * (j + 1); // bzero[j] of SNA::init (LAMMPS sna.cpp)
+    }
+    e0[2 * e] = coeff[0];
+    e0[2 * e + 1] += coeff[0];
+  }
+  std::vector<double> steptab;
+  std::vector<YiSeg> segs;
+  if (build_yi_plan(h, J2, full, cg, steptab, segs)) { delete s; return 1; }
   if (steptab.size() % 2) steptab.push_back(0.0);
   s->ntab = (int)steptab.size();
   if (steptab.size() > 0xffff) { set_error("emd_snap_create: step table too long for the packed descriptors"); delete s; return 1; }

@@ -259,6 +259,10 @@ typedef struct emd_snap emd_snap;
 /* SNA::SNA + SNA::init (sna_impl.hpp:25-53,136-140): index lists, Clebsch-Gordan and sqrt(p/q) tables,
  * plus the beta-folded block coefficients of the adjoint formulation; uploads them to the device */
 int emd_snap_create(emd_snap **out, const emd_snap_params *p);
+/* host-only self-check of snap_yi's work plan (items / segments / step table built by emd_snap_create): every (block, output
+ * row, ma1) of compute_zi (sna_impl.hpp:196-283) is covered exactly once; returns the plan's sizes, the Clebsch-Gordan terms it
+ * executes and the non-zero ones among them.  Needs no device. */
+int emd_snap_yi_plan_stats(int twojmax, int *nitems, int *nsegs, int *ntab, long long *terms_executed, long long *terms_nonzero);
 void emd_snap_destroy(emd_snap *s);
 /* ncoeff (sna.ncoeff), U/Y elements per atom on the half range, Z blocks, rcutmax (:321-327), and of the
  * last compute: in-cutoff pairs and the atom stride of the U array.  Any pointer may be NULL. */
