@@ -116,6 +116,7 @@ _SIGS = {
     "emd_force_lj_compute_tiles_with_energy": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
     "emd_force_lj_compute_tiles_part": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "emd_force_lj_compute_tiles_nve": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double]),
+    "emd_force_lj_compute_tiles_nve_thermo": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "emd_force_lj_compute_tiles_part_nve": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_double, C.c_double]),
     "emd_tiles_complete": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "emd_tiles_halo_split": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

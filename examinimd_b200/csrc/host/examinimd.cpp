@@ -166,6 +166,7 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next, bool observ
   T_V_FLOAT nve_factors[2] = {0.0, 0.0};
   static const bool fuse_nve = !(getenv("EMD_NO_FUSED_NVE") && atoi(getenv("EMD_NO_FUSED_NVE")));
   if (tm) tm->begin();
+  system->mv2_cached = false; // (a thermo sum left by the force launch of the step before)
   if (!initial_done) integrator->initial_integrate();
   initial_done = false;
   if (tm) tm->end(PhaseTimers::OTHER);
@@ -213,8 +214,12 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next, bool observ
     kicked = split_kick;
   } else {
     T_V_FLOAT dtf = 0.0, dtv = 0.0;
-    if (fuse_next && fuse_nve && !input->comm_newton && integrator->step_factors(&dtf, &dtv))
+    if (fuse_next && fuse_nve && !input->comm_newton && integrator->step_factors(&dtf, &dtv)) {
+      // on a thermo step the fused launch also sums the energy and m v^2 of the velocities between its two kicks (the state
+      // thermo reads in the reference), so the step keeps the fused integrator; a force that cannot do that declines
+      force->expect_energy(observed);
       kicked = force->compute_with_nve(system, binning, neighbor, dtf, dtv);
+    }
     if (!kicked) {
       if (!force->zeroes_forces())
         emd_memset_zero(system->ctx, system->f, sizeof(T_F_FLOAT) * 3 * (size_t)system->N_max);
@@ -230,7 +235,7 @@ void ExaMiniMD::step_once(int step, PhaseTimers *tm, bool fuse_next, bool observ
   }
 
   if (kicked) initial_done = true;
-  else if (fuse_next && fuse_nve) { integrator->final_initial_integrate(); initial_done = true; }
+  else if (fuse_next && fuse_nve && !observed) { integrator->final_initial_integrate(); initial_done = true; }
   else integrator->final_integrate();
   if (tm) tm->end(PhaseTimers::OTHER);
 }
@@ -244,7 +249,7 @@ void ExaMiniMD::run_quiet(int nsteps, T_FLOAT *last_thermo3) {
   for (int s = 1; s <= nsteps; s++) {
     const int step = ++current_step;
     const bool observed = input->thermo_rate > 0 && step % input->thermo_rate == 0;
-    step_once(step, nullptr, s < nsteps && !observed, observed);
+    step_once(step, nullptr, s < nsteps, observed); // (an observed step fuses only if the force launch can serve thermo itself)
     if (observed) {
       T_FLOAT T, PE, KE;
       thermo(&T, &PE, &KE);
@@ -261,9 +266,11 @@ void ExaMiniMD::run(int nsteps) {
 
   for (int s = 1; s <= nsteps; s++) {
     const int step = ++current_step;
-    // thermo output, dumps and the correctness check read x, v, f between two steps: no fusion across them
-    const bool observed = (input->thermo_rate > 0 && step % input->thermo_rate == 0) || input->dumpbinaryflag || input->correctnessflag;
-    step_once(step, &tm, s < nsteps && !observed, input->thermo_rate > 0 && step % input->thermo_rate == 0);
+    // dumps and the correctness check read x, v, f between two steps: no fusion across them; thermo output alone can be served
+    // by the force launch (step_once)
+    const bool thermo_step = input->thermo_rate > 0 && step % input->thermo_rate == 0;
+    const bool state_read = input->dumpbinaryflag || input->correctnessflag; // these read x, v, f themselves
+    step_once(step, &tm, s < nsteps && !state_read, thermo_step || state_read);
 
     if (input->thermo_rate > 0 && step % input->thermo_rate == 0) {
       T_FLOAT T, PE, KE;

@@ -61,8 +61,15 @@ bool ForceLJNeigh::compute_with_nve(System *system, Binning *, Neighbor *neighbo
   emd_tiles *t = neighbor->tiles();
   if (off || !t || comm_newton || !system->x_alt) return false;
   pe_cached = false;
-  const int rc = emd_force_lj_compute_tiles_nve(system->ctx, t, system->x, system->type, system->f, system->v, system->x_alt, system->mass,
-                                                dtf, dtv);
+  int rc;
+  if (want_energy) { // a thermo step: the launch also sums the potential energy and m v^2 between the two kicks
+    double mv2 = 0.0;
+    rc = emd_force_lj_compute_tiles_nve_thermo(system->ctx, t, system->x, system->type, system->f, system->v, system->x_alt, system->mass,
+                                               dtf, dtv, &pe_cache, &mv2);
+    if (rc == 0) { pe_cached = true; system->mv2_cached = true; system->mv2_cache = mv2; }
+  } else
+    rc = emd_force_lj_compute_tiles_nve(system->ctx, t, system->x, system->type, system->f, system->v, system->x_alt, system->mass,
+                                        dtf, dtv);
   if (rc == 3) return false; // an owned atom without a row: separate kernels
   if (rc) fail("compute_with_nve (tiles)");
   system->swap_x();

@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 static T_V_FLOAT sum_mv2(System *system) {
+  if (system->mv2_cached) return system->mv2_cache; // summed by the fused force + integrator launch of this (thermo) step
   double s = 0.0;
   if (emd_reduce_mv2(system->ctx, system->v, system->type, system->mass, system->N_local, &s)) {
     fprintf(stderr, "thermo reduction failed: %s\n", emd_last_error());

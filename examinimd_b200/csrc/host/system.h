@@ -42,6 +42,10 @@ public:
   T_X_FLOAT sub_domain_hi_x, sub_domain_hi_y, sub_domain_hi_z;
 
   T_FLOAT boltz, mvv2e, dt;
+  // sum m v^2 of the velocities thermo sees, left by a force launch that took the integrator kicks along on a thermo step
+  // (Force::compute_with_nve after expect_energy(true)); valid until the next step begins
+  bool mv2_cached = false;
+  double mv2_cache = 0.0;
   bool do_print, print_lammps;
 
   emd_ctx *ctx; // device context all modules launch on

@@ -710,16 +710,20 @@ constexpr int kProdUnroll = 16;
 // atom whose force was just accumulated (src/integrator_nve.cpp:47-74, 87-112: same operations, same order, so v and x are
 // bit-identical to the separate kernels): v is updated in place, the new position goes to a SECOND position array because
 // other CTAs still stage the old coordinates (the host swaps the two arrays after the launch).
-struct NveFuse { double *v; double *x_new; const double *mass; double dtf, dtv; };
-enum { MODE_FORCE = 0, MODE_ENERGY = 1, MODE_NVE = 2, MODE_FORCE_ENERGY = 3 };
+struct NveFuse { double *v; double *x_new; const double *mass; double dtf, dtv; double *mv2_partial; };
+// MODE_NVE_THERMO: MODE_NVE on a thermo step -- the pass also returns the potential energy (positions of this step) and
+// sum m v^2 of the velocities between the two kicks, i.e. what Temperature / PotE / KinE (property_*.cpp) read after
+// final_integrate, so that a thermo step keeps the fused integrator and needs no reduction pass of its own
+enum { MODE_FORCE = 0, MODE_ENERGY = 1, MODE_NVE = 2, MODE_FORCE_ENERGY = 3, MODE_NVE_THERMO = 4 };
 
 struct HaloGate { const int *flags; int seq, mask; }; // common.cuh: the neighbours' ghost stores of this step (comm_peer.cu)
 
 template <bool ONETYPE, int MODE>
 __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, int first, int ntiles, int nbuf, unsigned ring_off, LJOne one, const LJTab *__restrict__ tab,
                                                                    double *__restrict__ f, double *__restrict__ pe_partial, NveFuse nve, HaloGate gate) {
-  constexpr bool ENERGY = MODE == MODE_ENERGY || MODE == MODE_FORCE_ENERGY;
-  __shared__ double s_red[kForceWarps];
+  constexpr bool ENERGY = MODE == MODE_ENERGY || MODE == MODE_FORCE_ENERGY || MODE == MODE_NVE_THERMO;
+  constexpr bool NVE = MODE == MODE_NVE || MODE == MODE_NVE_THERMO;
+  __shared__ double s_red[kForceWarps], s_red2[kForceWarps];
   __shared__ unsigned long long s_full[kMaxBuf], s_empty[kMaxBuf];
   extern __shared__ __align__(16) unsigned char dyn[];
   const unsigned buf_bytes = (unsigned)(a.fcap + kDummySlots) * 24u;           // [16 dummy atoms + fcap][3] doubles: x,y,z of a staged atom adjacent
@@ -828,7 +832,8 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
   double pe = 0.0;
   int b = 0;
   unsigned parity = 0u;
-  const double dtfm1 = (MODE == MODE_NVE && ONETYPE) ? nve.dtf / nve.mass[0] : 0.0; // integrator_nve.cpp:67,106 (one type: one mass)
+  double mv2 = 0.0;
+  const double dtfm1 = (NVE && ONETYPE) ? nve.dtf / nve.mass[0] : 0.0; // integrator_nve.cpp:67,106 (one type: one mass)
   for (int k = 0; k < my_tiles; k++) {
     const int i_cur = i_nxt, own_cur = own_nxt, n_cur = n_nxt, tile = tile_nxt;
     const bool has_row = i_cur < a.n_local;
@@ -843,7 +848,7 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
       cp_async_commit();
     }
     load_desc(k + 1);
-    if (MODE == MODE_NVE && has_row) { prefetch_l1(nve.v + 3 * (size_t)i_cur); prefetch_l1(nve.v + 3 * (size_t)i_cur + 2); } // the epilogue's v
+    if (NVE && has_row) { prefetch_l1(nve.v + 3 * (size_t)i_cur); prefetch_l1(nve.v + 3 * (size_t)i_cur + 2); } // the epilogue's v
     if (producer) {
       // buffer (k + nbuf - 1) mod nbuf held tile k - 1
       if (k > 0) {
@@ -873,10 +878,11 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
     }
     if (has_row) {
       if (MODE != MODE_ENERGY) { f[3 * (size_t)i_cur] = fx; f[3 * (size_t)i_cur + 1] = fy; f[3 * (size_t)i_cur + 2] = fz; }
-      if (MODE == MODE_NVE) {
+      if (NVE) {
         const double dtfm = ONETYPE ? dtfm1 : nve.dtf / nve.mass[type_i];
         double *vp = nve.v + 3 * (size_t)i_cur, *xp = nve.x_new + 3 * (size_t)i_cur;
         const double fi[3] = {fx, fy, fz}, xi[3] = {x_i, y_i, z_i};
+        double vv = 0.0;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
           const double kick = __dmul_rn(dtfm, fi[d]);
@@ -884,7 +890,9 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
           const double v2 = __dadd_rn(v1, kick);               // initial_integrate of the next step :68-70
           vp[d] = v2;
           xp[d] = __dadd_rn(xi[d], __dmul_rn(nve.dtv, v2));    // :71-73
+          if (MODE == MODE_NVE_THERMO) vv += v1 * v1;          // property_temperature.cpp:52-56 on the velocities thermo sees
         }
+        if (MODE == MODE_NVE_THERMO) mv2 += vv * nve.mass[ONETYPE ? 0 : type_i];
       }
     }
     __syncwarp();
@@ -896,11 +904,21 @@ __global__ void __launch_bounds__(kForceThreads, 2) lj_tiles_kernel(TileArgs a, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pe += __shfl_down_sync(0xffffffffu, pe, o);
     if (lane == 0) s_red[warp] = pe;
+    if (MODE == MODE_NVE_THERMO) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mv2 += __shfl_down_sync(0xffffffffu, mv2, o);
+      if (lane == 0) s_red2[warp] = mv2;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       double s = 0.0;
       for (int w = 0; w < kForceWarps; w++) s += s_red[w];
       pe_partial[blockIdx.x] = s;
+      if (MODE == MODE_NVE_THERMO) {
+        double s2 = 0.0;
+        for (int w = 0; w < kForceWarps; w++) s2 += s_red2[w];
+        nve.mv2_partial[blockIdx.x] = s2;
+      }
     }
   }
 }
@@ -1082,6 +1100,7 @@ static void warm_kernels() {
   EMD_WARM((lj_tiles_kernel<true, MODE_FORCE>)); EMD_WARM((lj_tiles_kernel<true, MODE_ENERGY>)); EMD_WARM((lj_tiles_kernel<true, MODE_NVE>));
   EMD_WARM((lj_tiles_kernel<true, MODE_FORCE_ENERGY>)); EMD_WARM((lj_tiles_kernel<false, MODE_FORCE>)); EMD_WARM((lj_tiles_kernel<false, MODE_ENERGY>));
   EMD_WARM((lj_tiles_kernel<false, MODE_NVE>)); EMD_WARM((lj_tiles_kernel<false, MODE_FORCE_ENERGY>));
+  EMD_WARM((lj_tiles_kernel<true, MODE_NVE_THERMO>)); EMD_WARM((lj_tiles_kernel<false, MODE_NVE_THERMO>));
   EMD_WARM(tiles_search_kernel); EMD_WARM(tiles_order_kernel); EMD_WARM(tiles_lists_kernel<true>); EMD_WARM(tiles_lists_kernel<false>);
   EMD_WARM(tiles_counts_kernel); EMD_WARM(tiles_fill_kernel<FILL_CSR>); EMD_WARM(tiles_fill_kernel<FILL_2D>);
 #undef EMD_WARM
@@ -1259,11 +1278,11 @@ int emd_neigh_tiles_fill_2d(emd_ctx *ctx, emd_tiles *t, int half, int newton, in
 // this step has landed); 2 = the rest.  reserve_ctas > 0 leaves that many CTA slots of the persistent grid free, so that
 // the pack and transport kernels of a concurrent halo exchange find room on the SMs.
 static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *h_pe, int part,
-                           int reserve_ctas, const NveFuse *fuse = nullptr, bool force_too = false) {
+                           int reserve_ctas, const NveFuse *fuse = nullptr, bool force_too = false, double *h_mv2 = nullptr) {
   if (!t || !t->valid) { set_error("emd_force_lj_compute_tiles: tiles not built"); return 1; }
   if (ctx->lj.ntypes == 0) { set_error("emd_force_lj_compute_tiles: parameters not set"); return 1; }
   if (part < 0 || part > 2 || (h_pe && part != 0)) { set_error("emd_force_lj_compute_tiles: bad part"); return 1; }
-  if (fuse && h_pe) { set_error("emd_force_lj_compute_tiles: the energy launch cannot carry the integrator"); return 1; }
+  if (fuse && (h_pe != nullptr) != (h_mv2 != nullptr)) { set_error("emd_force_lj_compute_tiles: the fused thermo launch returns both sums"); return 1; }
   if (!t->rows_ready || !t->checked) { // a build that nobody asked a CSR / 2D list of
     const int rc = ensure_lists(ctx, t, false, 0, 0, nullptr);
     if (rc) { if (rc == 3) set_error("emd_force_lj_compute_tiles: tile lists not available"); return rc == 3 ? 1 : rc; }
@@ -1271,7 +1290,7 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
   // an owned atom outside the interior bins has no row (the reference leaves it without neighbors, neighbor_csr.h:184):
   // its force is the zero of the reference's deep_copy(f, 0)
   if (!t->all_owned_have_rows && (!h_pe || force_too) && part == 0) EMD_CUDA(cudaMemsetAsync(d_f, 0, sizeof(double) * 3 * (size_t)t->a.n_local, ctx->stream));
-  const NveFuse nve = fuse ? *fuse : NveFuse{nullptr, nullptr, nullptr, 0.0, 0.0};
+  NveFuse nve = fuse ? *fuse : NveFuse{nullptr, nullptr, nullptr, 0.0, 0.0, nullptr};
   TileArgs a = t->a;
   a.x = d_x; a.type = d_type;
   const bool one = ctx->lj.ntypes == 1;
@@ -1301,19 +1320,22 @@ static int lj_tiles_launch(emd_ctx *ctx, emd_tiles *t, const double *d_x, const 
   const int grid = std::max(1, std::min(count, 2 * emd_ctx_side_sms(ctx) - std::max(0, reserve_ctas)));
   double *partial = nullptr;
   if (h_pe) {
-    if (ctx->s_c.ensure(sizeof(double) * ((size_t)grid + 8))) return 1;
+    if (ctx->s_c.ensure(sizeof(double) * (2 * (size_t)grid + 16))) return 1;
     partial = ctx->s_c.as<double>() + 8;
+    nve.mv2_partial = partial + grid + 8;
   }
 #define EMD_LJ_TILES(ONE, MD)                                                                                              \
   do {                                                                                                                     \
     if (set_smem(lj_tiles_kernel<ONE, MD>, smem)) return 1;                                                                \
     EMD_LAUNCH(ctx, (lj_tiles_kernel<ONE, MD>), grid, kForceThreads, smem, a, first, count, nbuf, (unsigned)force_coord_smem(a.fcap, !one, nbuf), p1, t->d_tab, d_f, partial, nve, gate); \
   } while (0)
-  if (fuse) { if (one) EMD_LJ_TILES(true, MODE_NVE); else EMD_LJ_TILES(false, MODE_NVE); }
+  if (fuse && h_pe) { if (one) EMD_LJ_TILES(true, MODE_NVE_THERMO); else EMD_LJ_TILES(false, MODE_NVE_THERMO); }
+  else if (fuse) { if (one) EMD_LJ_TILES(true, MODE_NVE); else EMD_LJ_TILES(false, MODE_NVE); }
   else if (h_pe && force_too) { if (one) EMD_LJ_TILES(true, MODE_FORCE_ENERGY); else EMD_LJ_TILES(false, MODE_FORCE_ENERGY); }
   else if (h_pe) { if (one) EMD_LJ_TILES(true, MODE_ENERGY); else EMD_LJ_TILES(false, MODE_ENERGY); }
   else { if (one) EMD_LJ_TILES(true, MODE_FORCE); else EMD_LJ_TILES(false, MODE_FORCE); }
 #undef EMD_LJ_TILES
+  if (h_pe && h_mv2) { if (int rc = device_sum_partials(ctx, nve.mv2_partial, grid, h_mv2)) return rc; }
   if (h_pe) return device_sum_partials(ctx, partial, grid, h_pe);
   return 0;
 }
@@ -1338,15 +1360,23 @@ int emd_force_lj_compute_tiles_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x
                                    double *d_x_new, const double *d_mass, double dtf, double dtv) {
   if (t && t->valid && t->checked && !t->all_owned_have_rows) return 3; // an owned atom has no row: its position would not be advanced
   if (!d_v || !d_x_new || !d_mass || d_x_new == d_x) { set_error("emd_force_lj_compute_tiles_nve: v, mass and a second position array are required"); return 1; }
-  const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv};
+  const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv, nullptr};
   return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, 0, 0, &nve);
+}
+
+int emd_force_lj_compute_tiles_nve_thermo(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, double *d_v,
+                                          double *d_x_new, const double *d_mass, double dtf, double dtv, double *h_pe, double *h_mv2) {
+  if (t && t->valid && t->checked && !t->all_owned_have_rows) return 3;
+  if (!d_v || !d_x_new || !d_mass || d_x_new == d_x || !h_pe || !h_mv2) { set_error("emd_force_lj_compute_tiles_nve_thermo: v, mass, a second position array and both results are required"); return 1; }
+  const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv, nullptr};
+  return lj_tiles_launch(ctx, t, d_x, d_type, d_f, h_pe, 0, 0, &nve, true, h_mv2);
 }
 
 int emd_force_lj_compute_tiles_part_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f, int part,
                                         int reserve_ctas, double *d_v, double *d_x_new, const double *d_mass, double dtf, double dtv) {
   if (t && t->valid && t->checked && !t->all_owned_have_rows) return 3;
   if (!d_v || !d_x_new || !d_mass || d_x_new == d_x) { set_error("emd_force_lj_compute_tiles_part_nve: v, mass and a second position array are required"); return 1; }
-  const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv};
+  const NveFuse nve = {d_v, d_x_new, d_mass, dtf, dtv, nullptr};
   return lj_tiles_launch(ctx, t, d_x, d_type, d_f, nullptr, part, reserve_ctas, &nve);
 }
 

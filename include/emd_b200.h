@@ -237,6 +237,13 @@ int emd_tiles_complete(const emd_tiles *t, int *all_owned_have_rows);
  * Returns 3 (nothing done) if an owned atom has no row in the tile lists (it sits outside the interior bins). */
 int emd_force_lj_compute_tiles_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f,
                                    double *d_v, double *d_x_new, const double *d_mass, double dtf, double dtv);
+/* the same on a thermo step: the pass also returns *h_pe = the potential energy of the owned atoms at d_x (as
+ * emd_force_lj_compute_tiles_with_energy) and *h_mv2 = sum m v^2 over the owned atoms of the velocities BETWEEN the two kicks,
+ * i.e. what Temperature / KinE (src/property_temperature.cpp:43-62, property_kine.cpp:43-61) sum after final_integrate; the
+ * thermo step then keeps the fused integrator and needs no reduction pass of its own */
+int emd_force_lj_compute_tiles_nve_thermo(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f,
+                                          double *d_v, double *d_x_new, const double *d_mass, double dtf, double dtv,
+                                          double *h_pe, double *h_mv2);
 /* the same for one part of a split force (emd_force_lj_compute_tiles_part): every owned atom belongs to exactly one part */
 int emd_force_lj_compute_tiles_part_nve(emd_ctx *ctx, emd_tiles *t, const double *d_x, const int *d_type, double *d_f,
                                         int part, int reserve_ctas, double *d_v, double *d_x_new, const double *d_mass,

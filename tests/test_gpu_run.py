@@ -92,6 +92,34 @@ def test_fused_integrator_is_bit_identical(emd):
     a.close(); b.close()
 
 
+def test_thermo_step_keeps_the_fused_integrator(emd, oracle_lib):
+    """run(n) (the reference's loop: thermo every 10 steps) serves a thermo step from the force launch itself: potential energy
+    at the step's positions and sum m v^2 of the velocities between the two kicks (what the reference's Temperature / PotE /
+    KinE read after final_integrate), with the integrator kicks still fused.  T, PE, KE of steps 10..40 against the oracle,
+    the trajectory bit for bit against the unfused sequence, and one launch per thermo step instead of force + energy +
+    integrator + reduction kernels."""
+    argv = ["-il", str(DECK), "--neigh-type", "CSR", "--force-iteration", "NEIGH_HALF", "--comm-type", "SERIAL", "--region", "12", "12", "12"]
+    a, b = emd.App(argv), emd.App(argv)
+    md = OracleMD.from_deck(DECK, "CSR", "NEIGH_HALF", region=(12, 12, 12))
+    # a thermo step takes the fused path unless it is the last step of the call: run(15) returns the thermo of step 10, the next
+    # run(10) (steps 16..25) that of step 20 (a re-neighboring step as well), ...
+    done = 0
+    for n_run, at in ((15, 10), (10, 20), (10, 30)):
+        T, PE, KE = a.run(n_run)
+        md.step(at - done)
+        To, PEo, KEo = md.thermo()
+        assert abs(T - To) < 1e-10 * abs(To) and abs(PE - PEo) < 1e-10 * abs(PEo) and abs(KE - KEo) < 1e-10 * abs(KEo), (at, T, To, PE, PEo, KE, KEo)
+        done += n_run
+        md.step(done - at)
+    a.run(60 - done)
+    for _ in range(60):
+        b.advance(1)
+    sa, sb = a.download(), b.download()
+    for k in ("id", "x", "v", "f"):
+        np.testing.assert_array_equal(sa[k], sb[k])
+    a.close(); b.close(); md.close()
+
+
 @pytest.mark.parametrize("no_tiles", ["0", "1"])
 def test_binary_dump_and_correctness_flags(emd, tmp_path, no_tiles):
     """the ExaMiniMD executable with the reference's own record/replay flags (README.md:99-107); once on the
