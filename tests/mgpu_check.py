@@ -52,7 +52,10 @@ def parity(kind, nx, ny, nz, steps, iteration="NEIGH_HALF", group=None, device=N
     start = app.download()
     gathered0 = [None] * world
     dist.gather_object({k: start[k] for k in ("id", "x")}, gathered0 if rank == 0 else None, dst=0, group=group)
-    app.advance(steps)
+    if os.environ.get("EMD_MGPU_USE_RUN"):  # the reference's loop (thermo at the deck's cadence: thermo steps served by the fused force launch)
+        app.run(steps)
+    else:
+        app.advance(steps)
     cur = app.download()
     T, PE, KE = app.thermo()
     gathered = [None] * world

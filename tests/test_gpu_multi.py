@@ -32,10 +32,11 @@ def test_decomposed_run_matches_single_rank_oracle(emd, oracle_lib, n, args):
     run(n, *args, port=29701 + n)
 
 
-@pytest.mark.parametrize("env", [{"EMD_HALO_GATE": "1"}, {"EMD_HALO_TRANSPORT": "nccl"}, {"EMD_NO_OVERLAP": "1"}])
+@pytest.mark.parametrize("env", [{"EMD_HALO_GATE": "1"}, {"EMD_HALO_TRANSPORT": "nccl"}, {"EMD_NO_OVERLAP": "1"}, {"EMD_MGPU_USE_RUN": "1"}])
 def test_decomposed_run_other_halo_schedules(emd, oracle_lib, env):
     """the same parity bar for the schedules that are not the default: the force kernel waiting for the neighbours' arrival flags
-    itself (halo gate), NCCL send/recv groups instead of peer stores, and the blocking (not overlapped) refresh"""
+    itself (halo gate), NCCL send/recv groups instead of peer stores, the blocking (not overlapped) refresh, and the reference's
+    run loop (thermo steps served by the fused force + integrator launch of a decomposed run)"""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
     run(2, "lj", 12, 14, 14, 45, "half", port=29731, extra_env=env)
